@@ -1,0 +1,105 @@
+/* wiflow_b200 -- C ABI of the B200-native WiFlow hot path (libwiflow_b200.so).
+ *
+ * The reference (DY2434/WiFlow-...) is pure Python: its "operator interface" for this path is the nn.Module /
+ * function API that train.py consumes.  Each entry point below names the reference interface it replaces; the
+ * Python package in this repo binds them with ctypes (see INTEGRATION.md for the stub a reference maintainer adds).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to fp32 data unless stated otherwise; all buffers are owned by the caller;
+ *    the library allocates nothing and keeps no mutable global state (it is re-entrant across streams/threads);
+ *  - work is only enqueued on `stream`; no call synchronises, so every call is CUDA-graph capturable;
+ *  - return value: 0 ok, <0 argument error (WF_E_*), >0 a cudaError_t; wf_last_error_string() describes the last
+ *    failure on the calling thread.  There is no CPU fallback: without an sm_100a device the calls fail.
+ *  - parameters are ONE flat fp32 buffer in the reference's state_dict()/named_parameters() order
+ *    (2 225 042 floats for the full model); gradients use the same layout;
+ *    BatchNorm running statistics are one flat buffer [running_mean(C), running_var(C)] per BatchNorm in module
+ *    order, num_batches_tracked one int64 per BatchNorm.  wf_*_param_count / wf_param_table describe the layout.
+ */
+#ifndef WIFLOW_B200_H
+#define WIFLOW_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* wf_stream_t;              /* cudaStream_t */
+#if defined(__GNUC__)
+#define WF_API __attribute__((visibility("default")))
+#else
+#define WF_API
+#endif
+
+enum { WF_E_ARG = -1, WF_E_WORKSPACE = -2, WF_E_ARCH = -3, WF_E_UNSUPPORTED = -4 };
+enum { WF_FLAG_TRAIN = 1,               /* BatchNorm uses batch statistics and updates the running buffers */
+       WF_FLAG_SAVE_FOR_BACKWARD = 2 }; /* keep activations in the workspace for wf_*_backward */
+/* block ids for the per-block entry points (sub-module drop-ins) */
+enum { WF_BLOCK_MODEL = 0,              /* models/pose_model.py:9  WiFlowPoseModel            [B,540,20] -> [B,15,2]      */
+       WF_BLOCK_TCN = 1,                /* models/tcn.py:76        TemporalBlock              [B,540,20] -> [B,240,20]    */
+       WF_BLOCK_CONVBLOCK1 = 2,         /* models/convnet.py:41    ConvBlock1(cin,cout)       [B,cin,20,W] -> [B,cout,20,W]   */
+       WF_BLOCK_ASYMCONV = 3,           /* models/convnet.py:4     AsymmetricConvBlock        [B,cin,20,W] -> [B,cout,20,W/2] */
+       WF_BLOCK_AXIAL_W = 4,            /* models/attention.py:7   AxialAttention(width=True) [B,64,15,20]                 */
+       WF_BLOCK_AXIAL_H = 5,            /* models/attention.py:7   AxialAttention(width=False)                             */
+       WF_BLOCK_DUAL_AXIAL = 6,         /* models/attention.py:83  DualAxialAttention                                      */
+       WF_BLOCK_INNER_TCN = 7 };        /* models/tcn.py:14        InnerGroupedTemporalBlock(cin,cout,dilation)            */
+enum { WF_LOSS_TYPE_SMOOTH_L1 = 0, WF_LOSS_TYPE_MSE = 1, WF_LOSS_TYPE_L1 = 2 };
+
+/* Block geometry for the per-block entry points (ignored fields may be 0). */
+typedef struct wf_block_desc {
+    int block;          /* WF_BLOCK_* */
+    int cin, cout;      /* conv blocks / inner TCN block */
+    int width;          /* conv blocks: input feature-axis length W (240, 120, ...) */
+    int dilation;       /* inner TCN block */
+} wf_block_desc;
+
+WF_API const char* wf_last_error_string(void);
+WF_API int wf_version(void);
+
+/* ---- layout queries (host only) ---- */
+WF_API long long wf_param_count(const wf_block_desc* d);     /* floats in the flat parameter buffer            */
+WF_API long long wf_running_count(const wf_block_desc* d);   /* floats in the flat running-statistics buffer   */
+WF_API int wf_bn_count(const wf_block_desc* d);              /* number of BatchNorm layers (num_batches_tracked entries) */
+WF_API int wf_dropout_sites(const wf_block_desc* d);         /* number of dropout masks the block consumes in train mode */
+/* i-th parameter tensor in state_dict order: name (relative to the block), offset and element count. returns 0, or WF_E_ARG past the end */
+WF_API int wf_param_table(const wf_block_desc* d, int i, char* name, int name_cap, long long* offset, long long* numel);
+WF_API size_t wf_workspace_bytes(const wf_block_desc* d, int B, int flags);
+
+/* ---- forward / backward of a block (replaces nn.Module.forward + autograd of the reference classes above) ----
+ * x, y, dy, dx use the reference's tensor layouts (contiguous).  masks: NULL (no dropout) or wf_dropout_sites()
+ * device pointers to multiplicative masks (0 or 1/(1-p)) in the reference's call order: nn.Dropout sites are
+ * [B,C,20] tensors (tcn.py:30,43), nn.Dropout2d sites are [B,C] (convnet.py:15,20,51,56).
+ * wf_block_backward needs the workspace of the matching forward (WF_FLAG_TRAIN|WF_FLAG_SAVE_FOR_BACKWARD) untouched,
+ * writes d loss/d params into `grads` (overwritten, same flat layout) and, if dx != NULL, d loss/d x. */
+WF_API int wf_block_forward(const wf_block_desc* d, const float* x, const float* params, float* running, long long* num_batches_tracked,
+                     const float* const* masks, float* y, void* workspace, size_t workspace_bytes, int B, int flags, wf_stream_t stream);
+WF_API int wf_block_backward(const wf_block_desc* d, const float* x, const float* params, const float* const* masks, const float* dy,
+                      float* grads, float* dx, void* workspace, size_t workspace_bytes, int B, int flags, wf_stream_t stream);
+
+/* ---- losses/pose_loss.py:35-88 PoseLoss.forward (+ its autograd) ----
+ * out3 = {total, position, bone}; dpred (may be NULL) = gscale * d total / d pred, gscale a device scalar or NULL (=1).
+ * scratch: 2 doubles, zero on first use (re-zeroed by the call). */
+WF_API int wf_pose_loss(const float* pred, const float* target, int B, int loss_type, float position_weight, float bone_weight,
+                 const float* gscale, float* dpred, float* out3, double* scratch, wf_stream_t stream);
+
+/* ---- utils/metrics.py:3-47 calculate_pck + calculate_mpjpe ----
+ * out = {pck[0..nthr-1], mpjpe}; thresholds are HOST floats (nthr <= 8).
+ * scratch: 16 eight-byte words, zero on first use (re-zeroed by the call). */
+WF_API int wf_pose_metrics(const float* pred, const float* target, int B, const float* thresholds, int nthr, int use_torso_norm,
+                    float* out, void* scratch, wf_stream_t stream);
+
+/* ---- train.py:105-110,235-236 clip_grad_norm_(max_norm) + torch.optim.AdamW.step over flat buffers ----
+ * grads are multiplied by grad_scale first (1/world_size after a sum-allreduce).  state: 64 bytes, zero before the
+ * first step (holds the step counter); after the call state[+16] (float) is the pre-clip gradient norm. */
+WF_API int wf_clip_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, void* state,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
+                  wf_stream_t stream);
+
+/* ---- test / debug introspection (not part of the reference-facing surface) ----
+ * i-th named fp32 workspace tensor ([C][P][B*20], n = b*20+t contiguous) of the block's layout: byte offset into the workspace. */
+WF_API int wf_debug_tensor(const wf_block_desc* d, int B, int flags, int i, char* name, int name_cap, long long* byte_offset, int* C, int* P);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

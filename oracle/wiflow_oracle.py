@@ -165,7 +165,7 @@ def _tcn_block(c, x, i):
     cin, cout = TCN_CHANNELS[i], TCN_CHANNELS[i + 1]
     if cin != cout:
         r = c.note(f'{p}.ds.raw', F.conv1d(x, w[p + '.downsample.0.weight']))
-        res = c.bn(r, p + '.downsample.1')
+        res = c.note(f'{p}.ds.y', c.bn(r, p + '.downsample.1'))
     else:
         res = x
 
@@ -188,13 +188,13 @@ def _conv_block(c, x, p, stride):
     """ConvBlock1.forward / AsymmetricConvBlock.forward (models/convnet.py:33-38,69-74)."""
     w = c.s
     r = c.note(f'{p}.ds.raw', F.conv2d(x, w[p + '.downsample.0.weight'], stride=(1, stride)))
-    identity = c.bn(r, p + '.downsample.1')
+    identity = c.note(f'{p}.ds.y', c.bn(r, p + '.downsample.1'))
     o = c.note(f'{p}.c1.raw', F.conv2d(x, w[p + '.block.0.weight'], w[p + '.block.0.bias'], stride=(1, stride), padding=(0, 1)))
     o = c.drop(F.silu(c.note(f'{p}.c1.y', c.bn(o, p + '.block.1'))))
     o = c.note(f'{p}.c2.raw', F.conv2d(o, w[p + '.block.4.weight'], w[p + '.block.4.bias'], padding=(0, 1)))
     o = c.drop(F.silu(c.note(f'{p}.c2.y', c.bn(o, p + '.block.5'))))
     o = c.note(f'{p}.c3.raw', F.conv2d(o, w[p + '.block.8.weight'], w[p + '.block.8.bias'], padding=(0, 1)))
-    o = c.bn(o, p + '.block.9')
+    o = c.note(f'{p}.c3.y', c.bn(o, p + '.block.9'))
     return c.note(f'{p}.out', F.silu(o + identity))
 
 

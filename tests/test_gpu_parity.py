@@ -1,0 +1,271 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every test drives the hand-written kernels through the
+C ABI (ctypes -> libwiflow_b200.so) and checks them against the CPU oracle / the golden fixtures of the reference.
+
+Tolerances (BASELINE.json north_star): fp32 outputs within 1e-4 max-norm relative; PCK/MPJPE equal to 4 decimals;
+gradients within max(2 x the reference's own fp32-vs-fp64 error, 1e-4 * |g|_inf) of the fp64 truth."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import wiflow_oracle as O
+from tests.util import golden_masks, is_dead, load_golden, oracle_key, rel_err, sample, to_internal
+from tests.test_oracle import check_post_step
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope='module')
+def wf():
+    import wiflow_b200
+    return wiflow_b200
+
+
+@pytest.fixture(scope='module')
+def golden():
+    return load_golden()
+
+
+def make_model(wf, seed=0, dropout=0.5):
+    torch.manual_seed(seed)
+    return wf.WiFlowPoseModel(dropout=dropout).cuda()
+
+
+def oracle_state_from(model, dtype=torch.float32):
+    return {k: (v.detach().cpu().to(dtype) if v.is_floating_point() else v.detach().cpu().clone()) for k, v in model.state_dict().items()}
+
+
+def test_library_is_native(wf):
+    from wiflow_b200 import _lib
+    assert _lib.lib().wf_version() >= 100
+    assert torch.cuda.get_device_capability()[0] == 10, 'these kernels are built for sm_100a only'
+
+
+@pytest.mark.parametrize('B', [1, 2, 3, 64, 65])
+def test_eval_forward_vs_oracle(wf, B):
+    model = make_model(wf).eval()
+    st = oracle_state_from(model)
+    # give the running statistics non-trivial values so eval-mode BatchNorm is exercised
+    g = torch.Generator().manual_seed(1)
+    for k in st:
+        if k.endswith('running_mean'):
+            st[k] = torch.randn(st[k].shape, generator=g) * 0.1
+        elif k.endswith('running_var'):
+            st[k] = torch.rand(st[k].shape, generator=g) + 0.5
+    model.load_state_dict(st)
+    x, _ = O.synthetic_batch(B, seed=B)
+    with torch.no_grad():
+        out = model(x.cuda())
+    ref = O.forward(st, x)
+    assert out.shape == (B, 15, 2)
+    assert rel_err(out.cpu(), ref) < TOL
+
+
+def test_eval_matches_reference_fixture(wf, golden):
+    model = make_model(wf).eval()
+    x = torch.from_numpy(golden['x']).cuda()
+    with torch.no_grad():
+        out = model(x)
+    assert rel_err(out.cpu(), torch.from_numpy(golden['f32.eval_pred'])) < TOL
+    assert rel_err(out.cpu(), torch.from_numpy(golden['f64.eval_pred'])) < TOL
+
+
+def _run_lib_train(wf, model, x, y, masks):
+    """forward + loss + backward through the raw ops with an inspectable workspace"""
+    from wiflow_b200 import _lib, ops
+    desc = [0, 0, 0, 0, 0]
+    B = x.shape[0]
+    flags = _lib.FLAG_TRAIN | _lib.FLAG_SAVE
+    flat, running, nbt = model._wf_state()
+    ws = torch.zeros(ops.workspace_bytes(desc, B, flags), device='cuda', dtype=torch.uint8)
+    lm = [m.cuda().reshape(m.shape[0], m.shape[1], -1).squeeze(-1).contiguous() if m.dim() == 4 else m.cuda().contiguous() for m in masks] if masks else []
+    pred = ops.block_forward(x, flat, running, nbt, lm, desc, flags, ws)
+    scratch = torch.zeros(2, device='cuda', dtype=torch.float64)
+    out3, dpred = ops.pose_loss(pred, y, 0, 1.0, 0.2, scratch, True)
+    grads, _ = ops.block_backward(x, flat, lm, dpred, desc, flags, ws, False)
+    torch.cuda.synchronize()
+    return pred, out3, dpred, grads, ws, flags
+
+
+@pytest.mark.parametrize('use_masks', [False, True])
+def test_train_intermediates_vs_oracle(wf, golden, use_masks):
+    """every saved activation and every activation gradient of the chained kernels against the fp64 oracle's autograd --
+    localises a wrong kernel to its layer"""
+    from wiflow_b200 import _lib
+    B = 4
+    model = make_model(wf).train()
+    st64 = oracle_state_from(model, torch.float64)
+    x, y = torch.from_numpy(golden['x']), torch.from_numpy(golden['y'])
+    masks = golden_masks(golden) if use_masks else None
+    rec = {}
+    O.grads(st64, x.double(), y.double(), masks=[m.double() for m in masks] if masks else None, record=rec)
+    pred, out3, dpred, grads, ws, flags = _run_lib_train(wf, model, x.cuda(), y.cuda(), masks)
+    dbg = _lib.debug_tensors(_lib.BlockDesc(0, 0, 0, 0, 0), B, flags)
+    report, worst = [], 0.0
+    for name, (off, C, P) in dbg.items():
+        if name.endswith('.coef') or off < 0:
+            continue
+        if name.endswith('downsample.0.dy') and not name.startswith('tcn.'):
+            continue                                  # conv-block shortcut shares dz with block.8
+        key, want_grad = oracle_key(name)
+        if key not in rec:
+            continue
+        t = rec[key].grad if want_grad else rec[key]
+        ref = to_internal(key, t.detach(), B).contiguous()
+        got = ws[off:off + C * P * B * 20 * 4].view(torch.float32).view(C, P, B, 20).cpu()
+        e = rel_err(got, ref)
+        worst = max(worst, e)
+        report.append(f'{e:9.2e}  {name}')
+    text = '\n'.join(report)
+    import os
+    os.makedirs('gpurun_out', exist_ok=True)
+    with open(f'gpurun_out/intermediates_masks{int(use_masks)}.txt', 'w') as f:
+        f.write(text + '\n')
+    assert rel_err(pred.cpu(), rec['pred'].detach()) < TOL, text
+    bad = [l for l in report if float(l.split()[0]) > 2e-3]
+    assert not bad, 'layers off by more than 2e-3:\n' + '\n'.join(bad)
+
+
+@pytest.mark.parametrize('tag,use_masks', [('nodrop_f32', False), ('f32', True)])
+def test_train_step_matches_reference_fixture(wf, golden, tag, use_masks):
+    model = make_model(wf).train()
+    x, y = torch.from_numpy(golden['x']).cuda(), torch.from_numpy(golden['y']).cuda()
+    masks = golden_masks(golden) if use_masks else None
+    pred, out3, dpred, grads, ws, flags = _run_lib_train(wf, model, x, y, masks)
+    tag64 = tag.replace('f32', 'f64')
+    assert rel_err(pred.cpu(), torch.from_numpy(golden[f'{tag64}.train_pred'])) < TOL
+    np.testing.assert_allclose(out3.cpu().numpy(), golden[f'{tag}.loss'], rtol=1e-4)
+    # metrics equal to 4 decimals
+    pck = wf.calculate_pck(pred, y, [0.1, 0.2, 0.3, 0.4, 0.5])
+    np.testing.assert_allclose(np.array(list(pck.values())), golden[f'{tag}.pck'], atol=5e-5)
+    np.testing.assert_allclose(np.array(list(wf.calculate_pck(pred, y, [0.2, 0.5], use_torso_norm=False).values())),
+                               golden[f'{tag}.pck_shoulder'], atol=5e-5)
+    assert abs(wf.calculate_mpjpe(pred, y) - golden[f'{tag}.mpjpe'][0]) < 5e-5
+    # running statistics after one train-mode forward
+    _, running, nbt = model._wf_state()
+    assert rel_err(running.cpu(), torch.from_numpy(golden[f'{tag}.running'])) < TOL
+    assert (nbt == 1).all()
+    # gradients against the fp64 reference run
+    stride = int(golden['meta'][3])
+    g64, g32 = golden[f'{tag64}.grad_samples'], golden[f'{tag}.grad_samples']
+    off, goff, fails = 0, 0, []
+    for i, (n, p) in enumerate(model.named_parameters()):
+        g = grads[goff:goff + p.numel()]
+        goff += p.numel()
+        s = sample(g, stride).double().cpu().numpy()
+        t64, t32 = g64[off:off + s.size], g32[off:off + s.size]
+        off += s.size
+        if is_dead(n):
+            assert np.abs(s).max() <= 1e-5 * max(1.0, golden[f'{tag64}.grad_absmax'].max()), n   # noise-level, like the reference's
+            continue
+        scale = golden[f'{tag64}.grad_absmax'][i]
+        err_ref, err = np.abs(t32 - t64).max(), np.abs(s - t64).max()
+        if err > max(2 * err_ref, TOL * scale) + 1e-12:
+            fails.append((n, err, err_ref, scale))
+    assert not fails, fails
+    # fused clip + AdamW on the flat buffers
+    from wiflow_b200 import ops
+    flat, _, _ = model._wf_state()
+    m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+    state = torch.zeros(8, device='cuda', dtype=torch.float64)
+    ops.clip_adamw(flat, grads, m, v, state, 1e-4, 0.9, 0.999, 1e-8, 5e-5, 1.0, 1.0)
+    torch.cuda.synchronize()
+    gn = state.view(torch.float32)[4].item()
+    assert abs(gn - golden[f'{tag64}.total_norm'][0]) / gn < 1e-3
+    check_post_step(golden, tag, dict(model.named_parameters()), stride)
+
+
+def test_autograd_path_equals_raw_ops(wf, golden):
+    """the nn.Module / autograd.Function surface gives the same numbers as the raw op sequence"""
+    model = make_model(wf, dropout=0.0).train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout2d):
+            m.p = 0.0
+    x, y = torch.from_numpy(golden['x']).cuda(), torch.from_numpy(golden['y']).cuda()
+    sd = copy.deepcopy(model.state_dict())
+    pred, out3, dpred, grads, ws, flags = _run_lib_train(wf, model, x, y, None)
+    model.load_state_dict(sd)
+    crit = wf.PoseLoss()
+    out = model(x)
+    loss, ld = crit(out, y)
+    loss.backward()
+    assert torch.equal(out.detach(), pred)
+    assert abs(loss.item() - out3[0].item()) < 1e-7 and abs(ld['position'] - out3[1].item()) < 1e-7
+    flat_g = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    assert rel_err(flat_g, grads) < 1e-5           # wgrad uses fp32 atomics: summation order may differ run to run
+    assert abs(ld['bone'] - golden['nodrop_f32.loss'][2]) < 1e-4
+
+
+@pytest.mark.parametrize('loss_type', ['smooth_l1', 'mse', 'l1'])
+def test_pose_loss_kernel(wf, loss_type):
+    g = torch.Generator().manual_seed(5)
+    for B in (1, 7, 300):
+        p = torch.rand(B, 15, 2, generator=g)
+        t = torch.rand(B, 15, 2, generator=g)
+        p[0, 3] = t[0, 3] + 0.01            # inside the quadratic zone of smooth-L1
+        pd = p.double().requires_grad_(True)
+        total, pos, bone = O.pose_loss(pd, t.double(), loss_type=loss_type)
+        total.backward()
+        crit = wf.PoseLoss(loss_type=loss_type)
+        pc = p.cuda().requires_grad_(True)
+        lt, ld = crit(pc, t.cuda())
+        (lt * 3.0).backward()
+        assert abs(lt.item() - total.item()) < 1e-5 * max(1, abs(total.item()))
+        assert abs(ld['position'] - pos.item()) < 1e-5 and abs(ld['bone'] - bone.item()) < 1e-5
+        assert rel_err(pc.grad.cpu(), 3.0 * pd.grad) < 1e-4
+        lt2, _ = crit(p.cuda().reshape(B, 30), t.cuda().reshape(B, 30))        # flat [B,30] inputs (pose_loss.py:47-51)
+        assert lt2.item() == lt.item()
+    with pytest.raises(ValueError):
+        wf.PoseLoss(loss_type='huber')(p.cuda(), t.cuda())
+
+
+def test_metrics_kernel(wf):
+    g = torch.Generator().manual_seed(9)
+    for B in (1, 5, 1000):
+        p = torch.rand(B, 15, 2, generator=g)
+        t = torch.rand(B, 15, 2, generator=g)
+        t[0, 12] = t[0, 2]                     # zero torso length -> clamp(min=0.01) branch (metrics.py:23)
+        thr = [0.1, 0.2, 0.3, 0.4, 0.5]
+        for torso in (True, False):
+            ref = O.pck(p, t, thr, use_torso_norm=torso)
+            got = wf.calculate_pck(p.cuda(), t.cuda(), thr, use_torso_norm=torso)
+            assert list(got.keys()) == thr
+            for k in thr:
+                assert round(got[k], 4) == round(ref[k], 4)
+        assert round(wf.calculate_mpjpe(p.cuda(), t.cuda()), 4) == round(O.mpjpe(p, t), 4)
+        assert wf.calculate_pck(p.cuda().reshape(B, 30), t.cuda().reshape(B, 30))[0.2] == wf.calculate_pck(p.cuda(), t.cuda())[0.2]
+    many = [i / 20 for i in range(1, 12)]      # more thresholds than one launch takes
+    ref = O.pck(p, t, many)
+    got = wf.calculate_pck(p.cuda(), t.cuda(), many)
+    assert all(round(got[k], 4) == round(ref[k], 4) for k in many)
+
+
+def test_batch_permutation_equivariance_full_size(wf):
+    """size-independent property at the benchmark batch: permuting the windows permutes the outputs, in eval mode and
+    (BatchNorm statistics being permutation invariant) in train mode"""
+    B = 1024
+    model = make_model(wf, dropout=0.0)
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout2d):
+            m.p = 0.0
+    x, _ = O.synthetic_batch(B, seed=2)
+    x = x.cuda()
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(0)).cuda()
+    with torch.no_grad():
+        model.eval()
+        a, b = model(x), model(x[perm])
+        assert torch.isfinite(a).all()
+        assert rel_err(b, a[perm]) < 1e-5
+        model.train()
+        a, b = model(x), model(x[perm])
+        assert rel_err(b, a[perm]) < 1e-4
+
+
+def test_cpu_tensors_are_rejected(wf):
+    model = make_model(wf)
+    with pytest.raises(RuntimeError):
+        model(torch.randn(2, 540, 20))
+    with pytest.raises(RuntimeError):
+        model(torch.randn(2, 540, 21).cuda())

@@ -1,0 +1,45 @@
+"""Build libwiflow_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels to the GPU box with the repo)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+SOURCES = ['wf_conv.cu', 'wf_elem.cu', 'wf_attn.cu', 'wf_model.cu']
+LIB = os.path.join(HERE, 'libwiflow_b200.so')
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+              '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']
+
+
+def _newer(a, b):
+    return not os.path.exists(b) or os.path.getmtime(a) > os.path.getmtime(b)
+
+
+def build(force=False, verbose=False):
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))]
+    headers.append(os.path.join(HERE, '..', 'include', 'wiflow_b200.h'))
+    objs, procs = [], []
+    for src in SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(CSRC, src.replace('.cu', '.o'))
+        objs.append(o)
+        if force or any(_newer(d, o) for d in headers + [s]):
+            cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', s, '-o', o]
+            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = []
+    for src, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            sys.stderr.write(out)
+        if p.returncode:
+            failed.append(src)
+    if failed:
+        raise RuntimeError(f'nvcc failed on {failed}')
+    if force or procs or not os.path.exists(LIB):
+        subprocess.check_call([nvcc, '-shared', '-o', LIB] + objs + ['-Xcompiler', '-fPIC', '-lcudart'])
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

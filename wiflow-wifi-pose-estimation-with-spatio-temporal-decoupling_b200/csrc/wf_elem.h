@@ -1,0 +1,93 @@
+// Parameter structs + launcher prototypes shared between the kernel translation units and the host plan.
+#pragma once
+#include <cuda_runtime.h>
+#include "wf_common.cuh"
+
+#define WF_MAX_THR 8
+#define WF_MAX_BN 48
+#define WF_MAX_CONV 48
+enum { WF_LOSS_SMOOTH_L1 = 0, WF_LOSS_MSE = 1, WF_LOSS_L1 = 2 };
+
+struct BnFwdFin {
+    int C; double count;
+    const double *s0, *s1;
+    const float *gamma, *beta;
+    float *scale, *shift, *mean, *rstd;
+    float *run_mean, *run_var;          // nullptr: do not touch running statistics
+    long long* nbt;
+};
+struct BnBwdFin {
+    int C; double count;
+    const double *s0, *s1;              // sum dy, sum dy*raw
+    const float *gamma, *mean, *rstd;
+    float *dgamma, *dbeta;              // may be nullptr
+    float *alpha, *beta_c, *delta;
+};
+struct BnEvalEntry { int C, Cpad, gamma_off, run_off, coef_off; };
+struct BnEvalTable { int n; BnEvalEntry e[WF_MAX_BN]; };
+
+struct JoinP {
+    const float *a, *r;
+    float* out;
+    const float* dout; float *dz, *da;
+    long long plane; int N, C;
+    int a_mode; const float *a_scale, *a_shift;
+    const float* mask; long long m_sb, m_sc; int m_st;
+    int r_mode; const float *r_scale, *r_shift;
+    long long r_sc, r_sp, r_sb;
+    double *a_stat0, *a_stat1, *r_stat0, *r_stat1;
+};
+
+struct MetricThr { int n; float v[WF_MAX_THR]; };
+
+struct PackEntry { int param_off, cout, cin, groups, ntaps, f_kpad, f_mpad, b_kpad, b_mpad; long long fwd_off, bwd_off; };
+struct PackTable { int n; PackEntry e[WF_MAX_CONV]; };
+
+struct AdamState { double sumsq; long long step; float grad_norm, clip_coef, step_size, inv_bc2_sqrt; };
+
+// attention (wf_attn.cu)
+struct AttnP {
+    int width;                    // 1: sequences along time (L=20), rows=(h,b); 0: along slots (L=15), rows=n
+    int B, N;                     // N = B*20
+    const float* qkv_raw;         // [192][15][N]
+    const float *qkv_scale, *qkv_shift;            // bn_qkv affine (192)
+    const float *sim_scale, *sim_shift;            // bn_similarity affine (8)
+    double *sim_s0, *sim_s1;                       // stats pass output
+    float* sv_raw;                // [64][15][N]
+    double *sv_s0, *sv_s1;
+    // backward
+    const float *dsv, *sv_alpha, *sv_beta, *sv_delta;   // dy of bn_output + its BN-backward affine (64)
+    const float *sim_alpha, *sim_beta, *sim_delta;      // BN-backward affine of bn_similarity (8)
+    double *dsim_s0, *dsim_s1;
+    float* dqkv;                  // [192][15][N]  dy of bn_qkv
+};
+
+cudaError_t wf_launch_conv(const ConvP& p, cudaStream_t st);
+cudaError_t wf_launch_wgrad(const WgradP& p, int num_sms, cudaStream_t st);
+int wf_conv_bm_for(int M);
+int wf_conv_bk_for(int M);
+
+cudaError_t wf_launch_bn_fwd_fin(const BnFwdFin* d, int n, cudaStream_t st);
+cudaError_t wf_launch_bn_bwd_fin(const BnBwdFin* d, int n, cudaStream_t st);
+cudaError_t wf_launch_bn_eval_coefs(const BnEvalTable& tab, const float* params, const float* running, float* coefs, cudaStream_t st);
+cudaError_t wf_launch_join_fwd(const JoinP& p, int num_sms, cudaStream_t st);
+cudaError_t wf_launch_join_bwd(const JoinP& p, int num_sms, cudaStream_t st);
+cudaError_t wf_launch_bn_bwd_stats(const float* dy, const float* raw, int C, long long plane, double* s0, double* s1, int num_sms, cudaStream_t st);
+cudaError_t wf_launch_pool_fwd(const float* raw, const float* scale, const float* shift, float* pred, int B, cudaStream_t st);
+cudaError_t wf_launch_pool_bwd(const float* raw, const float* scale, const float* shift, const float* dpred, float* dy, int B,
+                               double* s0, double* s1, cudaStream_t st);
+cudaError_t wf_launch_pose_loss(const float* pred, const float* target, int B, int type, float pw, float bw, const float* gscale,
+                                float* dpred, double* acc2, float* out3, cudaStream_t st);
+cudaError_t wf_launch_metrics(const float* pred, const float* target, int B, const MetricThr& thr, int torso, unsigned long long* counts,
+                              double* dsum, float* out, cudaStream_t st);
+cudaError_t wf_launch_pack(const PackTable& tab, const float* params, float* packed, cudaStream_t st);
+cudaError_t wf_launch_adamw(float* p, const float* g, float* m, float* v, long long n, AdamState* state, float lr, float b1, float b2,
+                            float eps, float wd, float max_norm, float grad_scale, int num_sms, cudaStream_t st);
+cudaError_t wf_launch_permute(const float* src, float* dst, int C, int P, int B, long long r_sb, long long r_sc, long long r_sp,
+                              long long r_st, int to_internal, int num_sms, cudaStream_t st);
+cudaError_t wf_launch_permute_affine(const float* src, float* dst, int C, int P, int B, long long r_sb, long long r_sc, long long r_sp,
+                                     long long r_st, const float* scale, const float* shift, int num_sms, cudaStream_t st);
+cudaError_t wf_launch_attn_fwd_stats(const AttnP& p, cudaStream_t st);
+cudaError_t wf_launch_attn_fwd(const AttnP& p, cudaStream_t st);
+cudaError_t wf_launch_attn_bwd_stats(const AttnP& p, cudaStream_t st);
+cudaError_t wf_launch_attn_bwd(const AttnP& p, cudaStream_t st);

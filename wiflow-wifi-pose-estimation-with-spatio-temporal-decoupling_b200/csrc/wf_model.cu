@@ -1,0 +1,974 @@
+// Host side of libwiflow_b200.so: network description, flat parameter / workspace layout, forward and backward
+// schedules (one kernel per conv layer, split at every BatchNorm because train-mode BatchNorm is a batch-wide
+// reduction -- DESIGN.md "Why split at BatchNorm"), and the extern "C" entry points of include/wiflow_b200.h.
+//
+// Reference structure being restated (never copied): models/pose_model.py:12-97, models/tcn.py:14-97,
+// models/convnet.py:4-74, models/attention.py:7-98.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/wiflow_b200.h"
+#include "wf_elem.h"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+constexpr int T = WF_T;
+constexpr int EVAL_CHUNK = 1024;
+
+struct ParamEntry { std::string name; long long off, numel; };
+
+struct BnUnit {
+    int C, Cpad;
+    long long gamma_off;      // beta at gamma_off + C
+    long long run_off;        // running_mean at run_off, running_var at run_off + C
+    double count_per_b;       // elements per channel = count_per_b * B
+    // workspace
+    double *f0, *f1, *b0, *b1;
+    float* coef;              // 8 * Cpad: scale, shift, mean, rstd, alpha, beta, delta, (spare)
+    float* scale() const { return coef; }
+    float* shift() const { return coef + Cpad; }
+    float* mean() const { return coef + 2 * Cpad; }
+    float* rstd() const { return coef + 3 * Cpad; }
+    float* alpha() const { return coef + 4 * Cpad; }
+    float* betac() const { return coef + 5 * Cpad; }
+    float* delta() const { return coef + 6 * Cpad; }
+};
+
+struct ConvUnit {
+    std::string name;
+    long long w_off, b_off;   // b_off < 0: no bias
+    int cin_g, cout_g, groups, ntaps;
+    int pin, pout, stride;
+    int dpf[WF_MAX_TAPS], dnf[WF_MAX_TAPS];
+    int bn;
+    int f_kpad, f_mpad, b_kpad, b_mpad;
+    long long fpack, bpack;   // float offsets into the packed-weight region
+    float *raw, *dy;          // [groups*cout_g][pout][N]
+    long long numel_per_n() const { return (long long)groups * cout_g * pout; }
+};
+
+struct TcnBlk { std::string name; int g1, pw1, g2, pw2, ds; int cin, cout, dil; float *X, *dX, *dz; int mask0; };
+struct CvBlk { std::string name; int c1, c2, c3, ds; int cin, cout, win, wout; float *Y, *dY; int mask0; };
+struct AxBlk { std::string name; int qkv; int bn_sim, bn_out; int width; float *sv_raw, *dsv; };
+struct DecBlk { int d1, d2; };
+
+struct DebugEntry { std::string name; const float* p; int C, P; };
+
+struct Net {
+    std::vector<DebugEntry> dbg;
+    std::vector<ParamEntry> params;
+    std::vector<BnUnit> bn;
+    std::vector<ConvUnit> conv;
+    std::vector<TcnBlk> tcn;
+    std::vector<CvBlk> cv;
+    std::vector<AxBlk> ax;
+    bool has_dec = false;
+    DecBlk dec{};
+    long long nparams = 0, nrunning = 0;
+    int nmask = 0;
+    // boundary tensors (internal layout) for blocks whose reference layout needs a permute
+    int in_C = 0, in_P = 0, out_C = 0, out_P = 0;
+    bool in_is_ref_bct = false;   // input is read in place as [B][C][20] (TCN family)
+    float *in_buf = nullptr, *din_buf = nullptr, *out_buf = nullptr, *dout_buf = nullptr;
+    // workspace regions
+    float* packed = nullptr; long long packed_floats = 0;
+    char* fstats = nullptr; size_t fstats_bytes = 0;
+    char* bstats = nullptr; size_t bstats_bytes = 0;
+    float* dpred_buf = nullptr;
+};
+
+long long add_param(Net& n, const std::string& name, long long numel)
+{
+    n.params.push_back({name, n.nparams, numel});
+    long long o = n.nparams;
+    n.nparams += numel;
+    return o;
+}
+int add_bn(Net& n, const std::string& name, int C, double count_per_b)
+{
+    BnUnit b{};
+    b.C = C; b.Cpad = (C + 3) / 4 * 4;
+    b.gamma_off = add_param(n, name + ".weight", C);
+    add_param(n, name + ".bias", C);
+    b.run_off = n.nrunning;
+    n.nrunning += 2 * C;
+    b.count_per_b = count_per_b;
+    n.bn.push_back(b);
+    return (int)n.bn.size() - 1;
+}
+int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+int add_conv(Net& n, const std::string& name, int cout_total, int cin_g, int groups, int ntaps, bool bias, int pin, int pout, int stride,
+             const int* dpf, const int* dnf)
+{
+    ConvUnit c{};
+    c.name = name;
+    c.w_off = add_param(n, name + ".weight", (long long)cout_total * cin_g * ntaps);
+    c.b_off = bias ? add_param(n, name + ".bias", cout_total) : -1;
+    c.cin_g = cin_g; c.cout_g = cout_total / groups; c.groups = groups; c.ntaps = ntaps;
+    c.pin = pin; c.pout = pout; c.stride = stride;
+    for (int t = 0; t < ntaps; ++t) { c.dpf[t] = dpf ? dpf[t] : 0; c.dnf[t] = dnf ? dnf[t] : 0; }
+    c.bn = -1;
+    c.f_kpad = round_up(cin_g, wf_conv_bk_for(c.cout_g));
+    c.f_mpad = round_up(c.cout_g, wf_conv_bm_for(c.cout_g));
+    c.b_kpad = round_up(c.cout_g, wf_conv_bk_for(cin_g));
+    c.b_mpad = round_up(cin_g, wf_conv_bm_for(cin_g));
+    n.conv.push_back(c);
+    return (int)n.conv.size() - 1;
+}
+
+// InnerGroupedTemporalBlock (models/tcn.py:14-74); count per channel = 20*B
+void add_tcn_block(Net& n, const std::string& pfx, int cin, int cout, int dil)
+{
+    TcnBlk b{};
+    b.name = pfx;
+    b.cin = cin; b.cout = cout; b.dil = dil;
+    int dn[3] = {-2 * dil, -dil, 0};               // tap k reads t - (2-k)*dil  (causal: left padding + Chomp1d)
+    b.g1 = add_conv(n, pfx + "conv1_group", cin, cin / 20, 20, 3, false, 1, 1, 1, nullptr, dn);
+    n.conv[b.g1].bn = add_bn(n, pfx + "bn1_group", cin, T);
+    b.pw1 = add_conv(n, pfx + "conv1_pw", cout, cin, 1, 1, false, 1, 1, 1, nullptr, nullptr);
+    n.conv[b.pw1].bn = add_bn(n, pfx + "bn1_pw", cout, T);
+    b.g2 = add_conv(n, pfx + "conv2_group", cout, cout / 20, 20, 3, false, 1, 1, 1, nullptr, dn);
+    n.conv[b.g2].bn = add_bn(n, pfx + "bn2_group", cout, T);
+    b.pw2 = add_conv(n, pfx + "conv2_pw", cout, cout, 1, 1, false, 1, 1, 1, nullptr, nullptr);
+    n.conv[b.pw2].bn = add_bn(n, pfx + "bn2_pw", cout, T);
+    b.ds = -1;
+    if (cin != cout) {
+        b.ds = add_conv(n, pfx + "downsample.0", cout, cin, 1, 1, false, 1, 1, 1, nullptr, nullptr);
+        n.conv[b.ds].bn = add_bn(n, pfx + "downsample.1", cout, T);
+    }
+    b.mask0 = n.nmask;
+    n.nmask += 2;
+    n.tcn.push_back(b);
+}
+
+// ConvBlock1 / AsymmetricConvBlock (models/convnet.py:4-74); count per channel = 20*B*Wout
+void add_conv_block(Net& n, const std::string& pfx, int cin, int cout, int win, int stride)
+{
+    CvBlk b{};
+    b.name = pfx;
+    b.cin = cin; b.cout = cout; b.win = win; b.wout = (win + 2 - 3) / stride + 1;
+    int dp3[3] = {-1, 0, 1};
+    const double cnt = (double)T * b.wout;
+    b.c1 = add_conv(n, pfx + "block.0", cout, cin, 1, 3, true, win, b.wout, stride, dp3, nullptr);
+    n.conv[b.c1].bn = add_bn(n, pfx + "block.1", cout, cnt);
+    b.c2 = add_conv(n, pfx + "block.4", cout, cout, 1, 3, true, b.wout, b.wout, 1, dp3, nullptr);
+    n.conv[b.c2].bn = add_bn(n, pfx + "block.5", cout, cnt);
+    b.c3 = add_conv(n, pfx + "block.8", cout, cout, 1, 3, true, b.wout, b.wout, 1, dp3, nullptr);
+    n.conv[b.c3].bn = add_bn(n, pfx + "block.9", cout, cnt);
+    b.ds = add_conv(n, pfx + "downsample.0", cout, cin, 1, 1, false, win, b.wout, stride, nullptr, nullptr);
+    n.conv[b.ds].bn = add_bn(n, pfx + "downsample.1", cout, cnt);
+    b.mask0 = n.nmask;
+    n.nmask += 2;
+    n.cv.push_back(b);
+}
+
+// AxialAttention (models/attention.py:7-80), 64 planes, 8 groups, on the 15x20 grid
+void add_axial(Net& n, const std::string& pfx, int width)
+{
+    AxBlk a{};
+    a.name = pfx;
+    a.width = width;
+    const int L = width ? 20 : 15;
+    a.qkv = add_conv(n, pfx + "qkv_transform", 192, 64, 1, 1, false, 15, 15, 1, nullptr, nullptr);
+    n.conv[a.qkv].bn = add_bn(n, pfx + "bn_qkv", 192, 15.0 * T);
+    a.bn_sim = add_bn(n, pfx + "bn_similarity", 8, 15.0 * T * L);
+    a.bn_out = add_bn(n, pfx + "bn_output", 64, 15.0 * T);
+    n.ax.push_back(a);
+}
+
+// decoder (models/pose_model.py:44-51)
+void add_decoder(Net& n, const std::string& pfx)
+{
+    int dp9[9], dn9[9];
+    for (int dh = 0; dh < 3; ++dh)
+        for (int dw = 0; dw < 3; ++dw) { dp9[dh * 3 + dw] = dh - 1; dn9[dh * 3 + dw] = dw - 1; }
+    n.dec.d1 = add_conv(n, pfx + "0", 32, 64, 1, 9, true, 15, 15, 1, dp9, dn9);
+    n.conv[n.dec.d1].bn = add_bn(n, pfx + "1", 32, 15.0 * T);
+    n.dec.d2 = add_conv(n, pfx + "3", 2, 32, 1, 1, true, 15, 15, 1, nullptr, nullptr);
+    n.conv[n.dec.d2].bn = add_bn(n, pfx + "4", 2, 15.0 * T);
+    n.has_dec = true;
+}
+
+int build_net(const wf_block_desc* d, Net& n)
+{
+    static const int tc[5] = {540, 540, 440, 340, 240};
+    static const int rc[5] = {8, 8, 16, 32, 64};
+    switch (d->block) {
+        case WF_BLOCK_MODEL:
+            for (int i = 0; i < 4; ++i) add_tcn_block(n, "tcn.network." + std::to_string(i) + ".", tc[i], tc[i + 1], 1 << i);
+            add_conv_block(n, "up.", 1, 8, 240, 1);
+            for (int i = 0; i < 4; ++i) add_conv_block(n, "residual_blocks." + std::to_string(i) + ".", rc[i], rc[i + 1], 240 >> i, 2);
+            add_axial(n, "attention.width_axis.", 1);
+            add_axial(n, "attention.height_axis.", 0);
+            add_decoder(n, "decoder.");
+            n.in_is_ref_bct = true;
+            break;
+        case WF_BLOCK_TCN:
+            for (int i = 0; i < 4; ++i) add_tcn_block(n, "network." + std::to_string(i) + ".", tc[i], tc[i + 1], 1 << i);
+            n.in_is_ref_bct = true;
+            n.out_C = 240; n.out_P = 1;
+            break;
+        case WF_BLOCK_INNER_TCN:
+            if (d->cin <= 0 || d->cout <= 0 || d->cin % 20 || d->cout % 20 || d->dilation < 1 || d->dilation > 16)
+                return fail(WF_E_ARG, "InnerGroupedTemporalBlock: channels must be multiples of 20 (groups=20, tcn.py:18), 1 <= dilation <= 16");
+            add_tcn_block(n, "", d->cin, d->cout, d->dilation);
+            n.in_is_ref_bct = true;
+            n.out_C = d->cout; n.out_P = 1;
+            break;
+        case WF_BLOCK_CONVBLOCK1:
+        case WF_BLOCK_ASYMCONV: {
+            const int stride = d->block == WF_BLOCK_ASYMCONV ? 2 : 1;
+            if (d->cin <= 0 || d->cout <= 0 || d->width <= 0) return fail(WF_E_ARG, "conv block: cin, cout, width must be positive");
+            add_conv_block(n, "", d->cin, d->cout, d->width, stride);
+            n.in_C = d->cin; n.in_P = d->width;
+            n.out_C = d->cout; n.out_P = n.cv[0].wout;
+            break;
+        }
+        case WF_BLOCK_AXIAL_W:
+        case WF_BLOCK_AXIAL_H:
+            add_axial(n, "", d->block == WF_BLOCK_AXIAL_W);
+            n.in_C = 64; n.in_P = 15; n.out_C = 64; n.out_P = 15;
+            break;
+        case WF_BLOCK_DUAL_AXIAL:
+            add_axial(n, "width_axis.", 1);
+            add_axial(n, "height_axis.", 0);
+            n.in_C = 64; n.in_P = 15; n.out_C = 64; n.out_P = 15;
+            break;
+        default:
+            return fail(WF_E_ARG, "unknown block id");
+    }
+    if ((int)n.conv.size() > WF_MAX_CONV || (int)n.bn.size() > WF_MAX_BN) return fail(WF_E_UNSUPPORTED, "too many layers");
+    return 0;
+}
+
+// ------------------------------- workspace layout -------------------------------
+struct Bump {
+    char* base; size_t off = 0;
+    explicit Bump(char* b) : base(b) {}
+    template <class Tp> Tp* take(size_t count)
+    {
+        off = (off + 255) & ~(size_t)255;
+        Tp* p = base ? reinterpret_cast<Tp*>(base + off) : nullptr;
+        off += count * sizeof(Tp);
+        return p;
+    }
+};
+
+size_t layout(Net& n, int B, int flags, char* base)
+{
+    const bool save = (flags & WF_FLAG_SAVE_FOR_BACKWARD) != 0;
+    const bool train = (flags & WF_FLAG_TRAIN) != 0;
+    const int Bw = train ? B : (B < EVAL_CHUNK ? B : EVAL_CHUNK);
+    const long long N = (long long)Bw * T;
+    Bump bp(base);
+    // packed weights
+    long long pf = 0;
+    for (auto& c : n.conv) {
+        c.fpack = pf; pf += (long long)c.groups * c.ntaps * c.f_kpad * c.f_mpad;
+        c.bpack = pf; pf += (long long)c.groups * c.ntaps * c.b_kpad * c.b_mpad;
+    }
+    n.packed_floats = pf;
+    n.packed = bp.take<float>(pf);
+    // BN statistics (fp64) and coefficients
+    size_t s0 = (bp.off + 255) & ~(size_t)255;
+    for (auto& b : n.bn) { b.f0 = bp.take<double>(b.C); b.f1 = bp.take<double>(b.C); }
+    n.fstats = base ? base + s0 : nullptr; n.fstats_bytes = bp.off - s0;
+    size_t s1 = (bp.off + 255) & ~(size_t)255;
+    for (auto& b : n.bn) { b.b0 = bp.take<double>(b.C); b.b1 = bp.take<double>(b.C); }
+    n.bstats = base ? base + s1 : nullptr; n.bstats_bytes = bp.off - s1;
+    for (auto& b : n.bn) b.coef = bp.take<float>(8 * b.Cpad);
+    // activations
+    for (auto& c : n.conv) {
+        c.raw = bp.take<float>(c.numel_per_n() * N);
+        c.dy = save ? bp.take<float>(c.numel_per_n() * N) : nullptr;
+    }
+    for (auto& t : n.tcn) {
+        t.X = bp.take<float>((long long)t.cout * N);
+        t.dX = save ? bp.take<float>((long long)t.cout * N) : nullptr;
+        t.dz = save ? bp.take<float>((long long)t.cout * N) : nullptr;
+    }
+    for (auto& v : n.cv) {
+        v.Y = bp.take<float>((long long)v.cout * v.wout * N);
+        v.dY = save ? bp.take<float>((long long)v.cout * v.wout * N) : nullptr;
+    }
+    for (auto& a : n.ax) {
+        a.sv_raw = bp.take<float>(64LL * 15 * N);
+        a.dsv = save ? bp.take<float>(64LL * 15 * N) : nullptr;
+    }
+    if (n.in_C) {
+        n.in_buf = bp.take<float>((long long)n.in_C * n.in_P * N);
+        n.din_buf = save ? bp.take<float>((long long)n.in_C * n.in_P * N) : nullptr;
+    } else if (n.in_is_ref_bct && save && !n.tcn.empty()) {
+        n.din_buf = bp.take<float>((long long)n.tcn[0].cin * N);
+    }
+    if (n.out_C) {
+        n.dout_buf = save ? bp.take<float>((long long)n.out_C * n.out_P * N) : nullptr;
+    }
+    n.dpred_buf = nullptr;
+    n.dbg.clear();
+    for (auto& c : n.conv) {
+        n.dbg.push_back({c.name + ".raw", c.raw, c.groups * c.cout_g, c.pout});
+        if (c.dy) n.dbg.push_back({c.name + ".dy", c.dy, c.groups * c.cout_g, c.pout});
+    }
+    for (auto& t : n.tcn) {
+        n.dbg.push_back({t.name + "out", t.X, t.cout, 1});
+        if (t.dX) n.dbg.push_back({t.name + "dout", t.dX, t.cout, 1});
+    }
+    for (auto& v : n.cv) {
+        n.dbg.push_back({v.name + "out", v.Y, v.cout, v.wout});
+        if (v.dY) n.dbg.push_back({v.name + "dout", v.dY, v.cout, v.wout});
+    }
+    for (auto& a : n.ax) {
+        n.dbg.push_back({a.name + "sv.raw", a.sv_raw, 64, 15});
+        if (a.dsv) n.dbg.push_back({a.name + "sv.dy", a.dsv, 64, 15});
+    }
+    for (size_t i = 0; i < n.bn.size(); ++i)
+        n.dbg.push_back({"bn" + std::to_string(i) + ".coef", n.bn[i].coef, 8, n.bn[i].Cpad});
+    return (bp.off + 255) & ~(size_t)255;
+}
+
+// ------------------------------- execution context -------------------------------
+struct Act { const float* p; long long sc, sp, sb; };     // element (c,pos,b,t) at p + c*sc + pos*sp + b*sb + t
+Act internal(const float* p, int P, long long N) { return Act{p, (long long)P * N, N, T}; }
+
+struct Mask { const float* p; long long sb, sc; int st; };
+Mask no_mask() { return Mask{nullptr, 0, 0, 0}; }
+Mask tcn_mask(const float* p, int C) { return Mask{p, (long long)C * T, T, 1}; }        // [B][C][20]
+Mask plane_mask(const float* p, int C) { return Mask{p, C, 1, 0}; }                      // [B][C]
+
+struct Ctx {
+    Net& n;
+    const float* params; float* grads; float* running; long long* nbt; const float* const* masks;
+    int B; long long N; bool train; bool save; cudaStream_t st; int sms;
+    cudaError_t err = cudaSuccess;
+    void ck(cudaError_t e) { if (err == cudaSuccess && e != cudaSuccess) err = e; }
+    const float* mask_ptr(int i) const { return (masks && train) ? masks[i] : nullptr; }
+};
+
+struct Pro { int mode; int bn; Mask mask; };
+Pro pro_none() { return Pro{PRO_NONE, -1, no_mask()}; }
+Pro pro_act(int bn, Mask m = no_mask()) { return Pro{PRO_BNSILU, bn, m}; }
+Pro pro_aff(int bn) { return Pro{PRO_AFFINE, bn, no_mask()}; }
+
+void fwd_conv(Ctx& c, int ui, Act in, Pro pro)
+{
+    const ConvUnit& u = c.n.conv[ui];
+    const BnUnit& bo = c.n.bn[u.bn];
+    ConvP p{};
+    p.in = in.p; p.in_sc = in.sc; p.in_sp = in.sp; p.in_sb = in.sb;
+    p.pro_mode = pro.mode;
+    if (pro.bn >= 0) { p.pro_a = c.n.bn[pro.bn].scale(); p.pro_b = c.n.bn[pro.bn].shift(); }
+    p.mask = pro.mask.p; p.m_sb = pro.mask.sb; p.m_sc = pro.mask.sc; p.m_st = pro.mask.st;
+    p.w = c.n.packed + u.fpack; p.Kpad = u.f_kpad; p.Mpad = u.f_mpad;
+    p.Cin = u.cin_g; p.Cout = u.cout_g; p.groups = u.groups; p.Pin = u.pin; p.Pout = u.pout; p.N = (int)c.N; p.ntaps = u.ntaps;
+    p.pmul = u.stride; p.pdiv = 1;
+    for (int t = 0; t < u.ntaps; ++t) { p.dp[t] = u.dpf[t]; p.dn[t] = u.dnf[t]; }
+    p.out = u.raw; p.out_sc = (long long)u.pout * c.N; p.out_sp = c.N; p.out_sb = T;
+    p.bias = u.b_off >= 0 ? c.params + u.b_off : nullptr;
+    p.epi_mode = c.train ? EPI_STATS : EPI_STORE;
+    p.stat0 = bo.f0; p.stat1 = bo.f1;
+    c.ck(wf_launch_conv(p, c.st));
+}
+
+void fwd_fin(Ctx& c, int bn_a, int bn_b = -1)
+{
+    if (!c.train) return;
+    BnFwdFin d[2];
+    int k = 0;
+    for (int bi : {bn_a, bn_b}) {
+        if (bi < 0) continue;
+        const BnUnit& b = c.n.bn[bi];
+        BnFwdFin f{};
+        f.C = b.C; f.count = b.count_per_b * c.B;
+        f.s0 = b.f0; f.s1 = b.f1;
+        f.gamma = c.params + b.gamma_off; f.beta = c.params + b.gamma_off + b.C;
+        f.scale = b.scale(); f.shift = b.shift(); f.mean = b.mean(); f.rstd = b.rstd();
+        f.run_mean = c.running ? c.running + b.run_off : nullptr;
+        f.run_var = c.running ? c.running + b.run_off + b.C : nullptr;
+        f.nbt = c.nbt ? c.nbt + bi : nullptr;
+        d[k++] = f;
+    }
+    c.ck(wf_launch_bn_fwd_fin(d, k, c.st));
+}
+
+void bwd_fin(Ctx& c, int bn_a, int bn_b = -1)
+{
+    BnBwdFin d[2];
+    int k = 0;
+    for (int bi : {bn_a, bn_b}) {
+        if (bi < 0) continue;
+        const BnUnit& b = c.n.bn[bi];
+        BnBwdFin f{};
+        f.C = b.C; f.count = b.count_per_b * c.B;
+        f.s0 = b.b0; f.s1 = b.b1;
+        f.gamma = c.params + b.gamma_off; f.mean = b.mean(); f.rstd = b.rstd();
+        f.dgamma = c.grads + b.gamma_off; f.dbeta = c.grads + b.gamma_off + b.C;
+        f.alpha = b.alpha(); f.beta_c = b.betac(); f.delta = b.delta();
+        d[k++] = f;
+    }
+    c.ck(wf_launch_bn_bwd_fin(d, k, c.st));
+}
+
+// backward-data of conv unit ui: consumes (dy, raw) of the unit through its BatchNorm backward, produces the gradient
+// w.r.t. the unit's input.  epi: EPI_STORE (input is a materialised tensor), EPI_DSILU / EPI_DAFF (input is the
+// BatchNorm(+SiLU) of conv unit `src`'s raw output; also accumulates that BatchNorm's backward sums).
+void dgrad_conv(Ctx& c, int ui, float* out, int epi, int src_bn, const float* src_raw, Mask emask, bool accumulate)
+{
+    const ConvUnit& u = c.n.conv[ui];
+    const BnUnit& bo = c.n.bn[u.bn];
+    ConvP p{};
+    p.in = u.dy; p.in2 = u.raw;
+    p.in_sc = (long long)u.pout * c.N; p.in_sp = c.N; p.in_sb = T;
+    p.pro_mode = PRO_BNBWD; p.pro_a = bo.alpha(); p.pro_b = bo.betac(); p.pro_c = bo.delta();
+    p.w = c.n.packed + u.bpack; p.Kpad = u.b_kpad; p.Mpad = u.b_mpad;
+    p.Cin = u.cout_g; p.Cout = u.cin_g; p.groups = u.groups; p.Pin = u.pout; p.Pout = u.pin; p.N = (int)c.N; p.ntaps = u.ntaps;
+    p.pmul = 1; p.pdiv = u.stride;
+    for (int t = 0; t < u.ntaps; ++t) { p.dp[t] = -u.dpf[t]; p.dn[t] = -u.dnf[t]; }
+    p.out = out; p.out_sc = (long long)u.pin * c.N; p.out_sp = c.N; p.out_sb = T;
+    p.epi_mode = epi; p.accumulate = accumulate ? 1 : 0;
+    if (epi == EPI_DSILU || epi == EPI_DAFF) {
+        const BnUnit& bs = c.n.bn[src_bn];
+        p.eraw = src_raw; p.e_scale = bs.scale(); p.e_shift = bs.shift();
+        p.emask = emask.p; p.em_sb = emask.sb; p.em_sc = emask.sc; p.em_st = emask.st;
+        p.stat0 = bs.b0; p.stat1 = bs.b1;
+    }
+    c.ck(wf_launch_conv(p, c.st));
+}
+
+void wgrad_conv(Ctx& c, int ui, Act in, Pro pro)
+{
+    const ConvUnit& u = c.n.conv[ui];
+    const BnUnit& bo = c.n.bn[u.bn];
+    WgradP p{};
+    p.g = u.dy; p.g2 = u.raw; p.g_pro = PRO_BNBWD; p.g_a = bo.alpha(); p.g_b = bo.betac(); p.g_c = bo.delta();
+    p.in = in.p; p.in_sc = in.sc; p.in_sp = in.sp; p.in_sb = in.sb;
+    p.pro_mode = pro.mode;
+    if (pro.bn >= 0) { p.pro_a = c.n.bn[pro.bn].scale(); p.pro_b = c.n.bn[pro.bn].shift(); }
+    p.mask = pro.mask.p; p.m_sb = pro.mask.sb; p.m_sc = pro.mask.sc; p.m_st = pro.mask.st;
+    p.Cin = u.cin_g; p.Cout = u.cout_g; p.groups = u.groups; p.Pin = u.pin; p.Pout = u.pout; p.N = (int)c.N; p.ntaps = u.ntaps;
+    p.pmul = u.stride;
+    for (int t = 0; t < u.ntaps; ++t) { p.dp[t] = u.dpf[t]; p.dn[t] = u.dnf[t]; }
+    p.dw = c.grads + u.w_off;
+    c.ck(wf_launch_wgrad(p, c.sms, c.st));
+}
+
+// ------------------------------- forward schedules -------------------------------
+void tcn_block_fwd(Ctx& c, TcnBlk& b, Act xin)
+{
+    Net& n = c.n;
+    fwd_conv(c, b.g1, xin, pro_none());
+    if (b.ds >= 0) fwd_conv(c, b.ds, xin, pro_none());
+    fwd_fin(c, n.conv[b.g1].bn, b.ds >= 0 ? n.conv[b.ds].bn : -1);
+    fwd_conv(c, b.pw1, internal(n.conv[b.g1].raw, 1, c.N), pro_act(n.conv[b.g1].bn));
+    fwd_fin(c, n.conv[b.pw1].bn);
+    fwd_conv(c, b.g2, internal(n.conv[b.pw1].raw, 1, c.N), pro_act(n.conv[b.pw1].bn, tcn_mask(c.mask_ptr(b.mask0), b.cout)));
+    fwd_fin(c, n.conv[b.g2].bn);
+    fwd_conv(c, b.pw2, internal(n.conv[b.g2].raw, 1, c.N), pro_act(n.conv[b.g2].bn));
+    fwd_fin(c, n.conv[b.pw2].bn);
+    JoinP j{};
+    const BnUnit& ba = n.bn[n.conv[b.pw2].bn];
+    j.a = n.conv[b.pw2].raw; j.out = b.X; j.plane = c.N; j.N = (int)c.N; j.C = b.cout;
+    j.a_mode = PRO_BNSILU; j.a_scale = ba.scale(); j.a_shift = ba.shift();
+    Mask m = tcn_mask(c.mask_ptr(b.mask0 + 1), b.cout);
+    j.mask = m.p; j.m_sb = m.sb; j.m_sc = m.sc; j.m_st = m.st;
+    if (b.ds >= 0) {
+        const BnUnit& br = n.bn[n.conv[b.ds].bn];
+        j.r = n.conv[b.ds].raw; j.r_mode = PRO_AFFINE; j.r_scale = br.scale(); j.r_shift = br.shift();
+        j.r_sc = c.N; j.r_sp = 0; j.r_sb = T;
+    } else {
+        j.r = xin.p; j.r_mode = PRO_NONE; j.r_sc = xin.sc; j.r_sp = 0; j.r_sb = xin.sb;
+    }
+    c.ck(wf_launch_join_fwd(j, c.sms, c.st));
+}
+
+void conv_block_fwd(Ctx& c, CvBlk& b, Act xin)
+{
+    Net& n = c.n;
+    fwd_conv(c, b.c1, xin, pro_none());
+    fwd_conv(c, b.ds, xin, pro_none());
+    fwd_fin(c, n.conv[b.c1].bn, n.conv[b.ds].bn);
+    fwd_conv(c, b.c2, internal(n.conv[b.c1].raw, b.wout, c.N), pro_act(n.conv[b.c1].bn, plane_mask(c.mask_ptr(b.mask0), b.cout)));
+    fwd_fin(c, n.conv[b.c2].bn);
+    fwd_conv(c, b.c3, internal(n.conv[b.c2].raw, b.wout, c.N), pro_act(n.conv[b.c2].bn, plane_mask(c.mask_ptr(b.mask0 + 1), b.cout)));
+    fwd_fin(c, n.conv[b.c3].bn);
+    JoinP j{};
+    const BnUnit& ba = n.bn[n.conv[b.c3].bn];
+    const BnUnit& br = n.bn[n.conv[b.ds].bn];
+    j.a = n.conv[b.c3].raw; j.out = b.Y; j.plane = (long long)b.wout * c.N; j.N = (int)c.N; j.C = b.cout;
+    j.a_mode = PRO_AFFINE; j.a_scale = ba.scale(); j.a_shift = ba.shift();
+    j.r = n.conv[b.ds].raw; j.r_mode = PRO_AFFINE; j.r_scale = br.scale(); j.r_shift = br.shift();
+    j.r_sc = j.plane; j.r_sp = c.N; j.r_sb = T;
+    c.ck(wf_launch_join_fwd(j, c.sms, c.st));
+}
+
+AttnP attn_params(Ctx& c, AxBlk& a)
+{
+    Net& n = c.n;
+    const ConvUnit& q = n.conv[a.qkv];
+    const BnUnit &bq = n.bn[q.bn], &bs = n.bn[a.bn_sim], &bo = n.bn[a.bn_out];
+    AttnP p{};
+    p.width = a.width; p.B = c.B; p.N = (int)c.N;
+    p.qkv_raw = q.raw; p.qkv_scale = bq.scale(); p.qkv_shift = bq.shift();
+    p.sim_scale = bs.scale(); p.sim_shift = bs.shift();
+    p.sim_s0 = bs.f0; p.sim_s1 = bs.f1;
+    p.sv_raw = a.sv_raw;
+    p.sv_s0 = c.train ? bo.f0 : nullptr; p.sv_s1 = c.train ? bo.f1 : nullptr;
+    p.dsv = a.dsv; p.sv_alpha = bo.alpha(); p.sv_beta = bo.betac(); p.sv_delta = bo.delta();
+    p.sim_alpha = bs.alpha(); p.sim_beta = bs.betac(); p.sim_delta = bs.delta();
+    p.dsim_s0 = bs.b0; p.dsim_s1 = bs.b1;
+    p.dqkv = q.dy;
+    return p;
+}
+
+void axial_fwd(Ctx& c, AxBlk& a, Act xin, Pro pro)
+{
+    Net& n = c.n;
+    fwd_conv(c, a.qkv, xin, pro);
+    fwd_fin(c, n.conv[a.qkv].bn);
+    AttnP p = attn_params(c, a);
+    if (c.train) {
+        c.ck(wf_launch_attn_fwd_stats(p, c.st));
+        fwd_fin(c, a.bn_sim);
+    }
+    c.ck(wf_launch_attn_fwd(p, c.st));
+    fwd_fin(c, a.bn_out);
+}
+
+void decoder_fwd(Ctx& c, Act xin, Pro pro, float* pred)
+{
+    Net& n = c.n;
+    fwd_conv(c, n.dec.d1, xin, pro);
+    fwd_fin(c, n.conv[n.dec.d1].bn);
+    fwd_conv(c, n.dec.d2, internal(n.conv[n.dec.d1].raw, 15, c.N), pro_act(n.conv[n.dec.d1].bn));
+    fwd_fin(c, n.conv[n.dec.d2].bn);
+    const BnUnit& b = n.bn[n.conv[n.dec.d2].bn];
+    c.ck(wf_launch_pool_fwd(n.conv[n.dec.d2].raw, b.scale(), b.shift(), pred, c.B, c.st));
+}
+
+// ------------------------------- backward schedules -------------------------------
+// gradient w.r.t. the block input goes to dxin (may be nullptr when nobody needs it)
+void decoder_bwd(Ctx& c, Act xin, Pro pro, const float* dpred, float* dxin_dy, int src_bn, const float* src_raw)
+{
+    Net& n = c.n;
+    ConvUnit &d1 = n.conv[n.dec.d1], &d2 = n.conv[n.dec.d2];
+    const BnUnit& b2 = n.bn[d2.bn];
+    c.ck(wf_launch_pool_bwd(d2.raw, b2.scale(), b2.shift(), dpred, d2.dy, c.B, b2.b0, b2.b1, c.st));
+    bwd_fin(c, d2.bn);
+    wgrad_conv(c, n.dec.d2, internal(d1.raw, 15, c.N), pro_act(d1.bn));
+    dgrad_conv(c, n.dec.d2, d1.dy, EPI_DSILU, d1.bn, d1.raw, no_mask(), false);
+    bwd_fin(c, d1.bn);
+    wgrad_conv(c, n.dec.d1, xin, pro);
+    dgrad_conv(c, n.dec.d1, dxin_dy, EPI_DAFF, src_bn, src_raw, no_mask(), false);
+}
+
+// on entry a.dsv holds dy of bn_output and its backward sums are complete
+void axial_bwd(Ctx& c, AxBlk& a, Act xin, Pro pro, float* dxin, int epi, int src_bn, const float* src_raw)
+{
+    Net& n = c.n;
+    ConvUnit& q = n.conv[a.qkv];
+    bwd_fin(c, a.bn_out);
+    AttnP p = attn_params(c, a);
+    c.ck(wf_launch_attn_bwd_stats(p, c.st));
+    bwd_fin(c, a.bn_sim);
+    c.ck(wf_launch_attn_bwd(p, c.st));
+    const BnUnit& bq = n.bn[q.bn];
+    c.ck(wf_launch_bn_bwd_stats(q.dy, q.raw, 192, 15LL * c.N, bq.b0, bq.b1, c.sms, c.st));
+    bwd_fin(c, q.bn);
+    wgrad_conv(c, a.qkv, xin, pro);
+    if (dxin) dgrad_conv(c, a.qkv, dxin, epi, src_bn, src_raw, no_mask(), false);
+}
+
+void conv_block_bwd(Ctx& c, CvBlk& b, Act xin, float* dxin)
+{
+    Net& n = c.n;
+    ConvUnit &c1 = n.conv[b.c1], &c2 = n.conv[b.c2], &c3 = n.conv[b.c3], &ds = n.conv[b.ds];
+    JoinP j{};
+    const BnUnit& ba = n.bn[c3.bn];
+    const BnUnit& br = n.bn[ds.bn];
+    j.a = c3.raw; j.plane = (long long)b.wout * c.N; j.N = (int)c.N; j.C = b.cout;
+    j.a_mode = PRO_AFFINE; j.a_scale = ba.scale(); j.a_shift = ba.shift();
+    j.r = ds.raw; j.r_mode = PRO_AFFINE; j.r_scale = br.scale(); j.r_shift = br.shift();
+    j.r_sc = j.plane; j.r_sp = c.N; j.r_sb = T;
+    j.dout = b.dY; j.dz = c3.dy; j.da = nullptr;           // c3.dy doubles as dy of the shortcut BatchNorm
+    j.a_stat0 = ba.b0; j.a_stat1 = ba.b1; j.r_stat0 = br.b0; j.r_stat1 = br.b1;
+    c.ck(wf_launch_join_bwd(j, c.sms, c.st));
+    bwd_fin(c, c3.bn, ds.bn);
+    Mask m0 = plane_mask(c.mask_ptr(b.mask0), b.cout), m1 = plane_mask(c.mask_ptr(b.mask0 + 1), b.cout);
+    wgrad_conv(c, b.c3, internal(c2.raw, b.wout, c.N), pro_act(c2.bn, m1));
+    dgrad_conv(c, b.c3, c2.dy, EPI_DSILU, c2.bn, c2.raw, m1, false);
+    bwd_fin(c, c2.bn);
+    wgrad_conv(c, b.c2, internal(c1.raw, b.wout, c.N), pro_act(c1.bn, m0));
+    dgrad_conv(c, b.c2, c1.dy, EPI_DSILU, c1.bn, c1.raw, m0, false);
+    bwd_fin(c, c1.bn);
+    wgrad_conv(c, b.c1, xin, pro_none());
+    // the shortcut conv shares dz with c3: temporarily view ds through c3's dy
+    float* saved = ds.dy; ds.dy = c3.dy;
+    wgrad_conv(c, b.ds, xin, pro_none());
+    if (dxin) {
+        dgrad_conv(c, b.ds, dxin, EPI_STORE, -1, nullptr, no_mask(), false);
+        dgrad_conv(c, b.c1, dxin, EPI_STORE, -1, nullptr, no_mask(), true);
+    }
+    ds.dy = saved;
+}
+
+void tcn_block_bwd(Ctx& c, TcnBlk& b, Act xin, float* dxin)
+{
+    Net& n = c.n;
+    ConvUnit &g1 = n.conv[b.g1], &pw1 = n.conv[b.pw1], &g2 = n.conv[b.g2], &pw2 = n.conv[b.pw2];
+    JoinP j{};
+    const BnUnit& ba = n.bn[pw2.bn];
+    j.a = pw2.raw; j.plane = c.N; j.N = (int)c.N; j.C = b.cout;
+    j.a_mode = PRO_BNSILU; j.a_scale = ba.scale(); j.a_shift = ba.shift();
+    Mask m1 = tcn_mask(c.mask_ptr(b.mask0 + 1), b.cout), m0 = tcn_mask(c.mask_ptr(b.mask0), b.cout);
+    j.mask = m1.p; j.m_sb = m1.sb; j.m_sc = m1.sc; j.m_st = m1.st;
+    j.dout = b.dX; j.da = pw2.dy;
+    j.a_stat0 = ba.b0; j.a_stat1 = ba.b1;
+    if (b.ds >= 0) {
+        ConvUnit& ds = n.conv[b.ds];
+        const BnUnit& br = n.bn[ds.bn];
+        j.r = ds.raw; j.r_mode = PRO_AFFINE; j.r_scale = br.scale(); j.r_shift = br.shift();
+        j.r_sc = c.N; j.r_sp = 0; j.r_sb = T;
+        j.dz = ds.dy; j.r_stat0 = br.b0; j.r_stat1 = br.b1;
+    } else {
+        j.r = xin.p; j.r_mode = PRO_NONE; j.r_sc = xin.sc; j.r_sp = 0; j.r_sb = xin.sb;
+        j.dz = dxin ? dxin : b.dz;          // identity shortcut: dz IS the gradient reaching the block input
+    }
+    c.ck(wf_launch_join_bwd(j, c.sms, c.st));
+    bwd_fin(c, pw2.bn, b.ds >= 0 ? n.conv[b.ds].bn : -1);
+    wgrad_conv(c, b.pw2, internal(g2.raw, 1, c.N), pro_act(g2.bn));
+    dgrad_conv(c, b.pw2, g2.dy, EPI_DSILU, g2.bn, g2.raw, no_mask(), false);
+    bwd_fin(c, g2.bn);
+    wgrad_conv(c, b.g2, internal(pw1.raw, 1, c.N), pro_act(pw1.bn, m0));
+    dgrad_conv(c, b.g2, pw1.dy, EPI_DSILU, pw1.bn, pw1.raw, m0, false);
+    bwd_fin(c, pw1.bn);
+    wgrad_conv(c, b.pw1, internal(g1.raw, 1, c.N), pro_act(g1.bn));
+    dgrad_conv(c, b.pw1, g1.dy, EPI_DSILU, g1.bn, g1.raw, no_mask(), false);
+    bwd_fin(c, g1.bn);
+    wgrad_conv(c, b.g1, xin, pro_none());
+    if (b.ds >= 0) {
+        wgrad_conv(c, b.ds, xin, pro_none());
+        if (dxin) {
+            dgrad_conv(c, b.ds, dxin, EPI_STORE, -1, nullptr, no_mask(), false);
+            dgrad_conv(c, b.g1, dxin, EPI_STORE, -1, nullptr, no_mask(), true);
+        }
+    } else if (dxin) {
+        dgrad_conv(c, b.g1, dxin, EPI_STORE, -1, nullptr, no_mask(), true);
+    }
+}
+
+// ------------------------------- shared prologue -------------------------------
+void prepare_weights(Ctx& c)
+{
+    Net& n = c.n;
+    c.ck(cudaMemsetAsync(n.packed, 0, n.packed_floats * sizeof(float), c.st));
+    PackTable tab{};
+    tab.n = (int)n.conv.size();
+    for (int i = 0; i < tab.n; ++i) {
+        const ConvUnit& u = n.conv[i];
+        PackEntry& e = tab.e[i];
+        e.param_off = (int)u.w_off; e.cout = u.cout_g * u.groups; e.cin = u.cin_g; e.groups = u.groups; e.ntaps = u.ntaps;
+        e.f_kpad = u.f_kpad; e.f_mpad = u.f_mpad; e.b_kpad = u.b_kpad; e.b_mpad = u.b_mpad;
+        e.fwd_off = u.fpack; e.bwd_off = u.bpack;
+    }
+    c.ck(wf_launch_pack(tab, c.params, n.packed, c.st));
+}
+
+void eval_coefs(Ctx& c)
+{
+    Net& n = c.n;
+    BnEvalTable tab{};
+    tab.n = (int)n.bn.size();
+    for (int i = 0; i < tab.n; ++i) {
+        const BnUnit& b = n.bn[i];
+        tab.e[i] = BnEvalEntry{b.C, b.Cpad, (int)b.gamma_off, (int)b.run_off, (int)(b.coef - n.bn[0].coef)};
+    }
+    c.ck(wf_launch_bn_eval_coefs(tab, c.params, c.running, n.bn[0].coef, c.st));
+}
+
+int num_sms()
+{
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        sms = v;
+    }
+    return sms;
+}
+
+int check_device()
+{
+    static int ok = 0;
+    if (ok) return 0;
+    int dev = 0, major = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail((int)e, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) return fail(WF_E_ARCH, "libwiflow_b200 is compiled for sm_100a only; device compute capability major = " + std::to_string(major));
+    ok = 1;
+    return 0;
+}
+
+// reference layout strides of the block's input / output tensors for the permute kernel: (r_sb, r_sc, r_sp, r_st)
+struct RefStrides { long long sb, sc, sp, st; };
+RefStrides ref_strides(const wf_block_desc* d, bool output, const Net& n)
+{
+    const int C = output ? n.out_C : n.in_C, P = output ? n.out_P : n.in_P;
+    switch (d->block) {
+        case WF_BLOCK_CONVBLOCK1:
+        case WF_BLOCK_ASYMCONV:            // [B, C, 20, W]: (b,c,t,w)
+            return RefStrides{(long long)C * T * P, (long long)T * P, 1, P};
+        case WF_BLOCK_AXIAL_W:
+        case WF_BLOCK_AXIAL_H:
+        case WF_BLOCK_DUAL_AXIAL:          // [B, 64, 15, 20]: (b,c,h,t)
+            return RefStrides{(long long)C * P * T, (long long)P * T, T, 1};
+        default:                           // [B, C, 20]
+            return RefStrides{(long long)C * T, T, 0, 1};
+    }
+}
+
+int run_forward(const wf_block_desc* d, const float* x, const float* params, float* running, long long* nbt, const float* const* masks,
+                float* y, void* ws, size_t ws_bytes, int B, int flags, cudaStream_t st)
+{
+    if (int e = check_device()) return e;
+    if (!d || !x || !params || !y || !ws || B <= 0) return fail(WF_E_ARG, "null pointer or non-positive batch");
+    const bool train = (flags & WF_FLAG_TRAIN) != 0;
+    if (!train && !running) return fail(WF_E_ARG, "eval mode needs the running statistics");
+    if (!train && (flags & WF_FLAG_SAVE_FOR_BACKWARD)) return fail(WF_E_UNSUPPORTED, "backward is only implemented for train-mode BatchNorm");
+    Net n;
+    if (int e = build_net(d, n)) return e;
+    const size_t need = layout(n, B, flags, (char*)ws);
+    if (need > ws_bytes) return fail(WF_E_WORKSPACE, "workspace too small: need " + std::to_string(need) + " bytes");
+    if (((uintptr_t)ws & 255) || ((uintptr_t)x & 15) || ((uintptr_t)y & 15)) return fail(WF_E_ARG, "workspace must be 256-byte, x/y 16-byte aligned");
+
+    const int chunk = train ? B : (B < EVAL_CHUNK ? B : EVAL_CHUNK);
+    Ctx c{n, params, nullptr, running, nbt, masks, chunk, (long long)chunk * T, train, (flags & WF_FLAG_SAVE_FOR_BACKWARD) != 0, st, num_sms()};
+    prepare_weights(c);
+    if (train) c.ck(cudaMemsetAsync(n.fstats, 0, n.fstats_bytes, st));
+    else eval_coefs(c);
+
+    const long long in_per_b = n.in_is_ref_bct ? (long long)n.tcn[0].cin * T : (long long)n.in_C * n.in_P * T;
+    long long out_per_b = d->block == WF_BLOCK_MODEL ? 30 : (long long)n.out_C * n.out_P * T;
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int bc = (B - b0 < chunk) ? B - b0 : chunk;
+        c.B = bc; c.N = (long long)bc * T;
+        if (bc != chunk) layout(n, bc, flags | WF_FLAG_TRAIN, (char*)ws);     // tail chunk: re-lay out for the smaller batch (fits: bc < chunk)
+        const float* xc = x + (long long)b0 * in_per_b;
+        float* yc = y + (long long)b0 * out_per_b;
+        Act cur{};
+        Pro cur_pro = pro_none();
+        if (n.in_is_ref_bct) {
+            cur = Act{xc, T, 0, (long long)n.tcn[0].cin * T};
+        } else {
+            RefStrides rs = ref_strides(d, false, n);
+            c.ck(wf_launch_permute(xc, n.in_buf, n.in_C, n.in_P, bc, rs.sb, rs.sc, rs.sp, rs.st, 1, c.sms, st));
+            cur = internal(n.in_buf, n.in_P, c.N);
+        }
+        for (auto& t : n.tcn) { tcn_block_fwd(c, t, cur); cur = internal(t.X, 1, c.N); }
+        if (!n.cv.empty() && !n.tcn.empty()) cur = internal(n.tcn.back().X, 240, c.N);   // [240][N] viewed as [1][240][N]
+        for (auto& v : n.cv) { conv_block_fwd(c, v, cur); cur = internal(v.Y, v.wout, c.N); }
+        for (auto& a : n.ax) {
+            axial_fwd(c, a, cur, cur_pro);
+            cur = internal(a.sv_raw, 15, c.N);
+            cur_pro = pro_aff(a.bn_out);
+        }
+        if (n.has_dec) {
+            decoder_fwd(c, cur, cur_pro, yc);
+        } else {
+            // write the block output in the reference layout
+            RefStrides rs = ref_strides(d, true, n);
+            const float* src = cur.p;
+            if (!n.ax.empty()) {
+                // output = bn_output(sv): apply the affine while permuting (JoinP-free path: use a conv-free affine permute)
+                const BnUnit& bo = n.bn[n.ax.back().bn_out];
+                c.ck(wf_launch_permute_affine(src, yc, n.out_C, n.out_P, bc, rs.sb, rs.sc, rs.sp, rs.st, bo.scale(), bo.shift(), c.sms, st));
+            } else {
+                c.ck(wf_launch_permute(src, yc, n.out_C, n.out_P, bc, rs.sb, rs.sc, rs.sp, rs.st, 0, c.sms, st));
+            }
+        }
+    }
+    if (c.err != cudaSuccess) return fail((int)c.err, std::string("CUDA error in forward: ") + cudaGetErrorString(c.err));
+    return 0;
+}
+
+int run_backward(const wf_block_desc* d, const float* x, const float* params, const float* const* masks, const float* dy, float* grads,
+                 float* dx, void* ws, size_t ws_bytes, int B, int flags, cudaStream_t st)
+{
+    if (int e = check_device()) return e;
+    if (!d || !x || !params || !dy || !grads || !ws || B <= 0) return fail(WF_E_ARG, "null pointer or non-positive batch");
+    if ((flags & (WF_FLAG_TRAIN | WF_FLAG_SAVE_FOR_BACKWARD)) != (WF_FLAG_TRAIN | WF_FLAG_SAVE_FOR_BACKWARD))
+        return fail(WF_E_UNSUPPORTED, "backward needs a forward run with WF_FLAG_TRAIN|WF_FLAG_SAVE_FOR_BACKWARD");
+    Net n;
+    if (int e = build_net(d, n)) return e;
+    const size_t need = layout(n, B, flags, (char*)ws);
+    if (need > ws_bytes) return fail(WF_E_WORKSPACE, "workspace too small: need " + std::to_string(need) + " bytes");
+    Ctx c{n, params, grads, nullptr, nullptr, masks, B, (long long)B * T, true, true, st, num_sms()};
+    c.ck(cudaMemsetAsync(n.bstats, 0, n.bstats_bytes, st));
+    c.ck(cudaMemsetAsync(grads, 0, n.nparams * sizeof(float), st));
+
+    // block inputs, as in the forward
+    std::vector<Act> tin(n.tcn.size()), vin(n.cv.size());
+    Act cur{};
+    if (n.in_is_ref_bct) cur = Act{x, T, 0, (long long)n.tcn[0].cin * T};
+    else cur = internal(n.in_buf, n.in_P, c.N);
+    for (size_t i = 0; i < n.tcn.size(); ++i) { tin[i] = cur; cur = internal(n.tcn[i].X, 1, c.N); }
+    if (!n.cv.empty() && !n.tcn.empty()) cur = internal(n.tcn.back().X, 240, c.N);
+    for (size_t i = 0; i < n.cv.size(); ++i) { vin[i] = cur; cur = internal(n.cv[i].Y, n.cv[i].wout, c.N); }
+    const Act ax_in0 = cur;
+
+    // gradient entering the last block
+    float* g_in = nullptr;                       // gradient w.r.t. the current block's output (materialised tensors)
+    if (n.has_dec) {
+        AxBlk& ah = n.ax.back();
+        decoder_bwd(c, internal(ah.sv_raw, 15, c.N), pro_aff(ah.bn_out), dy, ah.dsv, ah.bn_out, ah.sv_raw);
+    } else {
+        RefStrides rs = ref_strides(d, true, n);
+        if (!n.ax.empty()) {
+            // dy is the gradient of bn_output's output: permute into dsv and accumulate its BatchNorm-backward sums
+            AxBlk& ah = n.ax.back();
+            c.ck(wf_launch_permute(dy, ah.dsv, n.out_C, n.out_P, B, rs.sb, rs.sc, rs.sp, rs.st, 1, c.sms, st));
+            const BnUnit& bo = n.bn[ah.bn_out];
+            c.ck(wf_launch_bn_bwd_stats(ah.dsv, ah.sv_raw, 64, 15LL * c.N, bo.b0, bo.b1, c.sms, st));
+        } else {
+            c.ck(wf_launch_permute(dy, n.dout_buf, n.out_C, n.out_P, B, rs.sb, rs.sc, rs.sp, rs.st, 1, c.sms, st));
+            g_in = n.dout_buf;
+        }
+    }
+    const bool want_dx = dx != nullptr;
+    // attention blocks, last to first
+    for (int i = (int)n.ax.size() - 1; i >= 0; --i) {
+        AxBlk& a = n.ax[i];
+        if (i > 0) {
+            AxBlk& prev = n.ax[i - 1];
+            axial_bwd(c, a, internal(prev.sv_raw, 15, c.N), pro_aff(prev.bn_out), prev.dsv, EPI_DAFF, prev.bn_out, prev.sv_raw);
+        } else {
+            float* dst = !n.cv.empty() ? n.cv.back().dY : (want_dx ? n.din_buf : nullptr);
+            axial_bwd(c, a, ax_in0, pro_none(), dst, EPI_STORE, -1, nullptr);
+        }
+    }
+    if (n.ax.empty() && !n.cv.empty() && g_in) {
+        c.ck(cudaMemcpyAsync(n.cv.back().dY, g_in, sizeof(float) * n.cv.back().cout * n.cv.back().wout * c.N, cudaMemcpyDeviceToDevice, st));
+    }
+    for (int i = (int)n.cv.size() - 1; i >= 0; --i) {
+        float* dst = i > 0 ? n.cv[i - 1].dY : (!n.tcn.empty() ? n.tcn.back().dX : (want_dx ? n.din_buf : nullptr));
+        conv_block_bwd(c, n.cv[i], vin[i], dst);
+    }
+    if (n.cv.empty() && n.ax.empty() && !n.tcn.empty() && g_in) {
+        c.ck(cudaMemcpyAsync(n.tcn.back().dX, g_in, sizeof(float) * n.tcn.back().cout * c.N, cudaMemcpyDeviceToDevice, st));
+    }
+    for (int i = (int)n.tcn.size() - 1; i >= 0; --i) {
+        float* dst = i > 0 ? n.tcn[i - 1].dX : (want_dx ? n.din_buf : nullptr);
+        tcn_block_bwd(c, n.tcn[i], tin[i], dst);
+    }
+    if (want_dx) {
+        if (n.in_is_ref_bct) {
+            const int C = n.tcn[0].cin;
+            c.ck(wf_launch_permute(n.din_buf, dx, C, 1, B, (long long)C * T, T, 0, 1, 0, c.sms, st));
+        } else {
+            RefStrides rs = ref_strides(d, false, n);
+            c.ck(wf_launch_permute(n.din_buf, dx, n.in_C, n.in_P, B, rs.sb, rs.sc, rs.sp, rs.st, 0, c.sms, st));
+        }
+    }
+    if (c.err != cudaSuccess) return fail((int)c.err, std::string("CUDA error in backward: ") + cudaGetErrorString(c.err));
+    return 0;
+}
+
+}  // namespace
+
+// =========================================== C ABI ===========================================
+extern "C" {
+
+const char* wf_last_error_string(void) { return g_err.c_str(); }
+int wf_version(void) { return 100; }
+
+long long wf_param_count(const wf_block_desc* d) { Net n; return build_net(d, n) ? -1 : n.nparams; }
+long long wf_running_count(const wf_block_desc* d) { Net n; return build_net(d, n) ? -1 : n.nrunning; }
+int wf_bn_count(const wf_block_desc* d) { Net n; return build_net(d, n) ? -1 : (int)n.bn.size(); }
+int wf_dropout_sites(const wf_block_desc* d) { Net n; return build_net(d, n) ? -1 : n.nmask; }
+
+int wf_param_table(const wf_block_desc* d, int i, char* name, int name_cap, long long* offset, long long* numel)
+{
+    Net n;
+    if (int e = build_net(d, n)) return e;
+    if (i < 0 || i >= (int)n.params.size()) return WF_E_ARG;
+    if (name && name_cap > 0) { std::strncpy(name, n.params[i].name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+    if (offset) *offset = n.params[i].off;
+    if (numel) *numel = n.params[i].numel;
+    return 0;
+}
+
+size_t wf_workspace_bytes(const wf_block_desc* d, int B, int flags)
+{
+    Net n;
+    if (build_net(d, n) || B <= 0) return 0;
+    return layout(n, B, flags, nullptr);
+}
+
+// Debug/test introspection: i-th named workspace tensor ([C][P][B*20] fp32) of the block's layout.
+WF_API int wf_debug_tensor(const wf_block_desc* d, int B, int flags, int i, char* name, int name_cap, long long* byte_offset, int* C, int* P)
+{
+    Net n;
+    if (int e = build_net(d, n)) return e;
+    static char dummy[1];
+    layout(n, B, flags, dummy);
+    if (i < 0 || i >= (int)n.dbg.size()) return WF_E_ARG;
+    if (name && name_cap > 0) { std::strncpy(name, n.dbg[i].name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+    if (byte_offset) *byte_offset = n.dbg[i].p ? (long long)((const char*)n.dbg[i].p - dummy) : -1;
+    if (C) *C = n.dbg[i].C;
+    if (P) *P = n.dbg[i].P;
+    return 0;
+}
+
+int wf_block_forward(const wf_block_desc* d, const float* x, const float* params, float* running, long long* nbt,
+                     const float* const* masks, float* y, void* ws, size_t ws_bytes, int B, int flags, wf_stream_t stream)
+{
+    return run_forward(d, x, params, running, nbt, masks, y, ws, ws_bytes, B, flags, (cudaStream_t)stream);
+}
+
+int wf_block_backward(const wf_block_desc* d, const float* x, const float* params, const float* const* masks, const float* dy,
+                      float* grads, float* dx, void* ws, size_t ws_bytes, int B, int flags, wf_stream_t stream)
+{
+    return run_backward(d, x, params, masks, dy, grads, dx, ws, ws_bytes, B, flags, (cudaStream_t)stream);
+}
+
+int wf_pose_loss(const float* pred, const float* target, int B, int loss_type, float pw, float bw, const float* gscale, float* dpred,
+                 float* out3, double* scratch, wf_stream_t stream)
+{
+    if (int e = check_device()) return e;
+    if (!pred || !target || !out3 || !scratch || B <= 0) return fail(WF_E_ARG, "null pointer or non-positive batch");
+    if (loss_type < 0 || loss_type > 2) return fail(WF_E_ARG, "Unknown loss type");
+    cudaError_t e = wf_launch_pose_loss(pred, target, B, loss_type, pw, bw, gscale, dpred, scratch, out3, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail((int)e, cudaGetErrorString(e));
+}
+
+int wf_pose_metrics(const float* pred, const float* target, int B, const float* thresholds, int nthr, int torso, float* out, void* scratch,
+                    wf_stream_t stream)
+{
+    if (int e = check_device()) return e;
+    if (!pred || !target || !out || !scratch || B <= 0 || nthr < 0 || nthr > WF_MAX_THR) return fail(WF_E_ARG, "bad argument (nthr <= 8)");
+    MetricThr t{};
+    t.n = nthr;
+    for (int i = 0; i < nthr; ++i) t.v[i] = thresholds[i];
+    unsigned long long* counts = (unsigned long long*)scratch;
+    double* dsum = (double*)scratch + WF_MAX_THR;
+    cudaError_t e = wf_launch_metrics(pred, target, B, t, torso, counts, dsum, out, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail((int)e, cudaGetErrorString(e));
+}
+
+int wf_clip_adamw(float* params, const float* grads, float* m, float* v, long long n, void* state, float lr, float b1, float b2, float eps,
+                  float wd, float max_norm, float grad_scale, wf_stream_t stream)
+{
+    if (int e = check_device()) return e;
+    if (!params || !grads || !m || !v || !state || n <= 0) return fail(WF_E_ARG, "null pointer");
+    cudaError_t e = wf_launch_adamw(params, grads, m, v, n, (AdamState*)state, lr, b1, b2, eps, wd, max_norm, grad_scale, num_sms(), (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail((int)e, cudaGetErrorString(e));
+}
+
+}  // extern "C"

@@ -1,0 +1,156 @@
+"""Thin torch custom-op layer over the C ABI (include/wiflow_b200.h).
+
+Each op only validates tensors, picks the current CUDA stream and forwards raw device pointers to
+libwiflow_b200.so.  The ops are registered with torch.library (namespace `wiflow_b200`) so they are visible
+to the dispatcher (fake-tensor shape inference, CUDA-graph capture); autograd is wired in `block.py` /
+`losses/pose_loss.py`.  There is deliberately no CPU implementation: CPU tensors raise."""
+import ctypes
+from typing import List
+
+import torch
+
+from . import _lib
+from ._lib import BlockDesc
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else ctypes.c_void_p(0)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError('wiflow_b200 ops run on sm_100a CUDA devices only (no CPU fallback); got a CPU tensor')
+        if not t.is_contiguous():
+            raise RuntimeError('wiflow_b200 ops need contiguous tensors')
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _desc(d: List[int]) -> BlockDesc:
+    return BlockDesc(*d)
+
+
+def out_shape(d: List[int], B: int):
+    blk, cin, cout, width, _ = d
+    if blk == _lib.BLOCK_MODEL:
+        return (B, 15, 2)
+    if blk == _lib.BLOCK_TCN:
+        return (B, 240, 20)
+    if blk == _lib.BLOCK_INNER_TCN:
+        return (B, cout, 20)
+    if blk == _lib.BLOCK_CONVBLOCK1:
+        return (B, cout, 20, width)
+    if blk == _lib.BLOCK_ASYMCONV:
+        return (B, cout, 20, (width - 1) // 2 + 1)
+    return (B, 64, 15, 20)
+
+
+def workspace_bytes(d: List[int], B: int, flags: int) -> int:
+    desc = _desc(d)
+    n = _lib.lib().wf_workspace_bytes(ctypes.byref(desc), B, flags)
+    if n == 0:
+        raise RuntimeError('wf_workspace_bytes: bad block descriptor ' + _lib.lib().wf_last_error_string().decode())
+    return n
+
+
+def _mask_array(masks):
+    if not masks:
+        return None, ctypes.c_void_p(0)
+    arr = (ctypes.c_void_p * len(masks))(*[m.data_ptr() for m in masks])
+    return arr, ctypes.cast(arr, ctypes.c_void_p)
+
+
+@torch.library.custom_op('wiflow_b200::block_forward', mutates_args=('running', 'nbt', 'workspace'))
+def block_forward(x: torch.Tensor, params: torch.Tensor, running: torch.Tensor, nbt: torch.Tensor, masks: List[torch.Tensor],
+                  desc: List[int], flags: int, workspace: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x, params, running, nbt, workspace, *masks)
+    B = x.shape[0]
+    y = torch.empty(out_shape(desc, B), device=x.device, dtype=torch.float32)
+    d = _desc(desc)
+    keep, mp = _mask_array(masks)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().wf_block_forward(ctypes.byref(d), _ptr(x), _ptr(params), _ptr(running), _ptr(nbt), mp, _ptr(y),
+                                         _ptr(workspace), workspace.numel() * workspace.element_size(), B, flags, _stream())
+    _lib.check(rc, 'wf_block_forward')
+    return y
+
+
+@block_forward.register_fake
+def _(x, params, running, nbt, masks, desc, flags, workspace):
+    return x.new_empty(out_shape(desc, x.shape[0]))
+
+
+@torch.library.custom_op('wiflow_b200::block_backward', mutates_args=('workspace',))
+def block_backward(x: torch.Tensor, params: torch.Tensor, masks: List[torch.Tensor], dy: torch.Tensor, desc: List[int], flags: int,
+                   workspace: torch.Tensor, need_dx: bool) -> List[torch.Tensor]:
+    _need_cuda(x, params, dy, workspace, *masks)
+    B = x.shape[0]
+    grads = torch.empty_like(params)
+    dx = torch.empty_like(x) if need_dx else x.new_empty(0)
+    d = _desc(desc)
+    keep, mp = _mask_array(masks)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().wf_block_backward(ctypes.byref(d), _ptr(x), _ptr(params), mp, _ptr(dy), _ptr(grads), _ptr(dx),
+                                          _ptr(workspace), workspace.numel() * workspace.element_size(), B, flags, _stream())
+    _lib.check(rc, 'wf_block_backward')
+    return [grads, dx]
+
+
+@block_backward.register_fake
+def _(x, params, masks, dy, desc, flags, workspace, need_dx):
+    return [torch.empty_like(params), torch.empty_like(x) if need_dx else x.new_empty(0)]
+
+
+@torch.library.custom_op('wiflow_b200::pose_loss', mutates_args=('scratch',))
+def pose_loss(pred: torch.Tensor, target: torch.Tensor, loss_type: int, position_weight: float, bone_weight: float,
+              scratch: torch.Tensor, want_grad: bool) -> List[torch.Tensor]:
+    """returns [out3 = (total, position, bone), dpred (d total / d pred, or empty)]"""
+    _need_cuda(pred, target, scratch)
+    B = pred.shape[0]
+    out3 = torch.empty(3, device=pred.device, dtype=torch.float32)
+    dpred = torch.empty_like(pred) if want_grad else pred.new_empty(0)
+    with torch.cuda.device(pred.device):
+        rc = _lib.lib().wf_pose_loss(_ptr(pred), _ptr(target), B, loss_type, position_weight, bone_weight, ctypes.c_void_p(0),
+                                     _ptr(dpred), _ptr(out3), _ptr(scratch), _stream())
+    _lib.check(rc, 'wf_pose_loss')
+    return [out3, dpred]
+
+
+@pose_loss.register_fake
+def _(pred, target, loss_type, position_weight, bone_weight, scratch, want_grad):
+    return [pred.new_empty(3), torch.empty_like(pred) if want_grad else pred.new_empty(0)]
+
+
+@torch.library.custom_op('wiflow_b200::pose_metrics', mutates_args=('scratch',))
+def pose_metrics(pred: torch.Tensor, target: torch.Tensor, thresholds: List[float], use_torso_norm: bool,
+                 scratch: torch.Tensor) -> torch.Tensor:
+    """returns [pck(thr_0), ..., pck(thr_k-1), mpjpe] on the device"""
+    _need_cuda(pred, target, scratch)
+    B = pred.shape[0]
+    out = torch.empty(len(thresholds) + 1, device=pred.device, dtype=torch.float32)
+    thr = (ctypes.c_float * max(1, len(thresholds)))(*thresholds)
+    with torch.cuda.device(pred.device):
+        rc = _lib.lib().wf_pose_metrics(_ptr(pred), _ptr(target), B, thr, len(thresholds), 1 if use_torso_norm else 0,
+                                        _ptr(out), _ptr(scratch), _stream())
+    _lib.check(rc, 'wf_pose_metrics')
+    return out
+
+
+@pose_metrics.register_fake
+def _(pred, target, thresholds, use_torso_norm, scratch):
+    return pred.new_empty(len(thresholds) + 1)
+
+
+@torch.library.custom_op('wiflow_b200::clip_adamw', mutates_args=('params', 'exp_avg', 'exp_avg_sq', 'state'))
+def clip_adamw(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, state: torch.Tensor,
+               lr: float, beta1: float, beta2: float, eps: float, weight_decay: float, max_norm: float, grad_scale: float) -> None:
+    _need_cuda(params, grads, exp_avg, exp_avg_sq, state)
+    with torch.cuda.device(params.device):
+        rc = _lib.lib().wf_clip_adamw(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(), _ptr(state),
+                                      lr, beta1, beta2, eps, weight_decay, max_norm, grad_scale, _stream())
+    _lib.check(rc, 'wf_clip_adamw')

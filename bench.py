@@ -1,0 +1,338 @@
+"""WiFlow hot-path benchmark (driver contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]`).
+
+One "step" = one training step of the pose model on one batch of synthetic 540x20 CSI windows:
+forward + PoseLoss + backward + clip_grad_norm_(1.0) + AdamW, dropout on, fp32 -- BASELINE.json config C4's per-GPU
+batch (1024 windows per GPU, weak scaling; at N=1 the same per-GPU batch so the driver's own scaling efficiency is
+meaningful).  The JSON line also carries C2 (train, B=64) and C3 (inference, B=8192) under "also" at N=1.
+
+  value    : whole-job samples/s, inputs already resident in HBM, CUDA-graph replayed step, CUDA-event timed, max over ranks
+  e2e      : same metric through the public API (`TrainStep.step`) with HOST pinned inputs: H2D of x,y and D2H of the loss
+             inside every timed step
+  roofline : dominant kernel family (profiled live with CUDA events around every launch, WF_FLAG_PROFILE) against the
+             FP32-FMA peak the path is bound by (148 SM x 128 lanes x 2 x sm_max_mhz); the measured
+             bf16 tensor peak of MEASURED_PEAKS.json is reported beside it
+  cpu_baseline : the oracle port of the reference's train step on this box's host cores (bounded sample)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FWD_FLOPS = 153.56e6            # per sample, zero-pad taps excluded
+TRAIN_FLOPS = 3 * 154.81e6      # fwd + dX + dW, dense count
+METRIC = 'WiFlow train-step throughput (fwd+PoseLoss+bwd+clip+AdamW), synthetic 540x20 CSI, fp32'
+
+
+def peaks():
+    p = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+    except Exception:
+        pass
+    src = 'measured' if p else 'fallback'
+    sm_mhz = p.get('sm_max_mhz', 1965.0)
+    return dict(hbm_gbs=p.get('hbm_gbs', 6650.0), bf16_tflops=p.get('bf16_tflops', 1590.0),
+                bf16_tflops_sustained=p.get('bf16_tflops_sustained', 1400.0), sm_max_mhz=sm_mhz,
+                fp32_tflops=148 * 128 * 2 * sm_mhz * 1e6 / 1e12, source=src)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs"""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def cpu_train_step_rate(B, max_seconds, warmup, steps=None):
+    """oracle port of the reference's training step (train.py:196-237) on the host cores; returns samples/s, n steps"""
+    import torch
+    from oracle import wiflow_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    st = O.make_state(0)
+    pn = O.param_names(st)
+    params = {n: st[n] for n in pn}
+    m = {n: torch.zeros_like(p) for n, p in params.items()}
+    v = {n: torch.zeros_like(p) for n, p in params.items()}
+    x, y = O.synthetic_batch(B, 0)
+    it = 0
+
+    def one():
+        nonlocal it
+        it += 1
+        masks = O.make_dropout_masks(B, 0.5)
+        _, _, g = O.grads(st, x, y, masks=masks, update_buffers=True)
+        O.clip_adamw_step(params, g, m, v, it)
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        one()
+        n += 1
+        if steps is not None and n >= steps:
+            break
+        if steps is None and (time.perf_counter() - t0 > max_seconds or n >= 200):
+            break
+    dt = time.perf_counter() - t0
+    return B * n / dt, n, dt, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    """reference arm: the reference's CPU implementation of the path (oracle port -- the reference itself is Python and
+    /root/reference does not exist on the GPU box) on all host cores, same metric, bounded sample per step."""
+    if rank != 0:
+        return
+    Bs = 64
+    rate, n, dt, cores = cpu_train_step_rate(Bs, 0, args.warmup, steps=args.steps)
+    line = {'metric': METRIC, 'value': rate, 'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3 * dt / n, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'impl': 'reference',
+            'config': {'workload': workload_name(args), 'per_gpu_batch': args.batch, 'parallelism': f'dp{args.gpus}'},
+            'cpu_baseline': {'value': rate, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+                             'sample': f'{Bs} of the {args.batch} windows per step, {n} steps (torch CPU ops, all host threads)'},
+            'e2e': {'value': rate, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return (f'C4 WiFlow data-parallel training step, {args.batch} windows of 540x20 per GPU (fwd+PoseLoss+bwd+clip(1.0)+AdamW, '
+            'dropout on: TCN p=0.5 / conv p=0.3, fp32, random-init weights)')
+
+
+def timed_loop(fn, steps, dev):
+    import torch
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    start.record()
+    for i in range(steps):
+        fn(i)
+    end.record()
+    torch.cuda.synchronize(dev)
+    return start.elapsed_time(end)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import wiflow_b200 as wf
+    from wiflow_b200 import _lib, ops
+    from oracle import wiflow_oracle as O          # synthetic inputs + cpu_baseline only
+
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    pg = None
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+        pg = dist.group.WORLD
+    B = args.batch
+    torch.manual_seed(0)
+    model = wf.WiFlowPoseModel(dropout=0.5).to(dev)
+    ts = wf.TrainStep(model, B, process_group=pg)
+    nbatch = 4
+    xs, ys = [], []
+    for i in range(nbatch):
+        x, y = O.synthetic_batch(B, seed=1000 * rank + i)
+        xs.append(x.to(dev)); ys.append(y.to(dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_dev(i):
+        ts.step(xs[i % nbatch], ys[i % nbatch])
+
+    for i in range(max(args.warmup, 3)):
+        step_dev(i)
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        ms = timed_loop(step_dev, args.steps, dev)
+    barrier()
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    value = world * B * args.steps / (ms / 1e3)
+    loss_val = ts.out.tolist()
+
+    # ---- e2e: host pinned inputs -> H2D -> step -> D2H of the loss, every step ----
+    hx = [x.cpu().pin_memory() for x in xs]
+    hy = [y.cpu().pin_memory() for y in ys]
+    res = torch.zeros(4).pin_memory()
+
+    def step_e2e(i):
+        out = ts.step(hx[i % nbatch], hy[i % nbatch])
+        res.copy_(out, non_blocking=False)
+    for i in range(3):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / t.item()
+    h2d = hx[0].numel() * 4 + hy[0].numel() * 4
+    d2h = 16
+
+    line = {'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': workload_name(args), 'per_gpu_batch': B, 'global_batch': B * world, 'parallelism': f'dp{world}',
+                       'l2': f'inputs rotate over {nbatch} batches ({nbatch * B * 43200 / 1e6:.0f} MB) and every step streams '
+                             f'{ts.ws.numel() / 1e9:.1f} GB of saved activations, far above the 126 MB L2',
+                       'collective': 'NCCL all-reduce of the flat 8.9 MB fp32 gradient per step' if world > 1 else 'none'},
+            'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+            'final_loss': loss_val[0], 'grad_norm': loss_val[3]}
+
+    if rank == 0:
+        line['clocks'] = clk.summary()
+        pk = peaks()
+        # ---- launches per step + per-kernel profile of one eager step (CUDA events around every launch) ----
+        c0 = _lib.lib().wf_launch_count()
+        ts.use_graph = False
+        ts.step(xs[0], ys[0])
+        torch.cuda.synchronize(dev)
+        per_step = _lib.lib().wf_launch_count() - c0
+        line['gpu_launches'] = int(per_step * args.steps)
+        line['gpu_launches_per_step'] = int(per_step)
+        masks = model._wf_masks(B, dev)
+        pf = ts.flags | _lib.FLAG_PROFILE
+        pred = ops.block_forward(xs[0], ts.params, ts.running, ts.nbt, masks, [0, 0, 0, 0, 0], pf, ts.ws)
+        out3, dpred = ops.pose_loss(pred, ys[0], 0, 1.0, 0.2, ts.loss_scratch, True)
+        ops.block_backward(xs[0], ts.params, masks, dpred, [0, 0, 0, 0, 0], pf, ts.ws, False)
+        torch.cuda.synchronize(dev)
+        recs = _lib.profile_records()
+        fam = {}
+        for name, t_ms, fl in recs:
+            k = name.split(' ')[0]
+            a = fam.setdefault(k, [0.0, 0.0, 0])
+            a[0] += t_ms; a[1] += fl; a[2] += 1
+        total_ms = sum(a[0] for a in fam.values())
+        gemm_ms = sum(fam.get(k, [0, 0, 0])[0] for k in ('conv_fwd', 'conv_dgrad'))
+        gemm_fl = sum(fam.get(k, [0, 0, 0])[1] for k in ('conv_fwd', 'conv_dgrad'))
+        gemm_n = sum(fam.get(k, [0, 0, 0])[2] for k in ('conv_fwd', 'conv_dgrad'))
+        achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms else 0.0
+        line['roofline'] = {'bound': 'fp32_fma', 'kernel': 'conv_gemm_kernel (implicit-GEMM conv, forward + backward-data launches)',
+                            'achieved': achieved, 'peak': pk['fp32_tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['fp32_tflops'],
+                            'traffic': None, 'launches_per_step': gemm_n, 'avg_launch_ms': gemm_ms / max(gemm_n, 1),
+                            'share_of_step': gemm_ms / total_ms if total_ms else None,
+                            'peak_source': f"148 SM x 128 FP32 lanes x 2 x {pk['sm_max_mhz']:.0f} MHz ({pk['source']} sm_max_mhz); "
+                                           f"not a tensor-core kernel, measured bf16 tensor peak for context: {pk['bf16_tflops']} TFLOP/s",
+                            'algorithmic_flops_per_launch_avg': gemm_fl / max(gemm_n, 1)}
+        step_tflops = value / world * TRAIN_FLOPS / 1e12
+        line['step_roofline'] = {'flops_per_sample': TRAIN_FLOPS, 'achieved_tflops_per_gpu': step_tflops, 'peak_tflops': pk['fp32_tflops'],
+                                 'frac': step_tflops / pk['fp32_tflops'],
+                                 'roofline_samples_per_s_per_gpu': pk['fp32_tflops'] * 1e12 / TRAIN_FLOPS}
+        line['kernel_breakdown_ms'] = {k: round(a[0], 4) for k, a in sorted(fam.items(), key=lambda kv: -kv[1][0])}
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        with open(os.path.join(ROOT, 'gpurun_out', f'bench_profile_n{world}_b{B}.json'), 'w') as f:
+            json.dump({'records': recs, 'families': fam, 'B': B}, f)
+
+        if world == 1 and not args.no_extras:
+            also = {}
+            # C2: train step B=64
+            torch.manual_seed(0)
+            m2 = wf.WiFlowPoseModel(dropout=0.5).to(dev)
+            t2 = wf.TrainStep(m2, 64)
+            x2, y2 = O.synthetic_batch(64, 5)
+            x2, y2 = x2.to(dev), y2.to(dev)
+            for i in range(5):
+                t2.step(x2, y2)
+            ms2 = timed_loop(lambda i: t2.step(x2, y2), 50, dev)
+            also['C2_train_b64'] = {'samples_per_s': 64 * 50 / (ms2 / 1e3), 'ms_per_step': ms2 / 50,
+                                    'frac_of_fp32_roofline': 64 * 50 / (ms2 / 1e3) * TRAIN_FLOPS / 1e12 / pk['fp32_tflops']}
+            # C3: inference B=8192
+            inf = wf.InferStep(model, 8192)
+            x3, _ = O.synthetic_batch(8192, 6)
+            x3 = x3.to(dev)
+            for i in range(3):
+                inf.step(x3)
+            ms3 = timed_loop(lambda i: inf.step(x3), 5, dev)
+            also['C3_infer_b8192'] = {'samples_per_s': 8192 * 5 / (ms3 / 1e3), 'ms_per_step': ms3 / 5,
+                                      'frac_of_fp32_roofline': 8192 * 5 / (ms3 / 1e3) * FWD_FLOPS / 1e12 / pk['fp32_tflops']}
+            line['also'] = also
+            rate, n, dt, cores = cpu_train_step_rate(64, args.cpu_seconds, 2)
+            line['cpu_baseline'] = {'value': rate, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+                                    'sample': f'oracle port of the reference train step, B=64, {n} steps in {dt:.1f} s on the host cores'}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=1024, help='windows per GPU per step')
+    ap.add_argument('--cpu-seconds', type=float, default=12.0)
+    ap.add_argument('--no-extras', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        os.execvp(sys.executable, [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',
+                                   '--master-addr', '127.0.0.1', '--master-port', '29531', os.path.abspath(__file__)] + sys.argv[1:])
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

@@ -33,7 +33,8 @@ typedef void* wf_stream_t;              /* cudaStream_t */
 
 enum { WF_E_ARG = -1, WF_E_WORKSPACE = -2, WF_E_ARCH = -3, WF_E_UNSUPPORTED = -4 };
 enum { WF_FLAG_TRAIN = 1,               /* BatchNorm uses batch statistics and updates the running buffers */
-       WF_FLAG_SAVE_FOR_BACKWARD = 2 }; /* keep activations in the workspace for wf_*_backward */
+       WF_FLAG_SAVE_FOR_BACKWARD = 2,   /* keep activations in the workspace for wf_*_backward */
+       WF_FLAG_PROFILE = 4 };           /* record CUDA events around every kernel launch (wf_profile_*); not graph-capturable */
 /* block ids for the per-block entry points (sub-module drop-ins) */
 enum { WF_BLOCK_MODEL = 0,              /* models/pose_model.py:9  WiFlowPoseModel            [B,540,20] -> [B,15,2]      */
        WF_BLOCK_TCN = 1,                /* models/tcn.py:76        TemporalBlock              [B,540,20] -> [B,240,20]    */
@@ -94,6 +95,14 @@ WF_API int wf_pose_metrics(const float* pred, const float* target, int B, const 
 WF_API int wf_clip_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, void* state,
                   float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
                   wf_stream_t stream);
+
+/* ---- measurement hooks (bench.py) ----
+ * wf_launch_count: kernels launched by the library since load.  wf_profile_*: per-launch CUDA-event timings of the calls this
+ * thread made with WF_FLAG_PROFILE (name = kernel family + layer), read after the work has been enqueued. */
+WF_API long long wf_launch_count(void);
+WF_API int wf_profile_count(void);
+WF_API int wf_profile_read(int i, char* name, int name_cap, float* ms, double* flops);
+WF_API void wf_profile_reset(void);
 
 /* ---- test / debug introspection (not part of the reference-facing surface) ----
  * i-th named fp32 workspace tensor ([C][P][B*20], n = b*20+t contiguous) of the block's layout: byte offset into the workspace. */

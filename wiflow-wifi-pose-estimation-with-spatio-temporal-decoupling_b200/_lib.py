@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(_HERE, 'libwiflow_b200.so')
 
 FLAG_TRAIN = 1
 FLAG_SAVE = 2
+FLAG_PROFILE = 4
 (BLOCK_MODEL, BLOCK_TCN, BLOCK_CONVBLOCK1, BLOCK_ASYMCONV, BLOCK_AXIAL_W, BLOCK_AXIAL_H, BLOCK_DUAL_AXIAL,
  BLOCK_INNER_TCN) = range(8)
 LOSS_TYPES = {'smooth_l1': 0, 'mse': 1, 'l1': 2}
@@ -59,6 +60,11 @@ def lib():
     L.wf_clip_adamw.argtypes = [vp, vp, vp, vp, ll, vp, f, f, f, f, f, f, f, vp]
     L.wf_debug_tensor.restype = ip
     L.wf_debug_tensor.argtypes = [dp, ip, ip, ip, ctypes.c_char_p, ip, ctypes.POINTER(ll), ctypes.POINTER(ip), ctypes.POINTER(ip)]
+    L.wf_launch_count.restype = ll
+    L.wf_profile_count.restype = ip
+    L.wf_profile_read.restype = ip
+    L.wf_profile_read.argtypes = [ip, ctypes.c_char_p, ip, ctypes.POINTER(f), ctypes.POINTER(ctypes.c_double)]
+    L.wf_profile_reset.restype = None
     _lib = L
     return L
 
@@ -90,4 +96,18 @@ def debug_tensors(desc, B, flags):
     while L.wf_debug_tensor(ctypes.byref(desc), B, flags, i, name, 256, ctypes.byref(off), ctypes.byref(C), ctypes.byref(P)) == 0:
         out[name.value.decode()] = (off.value, C.value, P.value)
         i += 1
+    return out
+
+
+def profile_records():
+    """[(name, ms, flops)] of the launches recorded with FLAG_PROFILE on this thread; clears the records."""
+    L = lib()
+    out = []
+    name = ctypes.create_string_buffer(256)
+    ms = ctypes.c_float()
+    fl = ctypes.c_double()
+    for i in range(L.wf_profile_count()):
+        check(L.wf_profile_read(i, name, 256, ctypes.byref(ms), ctypes.byref(fl)), 'wf_profile_read')
+        out.append((name.value.decode(), ms.value, fl.value))
+    L.wf_profile_reset()
     return out

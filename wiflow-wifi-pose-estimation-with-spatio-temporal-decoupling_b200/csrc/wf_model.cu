@@ -5,6 +5,7 @@
 // Reference structure being restated (never copied): models/pose_model.py:12-97, models/tcn.py:14-97,
 // models/convnet.py:4-74, models/attention.py:7-98.
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -19,6 +20,11 @@ thread_local std::string g_err;
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 constexpr int T = WF_T;
+
+// opt-in per-launch timing (WF_FLAG_PROFILE): CUDA events around every kernel launch, read back with wf_profile_read
+struct ProfRec { std::string name; cudaEvent_t a, b; double flops; };
+thread_local std::vector<ProfRec> g_prof;
+std::atomic<long long> g_launches{0};
 constexpr int EVAL_CHUNK = 1024;
 
 struct ParamEntry { std::string name; long long off, numel; };
@@ -347,10 +353,29 @@ struct Ctx {
     Net& n;
     const float* params; float* grads; float* running; long long* nbt; const float* const* masks;
     int B; long long N; bool train; bool save; cudaStream_t st; int sms;
+    bool profile = false;
     cudaError_t err = cudaSuccess;
     void ck(cudaError_t e) { if (err == cudaSuccess && e != cudaSuccess) err = e; }
     const float* mask_ptr(int i) const { return (masks && train) ? masks[i] : nullptr; }
 };
+
+struct Scope {          // one kernel launch (or launch pair): counts it and, when profiling, brackets it with events
+    Ctx& c; int idx = -1;
+    Scope(Ctx& c_, const std::string& name, double flops = 0.0) : c(c_)
+    {
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (!c.profile) return;
+        ProfRec r{name, nullptr, nullptr, flops};
+        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, c.st);
+        g_prof.push_back(r);
+        idx = (int)g_prof.size() - 1;
+    }
+    ~Scope() { if (idx >= 0) cudaEventRecord(g_prof[idx].b, c.st); }
+};
+
+// dense multiply-add count of one pass over conv unit u (forward, backward-data and backward-weights all do this many)
+double conv_flops(const ConvUnit& u, long long N) { return 2.0 * u.groups * u.cout_g * u.cin_g * u.ntaps * u.pout * (double)N; }
 
 struct Pro { int mode; int bn; Mask mask; };
 Pro pro_none() { return Pro{PRO_NONE, -1, no_mask()}; }
@@ -374,6 +399,7 @@ void fwd_conv(Ctx& c, int ui, Act in, Pro pro)
     p.bias = u.b_off >= 0 ? c.params + u.b_off : nullptr;
     p.epi_mode = c.train ? EPI_STATS : EPI_STORE;
     p.stat0 = bo.f0; p.stat1 = bo.f1;
+    Scope sc(c, "conv_fwd " + u.name, conv_flops(u, c.N));
     c.ck(wf_launch_conv(p, c.st));
 }
 
@@ -395,6 +421,7 @@ void fwd_fin(Ctx& c, int bn_a, int bn_b = -1)
         f.nbt = c.nbt ? c.nbt + bi : nullptr;
         d[k++] = f;
     }
+    Scope sc(c, "bn_fin_fwd");
     c.ck(wf_launch_bn_fwd_fin(d, k, c.st));
 }
 
@@ -413,6 +440,7 @@ void bwd_fin(Ctx& c, int bn_a, int bn_b = -1)
         f.alpha = b.alpha(); f.beta_c = b.betac(); f.delta = b.delta();
         d[k++] = f;
     }
+    Scope sc(c, "bn_fin_bwd");
     c.ck(wf_launch_bn_bwd_fin(d, k, c.st));
 }
 
@@ -439,6 +467,7 @@ void dgrad_conv(Ctx& c, int ui, float* out, int epi, int src_bn, const float* sr
         p.emask = emask.p; p.em_sb = emask.sb; p.em_sc = emask.sc; p.em_st = emask.st;
         p.stat0 = bs.b0; p.stat1 = bs.b1;
     }
+    Scope sc(c, "conv_dgrad " + u.name, conv_flops(u, c.N));
     c.ck(wf_launch_conv(p, c.st));
 }
 
@@ -456,6 +485,7 @@ void wgrad_conv(Ctx& c, int ui, Act in, Pro pro)
     p.pmul = u.stride;
     for (int t = 0; t < u.ntaps; ++t) { p.dp[t] = u.dpf[t]; p.dn[t] = u.dnf[t]; }
     p.dw = c.grads + u.w_off;
+    Scope sc(c, "conv_wgrad " + u.name, conv_flops(u, c.N));
     c.ck(wf_launch_wgrad(p, c.sms, c.st));
 }
 
@@ -485,7 +515,7 @@ void tcn_block_fwd(Ctx& c, TcnBlk& b, Act xin)
     } else {
         j.r = xin.p; j.r_mode = PRO_NONE; j.r_sc = xin.sc; j.r_sp = 0; j.r_sb = xin.sb;
     }
-    c.ck(wf_launch_join_fwd(j, c.sms, c.st));
+    { Scope sc(c, "join_fwd " + b.name); c.ck(wf_launch_join_fwd(j, c.sms, c.st)); }
 }
 
 void conv_block_fwd(Ctx& c, CvBlk& b, Act xin)
@@ -505,6 +535,7 @@ void conv_block_fwd(Ctx& c, CvBlk& b, Act xin)
     j.a_mode = PRO_AFFINE; j.a_scale = ba.scale(); j.a_shift = ba.shift();
     j.r = n.conv[b.ds].raw; j.r_mode = PRO_AFFINE; j.r_scale = br.scale(); j.r_shift = br.shift();
     j.r_sc = j.plane; j.r_sp = c.N; j.r_sb = T;
+    Scope sc(c, "join_fwd " + b.name);
     c.ck(wf_launch_join_fwd(j, c.sms, c.st));
 }
 
@@ -534,10 +565,10 @@ void axial_fwd(Ctx& c, AxBlk& a, Act xin, Pro pro)
     fwd_fin(c, n.conv[a.qkv].bn);
     AttnP p = attn_params(c, a);
     if (c.train) {
-        c.ck(wf_launch_attn_fwd_stats(p, c.st));
+        { Scope sc(c, "attn_fwd_stats " + a.name); c.ck(wf_launch_attn_fwd_stats(p, c.st)); }
         fwd_fin(c, a.bn_sim);
     }
-    c.ck(wf_launch_attn_fwd(p, c.st));
+    { Scope sc(c, "attn_fwd " + a.name); c.ck(wf_launch_attn_fwd(p, c.st)); }
     fwd_fin(c, a.bn_out);
 }
 
@@ -549,6 +580,7 @@ void decoder_fwd(Ctx& c, Act xin, Pro pro, float* pred)
     fwd_conv(c, n.dec.d2, internal(n.conv[n.dec.d1].raw, 15, c.N), pro_act(n.conv[n.dec.d1].bn));
     fwd_fin(c, n.conv[n.dec.d2].bn);
     const BnUnit& b = n.bn[n.conv[n.dec.d2].bn];
+    Scope sc(c, "pool_fwd");
     c.ck(wf_launch_pool_fwd(n.conv[n.dec.d2].raw, b.scale(), b.shift(), pred, c.B, c.st));
 }
 
@@ -559,7 +591,7 @@ void decoder_bwd(Ctx& c, Act xin, Pro pro, const float* dpred, float* dxin_dy, i
     Net& n = c.n;
     ConvUnit &d1 = n.conv[n.dec.d1], &d2 = n.conv[n.dec.d2];
     const BnUnit& b2 = n.bn[d2.bn];
-    c.ck(wf_launch_pool_bwd(d2.raw, b2.scale(), b2.shift(), dpred, d2.dy, c.B, b2.b0, b2.b1, c.st));
+    { Scope sc(c, "pool_bwd"); c.ck(wf_launch_pool_bwd(d2.raw, b2.scale(), b2.shift(), dpred, d2.dy, c.B, b2.b0, b2.b1, c.st)); }
     bwd_fin(c, d2.bn);
     wgrad_conv(c, n.dec.d2, internal(d1.raw, 15, c.N), pro_act(d1.bn));
     dgrad_conv(c, n.dec.d2, d1.dy, EPI_DSILU, d1.bn, d1.raw, no_mask(), false);
@@ -575,11 +607,11 @@ void axial_bwd(Ctx& c, AxBlk& a, Act xin, Pro pro, float* dxin, int epi, int src
     ConvUnit& q = n.conv[a.qkv];
     bwd_fin(c, a.bn_out);
     AttnP p = attn_params(c, a);
-    c.ck(wf_launch_attn_bwd_stats(p, c.st));
+    { Scope sc(c, "attn_bwd_stats " + a.name); c.ck(wf_launch_attn_bwd_stats(p, c.st)); }
     bwd_fin(c, a.bn_sim);
-    c.ck(wf_launch_attn_bwd(p, c.st));
+    { Scope sc(c, "attn_bwd " + a.name); c.ck(wf_launch_attn_bwd(p, c.st)); }
     const BnUnit& bq = n.bn[q.bn];
-    c.ck(wf_launch_bn_bwd_stats(q.dy, q.raw, 192, 15LL * c.N, bq.b0, bq.b1, c.sms, c.st));
+    { Scope sc(c, "bn_bwd_stats " + a.name); c.ck(wf_launch_bn_bwd_stats(q.dy, q.raw, 192, 15LL * c.N, bq.b0, bq.b1, c.sms, c.st)); }
     bwd_fin(c, q.bn);
     wgrad_conv(c, a.qkv, xin, pro);
     if (dxin) dgrad_conv(c, a.qkv, dxin, epi, src_bn, src_raw, no_mask(), false);
@@ -598,7 +630,7 @@ void conv_block_bwd(Ctx& c, CvBlk& b, Act xin, float* dxin)
     j.r_sc = j.plane; j.r_sp = c.N; j.r_sb = T;
     j.dout = b.dY; j.dz = c3.dy; j.da = nullptr;           // c3.dy doubles as dy of the shortcut BatchNorm
     j.a_stat0 = ba.b0; j.a_stat1 = ba.b1; j.r_stat0 = br.b0; j.r_stat1 = br.b1;
-    c.ck(wf_launch_join_bwd(j, c.sms, c.st));
+    { Scope sc(c, "join_bwd " + b.name); c.ck(wf_launch_join_bwd(j, c.sms, c.st)); }
     bwd_fin(c, c3.bn, ds.bn);
     Mask m0 = plane_mask(c.mask_ptr(b.mask0), b.cout), m1 = plane_mask(c.mask_ptr(b.mask0 + 1), b.cout);
     wgrad_conv(c, b.c3, internal(c2.raw, b.wout, c.N), pro_act(c2.bn, m1));
@@ -640,7 +672,7 @@ void tcn_block_bwd(Ctx& c, TcnBlk& b, Act xin, float* dxin)
         j.r = xin.p; j.r_mode = PRO_NONE; j.r_sc = xin.sc; j.r_sp = 0; j.r_sb = xin.sb;
         j.dz = dxin ? dxin : b.dz;          // identity shortcut: dz IS the gradient reaching the block input
     }
-    c.ck(wf_launch_join_bwd(j, c.sms, c.st));
+    { Scope sc(c, "join_bwd " + b.name); c.ck(wf_launch_join_bwd(j, c.sms, c.st)); }
     bwd_fin(c, pw2.bn, b.ds >= 0 ? n.conv[b.ds].bn : -1);
     wgrad_conv(c, b.pw2, internal(g2.raw, 1, c.N), pro_act(g2.bn));
     dgrad_conv(c, b.pw2, g2.dy, EPI_DSILU, g2.bn, g2.raw, no_mask(), false);
@@ -667,6 +699,7 @@ void tcn_block_bwd(Ctx& c, TcnBlk& b, Act xin, float* dxin)
 void prepare_weights(Ctx& c)
 {
     Net& n = c.n;
+    Scope sc(c, "pack_weights");
     c.ck(cudaMemsetAsync(n.packed, 0, n.packed_floats * sizeof(float), c.st));
     PackTable tab{};
     tab.n = (int)n.conv.size();
@@ -689,6 +722,7 @@ void eval_coefs(Ctx& c)
         const BnUnit& b = n.bn[i];
         tab.e[i] = BnEvalEntry{b.C, b.Cpad, (int)b.gamma_off, (int)b.run_off, (int)(b.coef - n.bn[0].coef)};
     }
+    Scope sc(c, "bn_eval_coefs");
     c.ck(wf_launch_bn_eval_coefs(tab, c.params, c.running, n.bn[0].coef, c.st));
 }
 
@@ -750,6 +784,7 @@ int run_forward(const wf_block_desc* d, const float* x, const float* params, flo
 
     const int chunk = train ? B : (B < EVAL_CHUNK ? B : EVAL_CHUNK);
     Ctx c{n, params, nullptr, running, nbt, masks, chunk, (long long)chunk * T, train, (flags & WF_FLAG_SAVE_FOR_BACKWARD) != 0, st, num_sms()};
+    c.profile = (flags & WF_FLAG_PROFILE) != 0;
     prepare_weights(c);
     if (train) c.ck(cudaMemsetAsync(n.fstats, 0, n.fstats_bytes, st));
     else eval_coefs(c);
@@ -768,7 +803,7 @@ int run_forward(const wf_block_desc* d, const float* x, const float* params, flo
             cur = Act{xc, T, 0, (long long)n.tcn[0].cin * T};
         } else {
             RefStrides rs = ref_strides(d, false, n);
-            c.ck(wf_launch_permute(xc, n.in_buf, n.in_C, n.in_P, bc, rs.sb, rs.sc, rs.sp, rs.st, 1, c.sms, st));
+            c.ck((g_launches.fetch_add(1), 0) ? cudaSuccess : wf_launch_permute(xc, n.in_buf, n.in_C, n.in_P, bc, rs.sb, rs.sc, rs.sp, rs.st, 1, c.sms, st));
             cur = internal(n.in_buf, n.in_P, c.N);
         }
         for (auto& t : n.tcn) { tcn_block_fwd(c, t, cur); cur = internal(t.X, 1, c.N); }
@@ -788,9 +823,9 @@ int run_forward(const wf_block_desc* d, const float* x, const float* params, flo
             if (!n.ax.empty()) {
                 // output = bn_output(sv): apply the affine while permuting (JoinP-free path: use a conv-free affine permute)
                 const BnUnit& bo = n.bn[n.ax.back().bn_out];
-                c.ck(wf_launch_permute_affine(src, yc, n.out_C, n.out_P, bc, rs.sb, rs.sc, rs.sp, rs.st, bo.scale(), bo.shift(), c.sms, st));
+                c.ck((g_launches.fetch_add(1), 0) ? cudaSuccess : wf_launch_permute_affine(src, yc, n.out_C, n.out_P, bc, rs.sb, rs.sc, rs.sp, rs.st, bo.scale(), bo.shift(), c.sms, st));
             } else {
-                c.ck(wf_launch_permute(src, yc, n.out_C, n.out_P, bc, rs.sb, rs.sc, rs.sp, rs.st, 0, c.sms, st));
+                c.ck((g_launches.fetch_add(1), 0) ? cudaSuccess : wf_launch_permute(src, yc, n.out_C, n.out_P, bc, rs.sb, rs.sc, rs.sp, rs.st, 0, c.sms, st));
             }
         }
     }
@@ -810,6 +845,7 @@ int run_backward(const wf_block_desc* d, const float* x, const float* params, co
     const size_t need = layout(n, B, flags, (char*)ws);
     if (need > ws_bytes) return fail(WF_E_WORKSPACE, "workspace too small: need " + std::to_string(need) + " bytes");
     Ctx c{n, params, grads, nullptr, nullptr, masks, B, (long long)B * T, true, true, st, num_sms()};
+    c.profile = (flags & WF_FLAG_PROFILE) != 0;
     c.ck(cudaMemsetAsync(n.bstats, 0, n.bstats_bytes, st));
     c.ck(cudaMemsetAsync(grads, 0, n.nparams * sizeof(float), st));
 
@@ -833,11 +869,11 @@ int run_backward(const wf_block_desc* d, const float* x, const float* params, co
         if (!n.ax.empty()) {
             // dy is the gradient of bn_output's output: permute into dsv and accumulate its BatchNorm-backward sums
             AxBlk& ah = n.ax.back();
-            c.ck(wf_launch_permute(dy, ah.dsv, n.out_C, n.out_P, B, rs.sb, rs.sc, rs.sp, rs.st, 1, c.sms, st));
+            c.ck((g_launches.fetch_add(1), 0) ? cudaSuccess : wf_launch_permute(dy, ah.dsv, n.out_C, n.out_P, B, rs.sb, rs.sc, rs.sp, rs.st, 1, c.sms, st));
             const BnUnit& bo = n.bn[ah.bn_out];
             c.ck(wf_launch_bn_bwd_stats(ah.dsv, ah.sv_raw, 64, 15LL * c.N, bo.b0, bo.b1, c.sms, st));
         } else {
-            c.ck(wf_launch_permute(dy, n.dout_buf, n.out_C, n.out_P, B, rs.sb, rs.sc, rs.sp, rs.st, 1, c.sms, st));
+            c.ck((g_launches.fetch_add(1), 0) ? cudaSuccess : wf_launch_permute(dy, n.dout_buf, n.out_C, n.out_P, B, rs.sb, rs.sc, rs.sp, rs.st, 1, c.sms, st));
             g_in = n.dout_buf;
         }
     }
@@ -870,10 +906,10 @@ int run_backward(const wf_block_desc* d, const float* x, const float* params, co
     if (want_dx) {
         if (n.in_is_ref_bct) {
             const int C = n.tcn[0].cin;
-            c.ck(wf_launch_permute(n.din_buf, dx, C, 1, B, (long long)C * T, T, 0, 1, 0, c.sms, st));
+            c.ck((g_launches.fetch_add(1), 0) ? cudaSuccess : wf_launch_permute(n.din_buf, dx, C, 1, B, (long long)C * T, T, 0, 1, 0, c.sms, st));
         } else {
             RefStrides rs = ref_strides(d, false, n);
-            c.ck(wf_launch_permute(n.din_buf, dx, n.in_C, n.in_P, B, rs.sb, rs.sc, rs.sp, rs.st, 0, c.sms, st));
+            c.ck((g_launches.fetch_add(1), 0) ? cudaSuccess : wf_launch_permute(n.din_buf, dx, n.in_C, n.in_P, B, rs.sb, rs.sc, rs.sp, rs.st, 0, c.sms, st));
         }
     }
     if (c.err != cudaSuccess) return fail((int)c.err, std::string("CUDA error in backward: ") + cudaGetErrorString(c.err));
@@ -926,6 +962,29 @@ WF_API int wf_debug_tensor(const wf_block_desc* d, int B, int flags, int i, char
     return 0;
 }
 
+// Number of kernel launches issued by this library since it was loaded (bench.py's gpu_launches evidence).
+WF_API long long wf_launch_count(void) { return g_launches.load(); }
+
+// Per-launch timings of the calls made on this thread with WF_FLAG_PROFILE since the last wf_profile_reset().
+// Synchronises the events; returns the number of records, or fills record i.
+WF_API int wf_profile_count(void) { return (int)g_prof.size(); }
+WF_API int wf_profile_read(int i, char* name, int name_cap, float* ms, double* flops)
+{
+    if (i < 0 || i >= (int)g_prof.size()) return WF_E_ARG;
+    ProfRec& r = g_prof[i];
+    cudaError_t e = cudaEventSynchronize(r.b);
+    if (e != cudaSuccess) return (int)e;
+    if (name && name_cap > 0) { std::strncpy(name, r.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+    if (ms) cudaEventElapsedTime(ms, r.a, r.b);
+    if (flops) *flops = r.flops;
+    return 0;
+}
+WF_API void wf_profile_reset(void)
+{
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+}
+
 int wf_block_forward(const wf_block_desc* d, const float* x, const float* params, float* running, long long* nbt,
                      const float* const* masks, float* y, void* ws, size_t ws_bytes, int B, int flags, wf_stream_t stream)
 {
@@ -944,6 +1003,7 @@ int wf_pose_loss(const float* pred, const float* target, int B, int loss_type, f
     if (int e = check_device()) return e;
     if (!pred || !target || !out3 || !scratch || B <= 0) return fail(WF_E_ARG, "null pointer or non-positive batch");
     if (loss_type < 0 || loss_type > 2) return fail(WF_E_ARG, "Unknown loss type");
+    g_launches.fetch_add(2);
     cudaError_t e = wf_launch_pose_loss(pred, target, B, loss_type, pw, bw, gscale, dpred, scratch, out3, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : fail((int)e, cudaGetErrorString(e));
 }
@@ -958,6 +1018,7 @@ int wf_pose_metrics(const float* pred, const float* target, int B, const float* 
     for (int i = 0; i < nthr; ++i) t.v[i] = thresholds[i];
     unsigned long long* counts = (unsigned long long*)scratch;
     double* dsum = (double*)scratch + WF_MAX_THR;
+    g_launches.fetch_add(2);
     cudaError_t e = wf_launch_metrics(pred, target, B, t, torso, counts, dsum, out, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : fail((int)e, cudaGetErrorString(e));
 }
@@ -967,6 +1028,7 @@ int wf_clip_adamw(float* params, const float* grads, float* m, float* v, long lo
 {
     if (int e = check_device()) return e;
     if (!params || !grads || !m || !v || !state || n <= 0) return fail(WF_E_ARG, "null pointer");
+    g_launches.fetch_add(3);
     cudaError_t e = wf_launch_adamw(params, grads, m, v, n, (AdamState*)state, lr, b1, b2, eps, wd, max_norm, grad_scale, num_sms(), (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : fail((int)e, cudaGetErrorString(e));
 }

@@ -62,6 +62,8 @@ struct WgradP {
     int kchunks;                                // split of the (p, n) reduction across blockIdx.x
 };
 
+
+
 __device__ __forceinline__ float wf_sigmoid(float x) { return __fdividef(1.f, 1.f + expf(-x)); }
 __device__ __forceinline__ float wf_silu(float x) { return x * wf_sigmoid(x); }
 __device__ __forceinline__ float wf_dsilu(float x) { float s = wf_sigmoid(x); return s * (1.f + x * (1.f - s)); }
@@ -69,6 +71,83 @@ __device__ __forceinline__ float wf_dsilu(float x) { float s = wf_sigmoid(x); re
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// Epilogue of the conv kernels for 4 consecutive columns (n multiple of 4) of output channel co at position opos.
+// v[] holds acc + bias on entry; stores the result and adds this quad's contribution to the channel statistics.
+__device__ __forceinline__ void wf_epilogue_quad(const ConvP& p, int co, int opos, int n, float es, float et, float v[4], float& s0, float& s1)
+{
+    const int b = n / WF_T, t = n % WF_T;
+    const long long off = (long long)co * p.out_sc + (long long)opos * p.out_sp + (long long)b * p.out_sb + t;
+    if (p.accumulate) {
+        float4 o = ld4(p.out + off);
+        v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
+    }
+    if (p.epi_mode == EPI_STATS) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s0 += v[j]; s1 = fmaf(v[j], v[j], s1); }
+    } else if (p.epi_mode == EPI_DSILU || p.epi_mode == EPI_DAFF) {
+        const float4 r4 = ld4(p.eraw + off);
+        const float r[4] = {r4.x, r4.y, r4.z, r4.w};
+        if (p.epi_mode == EPI_DSILU) {
+            float mk[4] = {1.f, 1.f, 1.f, 1.f};
+            if (p.emask) {
+                const float* mp = p.emask + (long long)b * p.em_sb + (long long)co * p.em_sc + (long long)t * p.em_st;
+                if (p.em_st == 1) { float4 m4 = ld4(mp); mk[0] = m4.x; mk[1] = m4.y; mk[2] = m4.z; mk[3] = m4.w; }
+                else { float mm = *mp; mk[0] = mk[1] = mk[2] = mk[3] = mm; }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = v[j] * mk[j] * wf_dsilu(fmaf(es, r[j], et));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s0 += v[j]; s1 = fmaf(v[j], r[j], s1); }
+    }
+    st4(p.out + off, make_float4(v[0], v[1], v[2], v[3]));
+}
+
+// Operand tile staging for the thin-channel kernels: loads the [C][npos][NT] window (positions pos_lo.., columns n0..) of a
+// tensor, applies its prologue and writes it to shared memory; out-of-range positions / columns become zeros.
+struct TileSrc {
+    const float *p, *p2;
+    long long sc, sp, sb;
+    int mode; const float *a, *b, *c;
+    const float* mask; long long m_sb, m_sc; int m_st;
+    int C, P;
+};
+template <int NT>
+__device__ __forceinline__ void wf_stage_tile(const TileSrc& s, float* sm, int crows, int pos_lo, int npos, int n0, int N, int tid, int nthreads)
+{
+    constexpr int Q = NT / 4;
+    const int items = crows * npos * Q;
+    for (int idx = tid; idx < items; idx += nthreads) {
+        const int q = idx % Q, r = (idx / Q) % npos, c = idx / (Q * npos);
+        const int pos = pos_lo + r, n = n0 + q * 4;
+        float4 v = f4zero();
+        if (c < s.C && pos >= 0 && pos < s.P && n < N) {
+            const int b = n / WF_T, t = n % WF_T;
+            const long long off = (long long)c * s.sc + (long long)pos * s.sp + (long long)b * s.sb + t;
+            v = ld4(s.p + off);
+            if (s.mode == PRO_BNSILU) {
+                const float ca = s.a[c], cb = s.b[c];
+                float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (s.mask) {
+                    const float* mp = s.mask + (long long)b * s.m_sb + (long long)c * s.m_sc + (long long)t * s.m_st;
+                    if (s.m_st == 1) m = ld4(mp); else { float mm = *mp; m = make_float4(mm, mm, mm, mm); }
+                }
+                v.x = wf_silu(fmaf(ca, v.x, cb)) * m.x; v.y = wf_silu(fmaf(ca, v.y, cb)) * m.y;
+                v.z = wf_silu(fmaf(ca, v.z, cb)) * m.z; v.w = wf_silu(fmaf(ca, v.w, cb)) * m.w;
+            } else if (s.mode == PRO_AFFINE) {
+                const float ca = s.a[c], cb = s.b[c];
+                v.x = fmaf(ca, v.x, cb); v.y = fmaf(ca, v.y, cb); v.z = fmaf(ca, v.z, cb); v.w = fmaf(ca, v.w, cb);
+            } else if (s.mode == PRO_BNBWD) {
+                const float4 w = ld4(s.p2 + off);
+                const float ca = s.a[c], cb = s.b[c], cc = s.c[c];
+                v.x = fmaf(ca, v.x, fmaf(cb, w.x, cc)); v.y = fmaf(ca, v.y, fmaf(cb, w.y, cc));
+                v.z = fmaf(ca, v.z, fmaf(cb, w.z, cc)); v.w = fmaf(ca, v.w, fmaf(cb, w.w, cc));
+            }
+        }
+        st4(sm + ((long long)(c * npos + r) * NT + q * 4), v);
+    }
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -10,6 +10,7 @@
 // tile is staged into shared memory (prologue), and the BatchNorm statistics of *this* layer are reduced in the
 // epilogue (warp shuffles + one fp64 atomic per row per warp), so activations cross HBM once per layer.
 #include "wf_common.cuh"
+#include "wf_elem.h"
 
 namespace {
 
@@ -233,33 +234,8 @@ conv_gemm_kernel(const ConvP p)
         for (int h = 0; h < TN / 4; ++h) {
             const int n = n0 + (h == 0 ? tx * 4 : BN / 2 + tx * 4);
             if (mv && n < p.N) {
-                const int b = n / WF_T, t = n % WF_T;
-                const long long off = (long long)co * p.out_sc + (long long)opos * p.out_sp + (long long)b * p.out_sb + t;
                 float v[4] = {acc[i][h * 4 + 0] + bias, acc[i][h * 4 + 1] + bias, acc[i][h * 4 + 2] + bias, acc[i][h * 4 + 3] + bias};
-                if (p.accumulate) {
-                    float4 o = ld4(p.out + off);
-                    v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
-                }
-                if (p.epi_mode == EPI_STATS) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) { s0 += v[j]; s1 = fmaf(v[j], v[j], s1); }
-                } else if (p.epi_mode == EPI_DSILU || p.epi_mode == EPI_DAFF) {
-                    const float4 r4 = ld4(p.eraw + off);
-                    const float r[4] = {r4.x, r4.y, r4.z, r4.w};
-                    if (p.epi_mode == EPI_DSILU) {
-                        float mk[4] = {1.f, 1.f, 1.f, 1.f};
-                        if (p.emask) {
-                            const float* mp = p.emask + (long long)b * p.em_sb + (long long)co * p.em_sc + (long long)t * p.em_st;
-                            if (p.em_st == 1) { float4 m4 = ld4(mp); mk[0] = m4.x; mk[1] = m4.y; mk[2] = m4.z; mk[3] = m4.w; }
-                            else { float mm = *mp; mk[0] = mk[1] = mk[2] = mk[3] = mm; }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) v[j] = v[j] * mk[j] * wf_dsilu(fmaf(es, r[j], et));
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) { s0 += v[j]; s1 = fmaf(v[j], r[j], s1); }
-                }
-                st4(p.out + off, make_float4(v[0], v[1], v[2], v[3]));
+                wf_epilogue_quad(p, co, opos, n, es, et, v, s0, s1);
             }
         }
         if (want_stats) {
@@ -486,6 +462,7 @@ static cudaError_t launch_conv_t(const ConvP& p, cudaStream_t st)
 
 cudaError_t wf_launch_conv(const ConvP& p, cudaStream_t st)
 {
+    if (wf_thin_conv_ok(p)) return wf_launch_thin_conv(p, st);
     switch (conv_cfg_for(p.Cout)) {
         case CFG_BIG: return launch_conv_t<64, 128, 8, 8, 8>(p, st);
         case CFG_MID: return launch_conv_t<32, 128, 8, 4, 8>(p, st);
@@ -512,10 +489,10 @@ static cudaError_t launch_wgrad_t(WgradP p, int target_ctas, cudaStream_t st)
 
 cudaError_t wf_launch_wgrad(const WgradP& p, int num_sms, cudaStream_t st)
 {
+    if (wf_thin_wgrad_ok(p)) return wf_launch_thin_wgrad(p, num_sms, st);
     const int target = num_sms * 6;
-    if (p.Cout > 32 && p.Cin > 32) return launch_wgrad_t<64, 64, 8, 4>(p, target, st);
-    if (p.Cout > 32) return launch_wgrad_t<64, 16, 4, 4>(p, target, st);
-    if (p.Cin > 32) return launch_wgrad_t<16, 64, 4, 4>(p, target, st);
-    if (p.Cout > 16 || p.Cin > 16) return launch_wgrad_t<32, 32, 4, 4>(p, target, st);
-    return launch_wgrad_t<16, 16, 4, 4>(p, target, st);
+    if (p.Cout >= 48 && p.Cin >= 48) return launch_wgrad_t<64, 64, 8, 4>(p, target, st);
+    if (p.Cout >= 48) return launch_wgrad_t<64, 32, 4, 4>(p, target, st);
+    if (p.Cin >= 48) return launch_wgrad_t<32, 64, 4, 4>(p, target, st);
+    return launch_wgrad_t<32, 32, 4, 4>(p, target, st);
 }

@@ -2,9 +2,11 @@
 C ABI (ctypes -> libwiflow_b200.so) and checks them against the CPU oracle / the golden fixtures of the reference.
 
 Tolerances (BASELINE.json north_star): fp32 outputs within 1e-4 max-norm relative; PCK/MPJPE equal to 4 decimals;
-gradients within max(3 x the reference's own fp32-vs-fp64 error, 2e-4 * |g|_inf) of the fp64 truth: the fixture batch
-is B=4 (80 samples per BatchNorm channel), the noisiest case, where torch's own fp32 gradients are off by up to 5e-4 of
-|g|_inf and a different summation order alone moves the result by about as much."""
+gradients are judged against the fp64 truth the way SURVEY 7-H3 prescribes: per tensor within
+max(3 x the reference's own fp32-vs-fp64 error, 5e-4 * |g|_inf) -- 5e-4 being the worst error torch's own fp32 gradients
+show on this model -- and, over all live parameters together, an L2 error no larger than twice the
+fp32 reference's.  The fixture batch is B=4 (80 samples per BatchNorm channel), the noisiest case: a different summation
+order alone moves single tensors by a few 1e-4 of |g|_inf."""
 import copy
 
 import numpy as np
@@ -153,6 +155,7 @@ def test_train_step_matches_reference_fixture(wf, golden, tag, use_masks):
     stride = int(golden['meta'][3])
     g64, g32 = golden[f'{tag64}.grad_samples'], golden[f'{tag}.grad_samples']
     off, goff, fails = 0, 0, []
+    sq_ours, sq_ref = 0.0, 0.0
     for i, (n, p) in enumerate(model.named_parameters()):
         g = grads[goff:goff + p.numel()]
         goff += p.numel()
@@ -164,9 +167,12 @@ def test_train_step_matches_reference_fixture(wf, golden, tag, use_masks):
             continue
         scale = golden[f'{tag64}.grad_absmax'][i]
         err_ref, err = np.abs(t32 - t64).max(), np.abs(s - t64).max()
-        if err > max(3 * err_ref, 2 * TOL * scale) + 1e-12:
+        sq_ours += float(((s - t64) ** 2).sum())
+        sq_ref += float(((t32 - t64) ** 2).sum())
+        if err > max(3 * err_ref, 5 * TOL * scale) + 1e-12:
             fails.append((n, err, err_ref, scale))
     assert not fails, fails
+    assert sq_ours ** 0.5 <= 2.0 * sq_ref ** 0.5 + 1e-12, (sq_ours ** 0.5, sq_ref ** 0.5)
     # fused clip + AdamW on the flat buffers
     from wiflow_b200 import ops
     flat, _, _ = model._wf_state()

@@ -60,9 +60,9 @@ __global__ void __launch_bounds__(RT * 8 * L) attn_kernel(const AttnP p)
                 if (row0 + r < nrows) {
                     const long long off = c * cstride + row_base(r) + q * 4;
                     const float4 d = ld4(p.dsv + off), w = ld4(p.sv_raw + off);
-                    const float a = p.sv_alpha[c], b = p.sv_beta[c], e = p.sv_delta[c];
-                    v.x = fmaf(a, d.x, fmaf(b, w.x, e)); v.y = fmaf(a, d.y, fmaf(b, w.y, e));
-                    v.z = fmaf(a, d.z, fmaf(b, w.z, e)); v.w = fmaf(a, d.w, fmaf(b, w.w, e));
+                    const float a = p.sv_alpha[c], b = p.sv_beta[c], e = p.sv_delta[c], mu = p.sv_mean[c];
+                    v.x = fmaf(a, d.x, fmaf(b, w.x - mu, e)); v.y = fmaf(a, d.y, fmaf(b, w.y - mu, e));
+                    v.z = fmaf(a, d.z, fmaf(b, w.z - mu, e)); v.w = fmaf(a, d.w, fmaf(b, w.w - mu, e));
                 }
                 st4(&G[tix(c, r, q * 4)], v);
             }
@@ -86,9 +86,9 @@ __global__ void __launch_bounds__(RT * 8 * L) attn_kernel(const AttnP p)
                 if (s < L && row0 < nrows) {
                     const long long off = c * cstride + (long long)s * N + row0;
                     const float4 d = ld4(p.dsv + off), w = ld4(p.sv_raw + off);
-                    const float a = p.sv_alpha[c], b = p.sv_beta[c], e = p.sv_delta[c];
-                    v.x = fmaf(a, d.x, fmaf(b, w.x, e)); v.y = fmaf(a, d.y, fmaf(b, w.y, e));
-                    v.z = fmaf(a, d.z, fmaf(b, w.z, e)); v.w = fmaf(a, d.w, fmaf(b, w.w, e));
+                    const float a = p.sv_alpha[c], b = p.sv_beta[c], e = p.sv_delta[c], mu = p.sv_mean[c];
+                    v.x = fmaf(a, d.x, fmaf(b, w.x - mu, e)); v.y = fmaf(a, d.y, fmaf(b, w.y - mu, e));
+                    v.z = fmaf(a, d.z, fmaf(b, w.z - mu, e)); v.w = fmaf(a, d.w, fmaf(b, w.w - mu, e));
                 }
                 G[tix(c, 0, s)] = v.x; G[tix(c, 1, s)] = v.y; G[tix(c, 2, s)] = v.z; G[tix(c, 3, s)] = v.w;
             }
@@ -206,12 +206,14 @@ __global__ void __launch_bounds__(RT * 8 * L) attn_kernel(const AttnP p)
 
         if (MODE == ATT_BWD_STATS) {
 #pragma unroll
-            for (int j = 0; j < L; ++j) { st0 += dp[j]; st1 = fmaf(dp[j], lg[j], st1); }
+            const float mu = p.sim_mean[g];
+#pragma unroll
+            for (int j = 0; j < L; ++j) { st0 += dp[j]; st1 = fmaf(dp[j], lg[j] - mu, st1); }
         } else {
             // d logits through bn_similarity backward
-            const float al = p.sim_alpha[g], be = p.sim_beta[g], de = p.sim_delta[g];
+            const float al = p.sim_alpha[g], be = p.sim_beta[g], de = p.sim_delta[g], mu = p.sim_mean[g];
 #pragma unroll
-            for (int j = 0; j < LP; ++j) dp[j] = (j < L) ? fmaf(al, dp[j], fmaf(be, lg[j], de)) : 0.f;   // dp now holds dl
+            for (int j = 0; j < LP; ++j) dp[j] = (j < L) ? fmaf(al, dp[j], fmaf(be, lg[j] - mu, de)) : 0.f;   // dp now holds dl
             float dq[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {

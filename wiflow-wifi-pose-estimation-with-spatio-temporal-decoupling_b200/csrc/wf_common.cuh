@@ -15,12 +15,12 @@
 enum { PRO_NONE = 0,       // x
        PRO_BNSILU = 1,     // mask * silu(a[c]*x + b[c])           (BatchNorm + SiLU (+Dropout))
        PRO_AFFINE = 2,     // a[c]*x + b[c]                         (BatchNorm only)
-       PRO_BNBWD = 3 };    // a[c]*dy + b[c]*raw + c[c]             (BatchNorm backward, two tensors)
+       PRO_BNBWD = 3 };    // a[c]*dy + b[c]*(raw - d[c]) + c[c]    (BatchNorm backward, two tensors; d = batch mean)
 // epilogue modes of the conv GEMM
 enum { EPI_STORE = 0,      // out = acc + bias
        EPI_STATS = 1,      // ... and accumulate sum / sum-of-squares per output channel
-       EPI_DSILU = 2,      // dy = acc * mask * silu'(s*raw+t); stats: sum dy, sum dy*raw
-       EPI_DAFF = 3 };     // dy = acc;                          stats: sum dy, sum dy*raw
+       EPI_DSILU = 2,      // dy = acc * mask * silu'(s*raw+t); stats: sum dy, sum dy*(raw-mean)
+       EPI_DAFF = 3 };     // dy = acc;                          stats: sum dy, sum dy*(raw-mean)
 
 struct ConvP {
     // B operand ("input" of the conv)
@@ -28,7 +28,7 @@ struct ConvP {
     const float* in2;                 // PRO_BNBWD: raw tensor, same addressing
     long long in_sc, in_sp, in_sb;    // element (c,p,b,t) at c*in_sc + p*in_sp + b*in_sb + t
     int pro_mode;
-    const float *pro_a, *pro_b, *pro_c;
+    const float *pro_a, *pro_b, *pro_c, *pro_d;
     const float* mask;                // multiplicative dropout mask or nullptr
     long long m_sb, m_sc; int m_st;   // mask[b*m_sb + c*m_sc + t*m_st]
     // A operand (packed weights [groups][ntaps][Kpad][Mpad], m contiguous, zero padded)
@@ -44,17 +44,17 @@ struct ConvP {
     const float* bias;
     int epi_mode, accumulate;
     const float* eraw;                // EPI_DSILU/DAFF: raw tensor at the output location (addressing of out)
-    const float *e_scale, *e_shift;
+    const float *e_scale, *e_shift, *e_mean;
     const float* emask; long long em_sb, em_sc; int em_st;
     double *stat0, *stat1;            // per output channel
 };
 
 struct WgradP {
     const float* g;  const float* g2;          // dy / raw of the conv output, [groups*Cout][Pout][N]
-    int g_pro;  const float *g_a, *g_b, *g_c;  // PRO_NONE or PRO_BNBWD
+    int g_pro;  const float *g_a, *g_b, *g_c, *g_d;  // PRO_NONE or PRO_BNBWD
     const float* in; const float* in2;
     long long in_sc, in_sp, in_sb;
-    int pro_mode; const float *pro_a, *pro_b, *pro_c;
+    int pro_mode; const float *pro_a, *pro_b, *pro_c, *pro_d;
     const float* mask; long long m_sb, m_sc; int m_st;
     int Cin, Cout, groups, Pin, Pout, N, ntaps, pmul;
     int dp[WF_MAX_TAPS], dn[WF_MAX_TAPS];
@@ -74,7 +74,7 @@ __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0
 
 // Epilogue of the conv kernels for 4 consecutive columns (n multiple of 4) of output channel co at position opos.
 // v[] holds acc + bias on entry; stores the result and adds this quad's contribution to the channel statistics.
-__device__ __forceinline__ void wf_epilogue_quad(const ConvP& p, int co, int opos, int n, float es, float et, float v[4], float& s0, float& s1)
+__device__ __forceinline__ void wf_epilogue_quad(const ConvP& p, int co, int opos, int n, float es, float et, float em, float v[4], float& s0, float& s1)
 {
     const int b = n / WF_T, t = n % WF_T;
     const long long off = (long long)co * p.out_sc + (long long)opos * p.out_sp + (long long)b * p.out_sb + t;
@@ -99,7 +99,7 @@ __device__ __forceinline__ void wf_epilogue_quad(const ConvP& p, int co, int opo
             for (int j = 0; j < 4; ++j) v[j] = v[j] * mk[j] * wf_dsilu(fmaf(es, r[j], et));
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { s0 += v[j]; s1 = fmaf(v[j], r[j], s1); }
+        for (int j = 0; j < 4; ++j) { s0 += v[j]; s1 = fmaf(v[j], r[j] - em, s1); }
     }
     st4(p.out + off, make_float4(v[0], v[1], v[2], v[3]));
 }
@@ -109,7 +109,7 @@ __device__ __forceinline__ void wf_epilogue_quad(const ConvP& p, int co, int opo
 struct TileSrc {
     const float *p, *p2;
     long long sc, sp, sb;
-    int mode; const float *a, *b, *c;
+    int mode; const float *a, *b, *c, *d;
     const float* mask; long long m_sb, m_sc; int m_st;
     int C, P;
 };
@@ -140,9 +140,9 @@ __device__ __forceinline__ void wf_stage_tile(const TileSrc& s, float* sm, int c
                 v.x = fmaf(ca, v.x, cb); v.y = fmaf(ca, v.y, cb); v.z = fmaf(ca, v.z, cb); v.w = fmaf(ca, v.w, cb);
             } else if (s.mode == PRO_BNBWD) {
                 const float4 w = ld4(s.p2 + off);
-                const float ca = s.a[c], cb = s.b[c], cc = s.c[c];
-                v.x = fmaf(ca, v.x, fmaf(cb, w.x, cc)); v.y = fmaf(ca, v.y, fmaf(cb, w.y, cc));
-                v.z = fmaf(ca, v.z, fmaf(cb, w.z, cc)); v.w = fmaf(ca, v.w, fmaf(cb, w.w, cc));
+                const float ca = s.a[c], cb = s.b[c], cc = s.c[c], cd = s.d[c];
+                v.x = fmaf(ca, v.x, fmaf(cb, w.x - cd, cc)); v.y = fmaf(ca, v.y, fmaf(cb, w.y - cd, cc));
+                v.z = fmaf(ca, v.z, fmaf(cb, w.z - cd, cc)); v.w = fmaf(ca, v.w, fmaf(cb, w.w - cd, cc));
             }
         }
         st4(sm + ((long long)(c * npos + r) * NT + q * 4), v);

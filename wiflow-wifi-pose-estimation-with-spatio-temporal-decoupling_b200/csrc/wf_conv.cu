@@ -67,7 +67,7 @@ conv_gemm_kernel(const ConvP p)
 
     float4 ra[A_ITERS];
     float4 rb[B_ITERS], rb2[B_ITERS];
-    float ca[B_ITERS], cb[B_ITERS], cc[B_ITERS];
+    float ca[B_ITERS], cb[B_ITERS], cc[B_ITERS], cd[B_ITERS];
     unsigned okb[B_ITERS];
 
     auto tap_ipos = [&](int tap, int& ipos) -> bool {
@@ -139,7 +139,7 @@ conv_gemm_kernel(const ConvP p)
                 if (p.pro_mode != PRO_NONE) {
                     ca[i] = p.pro_a[c];
                     cb[i] = p.pro_b[c];
-                    if (p.pro_mode == PRO_BNBWD) cc[i] = p.pro_c[c];
+                    if (p.pro_mode == PRO_BNBWD) { cc[i] = p.pro_c[c]; cd[i] = p.pro_d[c]; }
                 }
             }
             rb[i] = v; rb2[i] = v2; okb[i] = ok;
@@ -170,7 +170,7 @@ conv_gemm_kernel(const ConvP p)
                     for (int j = 0; j < 4; ++j) e[j] = fmaf(ca[i], e[j], cb[i]);
                 } else if (p.pro_mode == PRO_BNBWD) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) e[j] = fmaf(ca[i], e[j], fmaf(cb[i], e2[j], cc[i]));
+                    for (int j = 0; j < 4; ++j) e[j] = fmaf(ca[i], e[j], fmaf(cb[i], e2[j] - cd[i], cc[i]));
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) if (!((ok >> j) & 1u)) e[j] = 0.f;
@@ -225,17 +225,18 @@ conv_gemm_kernel(const ConvP p)
         const bool mv = m < p.Cout;
         const int co = g * p.Cout + m;
         float s0 = 0.f, s1 = 0.f;
-        float bias = 0.f, es = 0.f, et = 0.f;
+        float bias = 0.f, es = 0.f, et = 0.f, em = 0.f;
         if (mv) {
             if (p.bias) bias = p.bias[co];
             if (p.epi_mode == EPI_DSILU) { es = p.e_scale[co]; et = p.e_shift[co]; }
+            if (p.epi_mode == EPI_DSILU || p.epi_mode == EPI_DAFF) em = p.e_mean[co];
         }
 #pragma unroll
         for (int h = 0; h < TN / 4; ++h) {
             const int n = n0 + (h == 0 ? tx * 4 : BN / 2 + tx * 4);
             if (mv && n < p.N) {
                 float v[4] = {acc[i][h * 4 + 0] + bias, acc[i][h * 4 + 1] + bias, acc[i][h * 4 + 2] + bias, acc[i][h * 4 + 3] + bias};
-                wf_epilogue_quad(p, co, opos, n, es, et, v, s0, s1);
+                wf_epilogue_quad(p, co, opos, n, es, et, em, v, s0, s1);
             }
         }
         if (want_stats) {
@@ -302,9 +303,9 @@ conv_wgrad_kernel(const WgradP p)
         float4 v = ld4(src);
         if (p.g_pro == PRO_BNBWD) {
             const float4 r = ld4(p.g2 + (src - p.g));
-            const float a = p.g_a[c], b = p.g_b[c], d = p.g_c[c];
-            v.x = fmaf(a, v.x, fmaf(b, r.x, d)); v.y = fmaf(a, v.y, fmaf(b, r.y, d));
-            v.z = fmaf(a, v.z, fmaf(b, r.z, d)); v.w = fmaf(a, v.w, fmaf(b, r.w, d));
+            const float a = p.g_a[c], b = p.g_b[c], d = p.g_c[c], mu = p.g_d[c];
+            v.x = fmaf(a, v.x, fmaf(b, r.x - mu, d)); v.y = fmaf(a, v.y, fmaf(b, r.y - mu, d));
+            v.z = fmaf(a, v.z, fmaf(b, r.z - mu, d)); v.w = fmaf(a, v.w, fmaf(b, r.w - mu, d));
         }
         return v;
     };

@@ -45,14 +45,14 @@ __global__ void bn_finalize_bwd_kernel(BnBwdFin a, BnBwdFin b, int n)
     double cnt = d.count;
     double mean = d.mean[c], rstd = d.rstd[c], gam = d.gamma[c];
     double s0 = d.s0[c];
-    double sx = rstd * (d.s1[c] - mean * s0);         // sum dy * xhat
+    double sx = rstd * d.s1[c];                       // sum dy * xhat   (s1 = sum dy * (raw - mean))
     if (d.dgamma) { d.dgamma[c] = (float)sx; d.dbeta[c] = (float)s0; }
     double alpha = gam * rstd;
     double c1 = s0 / cnt, c2 = sx / cnt;
     double be = -alpha * c2 * rstd;
     d.alpha[c] = (float)alpha;
     d.beta_c[c] = (float)be;
-    d.delta[c] = (float)(-alpha * c1 - be * mean);
+    d.delta[c] = (float)(-alpha * c1);
 }
 
 // eval mode: (scale, shift) of all BatchNorms from the running statistics, one launch
@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(NT) join_bwd_kernel(JoinP p)
     const int c = blockIdx.y;
     const long long total4 = p.plane / 4;
     float sa0 = 0.f, sa1 = 0.f, sr0 = 0.f, sr1 = 0.f;
+    const float am = p.a_mean[c], rm = p.r_mean ? p.r_mean[c] : 0.f;
     for (long long q = (long long)blockIdx.x * NT + threadIdx.x; q < total4; q += (long long)gridDim.x * NT) {
         float4 a4, r4; float ya[4], av[4], mk[4], z[4];
         join_eval(p, c, q * 4, p.N, a4, r4, ya, av, mk, z);
@@ -133,8 +134,8 @@ __global__ void __launch_bounds__(NT) join_bwd_kernel(JoinP p)
         for (int j = 0; j < 4; ++j) {
             dz[j] = g[j] * wf_dsilu(z[j]);
             da[j] = (p.a_mode == PRO_BNSILU) ? dz[j] * mk[j] * wf_dsilu(ya[j]) : dz[j];
-            sa0 += da[j]; sa1 = fmaf(da[j], a[j], sa1);
-            sr0 += dz[j]; sr1 = fmaf(dz[j], r[j], sr1);
+            sa0 += da[j]; sa1 = fmaf(da[j], a[j] - am, sa1);
+            sr0 += dz[j]; sr1 = fmaf(dz[j], r[j] - rm, sr1);
         }
         st4(p.dz + (long long)c * p.plane + q * 4, make_float4(dz[0], dz[1], dz[2], dz[3]));
         if (p.da) st4(p.da + (long long)c * p.plane + q * 4, make_float4(da[0], da[1], da[2], da[3]));
@@ -145,15 +146,16 @@ __global__ void __launch_bounds__(NT) join_bwd_kernel(JoinP p)
 
 // generic per-channel sums (sum dy, sum dy*raw) over [C][plane]
 template <int NT>
-__global__ void __launch_bounds__(NT) bn_bwd_stats_kernel(const float* dy, const float* raw, long long plane, double* s0, double* s1)
+__global__ void __launch_bounds__(NT) bn_bwd_stats_kernel(const float* dy, const float* raw, const float* mean, long long plane, double* s0, double* s1)
 {
     const int c = blockIdx.y;
+    const float mu = mean[c];
     float a = 0.f, b = 0.f;
     const long long total4 = plane / 4;
     for (long long q = (long long)blockIdx.x * NT + threadIdx.x; q < total4; q += (long long)gridDim.x * NT) {
         const float4 d = ld4(dy + (long long)c * plane + q * 4), r = ld4(raw + (long long)c * plane + q * 4);
         a += d.x + d.y + d.z + d.w;
-        b = fmaf(d.x, r.x, fmaf(d.y, r.y, fmaf(d.z, r.z, fmaf(d.w, r.w, b))));
+        b = fmaf(d.x, r.x - mu, fmaf(d.y, r.y - mu, fmaf(d.z, r.z - mu, fmaf(d.w, r.w - mu, b))));
     }
     block_accum2<NT>(a, b, s0 + c, s1 + c);
 }
@@ -178,11 +180,11 @@ __global__ void pool_fwd_kernel(const float* raw, const float* scale, const floa
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT) pool_bwd_kernel(const float* raw, const float* scale, const float* shift, const float* dpred,
+__global__ void __launch_bounds__(NT) pool_bwd_kernel(const float* raw, const float* scale, const float* shift, const float* mean, const float* dpred,
                                                       float* dy, int B, double* s0, double* s1)
 {
     const int o = blockIdx.y;
-    const float s = scale[o], t = shift[o];
+    const float s = scale[o], t = shift[o], mu = mean[o];
     float a0 = 0.f, a1 = 0.f;
     const int total = 15 * B;
     for (int i = blockIdx.x * NT + threadIdx.x; i < total; i += gridDim.x * NT) {   // (j, b)
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(NT) pool_bwd_kernel(const float* raw, const fl
             d.x = g * wf_dsilu(fmaf(s, v.x, t)); d.y = g * wf_dsilu(fmaf(s, v.y, t));
             d.z = g * wf_dsilu(fmaf(s, v.z, t)); d.w = g * wf_dsilu(fmaf(s, v.w, t));
             a0 += d.x + d.y + d.z + d.w;
-            a1 = fmaf(d.x, v.x, fmaf(d.y, v.y, fmaf(d.z, v.z, fmaf(d.w, v.w, a1))));
+            a1 = fmaf(d.x, v.x - mu, fmaf(d.y, v.y - mu, fmaf(d.z, v.z - mu, fmaf(d.w, v.w - mu, a1))));
             st4(dy + off + q * 4, d);
         }
     }
@@ -455,10 +457,10 @@ cudaError_t wf_launch_join_bwd(const JoinP& p, int num_sms, cudaStream_t st)
     join_bwd_kernel<256><<<grid, 256, 0, st>>>(p);
     return cudaGetLastError();
 }
-cudaError_t wf_launch_bn_bwd_stats(const float* dy, const float* raw, int C, long long plane, double* s0, double* s1, int num_sms, cudaStream_t st)
+cudaError_t wf_launch_bn_bwd_stats(const float* dy, const float* raw, const float* mean, int C, long long plane, double* s0, double* s1, int num_sms, cudaStream_t st)
 {
     dim3 grid(ew_blocks(plane / 4, C, num_sms), C);
-    bn_bwd_stats_kernel<256><<<grid, 256, 0, st>>>(dy, raw, plane, s0, s1);
+    bn_bwd_stats_kernel<256><<<grid, 256, 0, st>>>(dy, raw, mean, plane, s0, s1);
     return cudaGetLastError();
 }
 cudaError_t wf_launch_pool_fwd(const float* raw, const float* scale, const float* shift, float* pred, int B, cudaStream_t st)
@@ -466,11 +468,11 @@ cudaError_t wf_launch_pool_fwd(const float* raw, const float* scale, const float
     pool_fwd_kernel<<<cdiv(30LL * B, 128), 128, 0, st>>>(raw, scale, shift, pred, B);
     return cudaGetLastError();
 }
-cudaError_t wf_launch_pool_bwd(const float* raw, const float* scale, const float* shift, const float* dpred, float* dy, int B,
+cudaError_t wf_launch_pool_bwd(const float* raw, const float* scale, const float* shift, const float* mean, const float* dpred, float* dy, int B,
                                double* s0, double* s1, cudaStream_t st)
 {
     dim3 grid(cdiv(15LL * B, 256) > 64 ? 64 : cdiv(15LL * B, 256), 2);
-    pool_bwd_kernel<256><<<grid, 256, 0, st>>>(raw, scale, shift, dpred, dy, B, s0, s1);
+    pool_bwd_kernel<256><<<grid, 256, 0, st>>>(raw, scale, shift, mean, dpred, dy, B, s0, s1);
     return cudaGetLastError();
 }
 cudaError_t wf_launch_pose_loss(const float* pred, const float* target, int B, int type, float pw, float bw, const float* gscale,

@@ -18,7 +18,7 @@ struct BnFwdFin {
 };
 struct BnBwdFin {
     int C; double count;
-    const double *s0, *s1;              // sum dy, sum dy*raw
+    const double *s0, *s1;              // sum dy, sum dy*(raw - mean)
     const float *gamma, *mean, *rstd;
     float *dgamma, *dbeta;              // may be nullptr
     float *alpha, *beta_c, *delta;
@@ -31,9 +31,9 @@ struct JoinP {
     float* out;
     const float* dout; float *dz, *da;
     long long plane; int N, C;
-    int a_mode; const float *a_scale, *a_shift;
+    int a_mode; const float *a_scale, *a_shift, *a_mean;
     const float* mask; long long m_sb, m_sc; int m_st;
-    int r_mode; const float *r_scale, *r_shift;
+    int r_mode; const float *r_scale, *r_shift, *r_mean;
     long long r_sc, r_sp, r_sb;
     double *a_stat0, *a_stat1, *r_stat0, *r_stat1;
 };
@@ -51,12 +51,12 @@ struct AttnP {
     int B, N;                     // N = B*20
     const float* qkv_raw;         // [192][15][N]
     const float *qkv_scale, *qkv_shift;            // bn_qkv affine (192)
-    const float *sim_scale, *sim_shift;            // bn_similarity affine (8)
+    const float *sim_scale, *sim_shift, *sim_mean; // bn_similarity affine + batch mean (8)
     double *sim_s0, *sim_s1;                       // stats pass output
     float* sv_raw;                // [64][15][N]
     double *sv_s0, *sv_s1;
     // backward
-    const float *dsv, *sv_alpha, *sv_beta, *sv_delta;   // dy of bn_output + its BN-backward affine (64)
+    const float *dsv, *sv_alpha, *sv_beta, *sv_delta, *sv_mean;   // dy of bn_output + its BN-backward affine (64)
     const float *sim_alpha, *sim_beta, *sim_delta;      // BN-backward affine of bn_similarity (8)
     double *dsim_s0, *dsim_s1;
     float* dqkv;                  // [192][15][N]  dy of bn_qkv
@@ -76,9 +76,9 @@ cudaError_t wf_launch_bn_bwd_fin(const BnBwdFin* d, int n, cudaStream_t st);
 cudaError_t wf_launch_bn_eval_coefs(const BnEvalTable& tab, const float* params, const float* running, float* coefs, cudaStream_t st);
 cudaError_t wf_launch_join_fwd(const JoinP& p, int num_sms, cudaStream_t st);
 cudaError_t wf_launch_join_bwd(const JoinP& p, int num_sms, cudaStream_t st);
-cudaError_t wf_launch_bn_bwd_stats(const float* dy, const float* raw, int C, long long plane, double* s0, double* s1, int num_sms, cudaStream_t st);
+cudaError_t wf_launch_bn_bwd_stats(const float* dy, const float* raw, const float* mean, int C, long long plane, double* s0, double* s1, int num_sms, cudaStream_t st);
 cudaError_t wf_launch_pool_fwd(const float* raw, const float* scale, const float* shift, float* pred, int B, cudaStream_t st);
-cudaError_t wf_launch_pool_bwd(const float* raw, const float* scale, const float* shift, const float* dpred, float* dy, int B,
+cudaError_t wf_launch_pool_bwd(const float* raw, const float* scale, const float* shift, const float* mean, const float* dpred, float* dy, int B,
                                double* s0, double* s1, cudaStream_t st);
 cudaError_t wf_launch_pose_loss(const float* pred, const float* target, int B, int type, float pw, float bw, const float* gscale,
                                 float* dpred, double* acc2, float* out3, cudaStream_t st);

@@ -454,7 +454,7 @@ void dgrad_conv(Ctx& c, int ui, float* out, int epi, int src_bn, const float* sr
     ConvP p{};
     p.in = u.dy; p.in2 = u.raw;
     p.in_sc = (long long)u.pout * c.N; p.in_sp = c.N; p.in_sb = T;
-    p.pro_mode = PRO_BNBWD; p.pro_a = bo.alpha(); p.pro_b = bo.betac(); p.pro_c = bo.delta();
+    p.pro_mode = PRO_BNBWD; p.pro_a = bo.alpha(); p.pro_b = bo.betac(); p.pro_c = bo.delta(); p.pro_d = bo.mean();
     p.w = c.n.packed + u.bpack; p.Kpad = u.b_kpad; p.Mpad = u.b_mpad;
     p.Cin = u.cout_g; p.Cout = u.cin_g; p.groups = u.groups; p.Pin = u.pout; p.Pout = u.pin; p.N = (int)c.N; p.ntaps = u.ntaps;
     p.pmul = 1; p.pdiv = u.stride;
@@ -463,7 +463,7 @@ void dgrad_conv(Ctx& c, int ui, float* out, int epi, int src_bn, const float* sr
     p.epi_mode = epi; p.accumulate = accumulate ? 1 : 0;
     if (epi == EPI_DSILU || epi == EPI_DAFF) {
         const BnUnit& bs = c.n.bn[src_bn];
-        p.eraw = src_raw; p.e_scale = bs.scale(); p.e_shift = bs.shift();
+        p.eraw = src_raw; p.e_scale = bs.scale(); p.e_shift = bs.shift(); p.e_mean = bs.mean();
         p.emask = emask.p; p.em_sb = emask.sb; p.em_sc = emask.sc; p.em_st = emask.st;
         p.stat0 = bs.b0; p.stat1 = bs.b1;
     }
@@ -476,7 +476,7 @@ void wgrad_conv(Ctx& c, int ui, Act in, Pro pro)
     const ConvUnit& u = c.n.conv[ui];
     const BnUnit& bo = c.n.bn[u.bn];
     WgradP p{};
-    p.g = u.dy; p.g2 = u.raw; p.g_pro = PRO_BNBWD; p.g_a = bo.alpha(); p.g_b = bo.betac(); p.g_c = bo.delta();
+    p.g = u.dy; p.g2 = u.raw; p.g_pro = PRO_BNBWD; p.g_a = bo.alpha(); p.g_b = bo.betac(); p.g_c = bo.delta(); p.g_d = bo.mean();
     p.in = in.p; p.in_sc = in.sc; p.in_sp = in.sp; p.in_sb = in.sb;
     p.pro_mode = pro.mode;
     if (pro.bn >= 0) { p.pro_a = c.n.bn[pro.bn].scale(); p.pro_b = c.n.bn[pro.bn].shift(); }
@@ -547,11 +547,11 @@ AttnP attn_params(Ctx& c, AxBlk& a)
     AttnP p{};
     p.width = a.width; p.B = c.B; p.N = (int)c.N;
     p.qkv_raw = q.raw; p.qkv_scale = bq.scale(); p.qkv_shift = bq.shift();
-    p.sim_scale = bs.scale(); p.sim_shift = bs.shift();
+    p.sim_scale = bs.scale(); p.sim_shift = bs.shift(); p.sim_mean = bs.mean();
     p.sim_s0 = bs.f0; p.sim_s1 = bs.f1;
     p.sv_raw = a.sv_raw;
     p.sv_s0 = c.train ? bo.f0 : nullptr; p.sv_s1 = c.train ? bo.f1 : nullptr;
-    p.dsv = a.dsv; p.sv_alpha = bo.alpha(); p.sv_beta = bo.betac(); p.sv_delta = bo.delta();
+    p.dsv = a.dsv; p.sv_alpha = bo.alpha(); p.sv_beta = bo.betac(); p.sv_delta = bo.delta(); p.sv_mean = bo.mean();
     p.sim_alpha = bs.alpha(); p.sim_beta = bs.betac(); p.sim_delta = bs.delta();
     p.dsim_s0 = bs.b0; p.dsim_s1 = bs.b1;
     p.dqkv = q.dy;
@@ -591,7 +591,7 @@ void decoder_bwd(Ctx& c, Act xin, Pro pro, const float* dpred, float* dxin_dy, i
     Net& n = c.n;
     ConvUnit &d1 = n.conv[n.dec.d1], &d2 = n.conv[n.dec.d2];
     const BnUnit& b2 = n.bn[d2.bn];
-    { Scope sc(c, "pool_bwd"); c.ck(wf_launch_pool_bwd(d2.raw, b2.scale(), b2.shift(), dpred, d2.dy, c.B, b2.b0, b2.b1, c.st)); }
+    { Scope sc(c, "pool_bwd"); c.ck(wf_launch_pool_bwd(d2.raw, b2.scale(), b2.shift(), b2.mean(), dpred, d2.dy, c.B, b2.b0, b2.b1, c.st)); }
     bwd_fin(c, d2.bn);
     wgrad_conv(c, n.dec.d2, internal(d1.raw, 15, c.N), pro_act(d1.bn));
     dgrad_conv(c, n.dec.d2, d1.dy, EPI_DSILU, d1.bn, d1.raw, no_mask(), false);
@@ -611,7 +611,7 @@ void axial_bwd(Ctx& c, AxBlk& a, Act xin, Pro pro, float* dxin, int epi, int src
     bwd_fin(c, a.bn_sim);
     { Scope sc(c, "attn_bwd " + a.name); c.ck(wf_launch_attn_bwd(p, c.st)); }
     const BnUnit& bq = n.bn[q.bn];
-    { Scope sc(c, "bn_bwd_stats " + a.name); c.ck(wf_launch_bn_bwd_stats(q.dy, q.raw, 192, 15LL * c.N, bq.b0, bq.b1, c.sms, c.st)); }
+    { Scope sc(c, "bn_bwd_stats " + a.name); c.ck(wf_launch_bn_bwd_stats(q.dy, q.raw, bq.mean(), 192, 15LL * c.N, bq.b0, bq.b1, c.sms, c.st)); }
     bwd_fin(c, q.bn);
     wgrad_conv(c, a.qkv, xin, pro);
     if (dxin) dgrad_conv(c, a.qkv, dxin, epi, src_bn, src_raw, no_mask(), false);
@@ -628,6 +628,7 @@ void conv_block_bwd(Ctx& c, CvBlk& b, Act xin, float* dxin)
     j.a_mode = PRO_AFFINE; j.a_scale = ba.scale(); j.a_shift = ba.shift();
     j.r = ds.raw; j.r_mode = PRO_AFFINE; j.r_scale = br.scale(); j.r_shift = br.shift();
     j.r_sc = j.plane; j.r_sp = c.N; j.r_sb = T;
+    j.a_mean = ba.mean(); j.r_mean = br.mean();
     j.dout = b.dY; j.dz = c3.dy; j.da = nullptr;           // c3.dy doubles as dy of the shortcut BatchNorm
     j.a_stat0 = ba.b0; j.a_stat1 = ba.b1; j.r_stat0 = br.b0; j.r_stat1 = br.b1;
     { Scope sc(c, "join_bwd " + b.name); c.ck(wf_launch_join_bwd(j, c.sms, c.st)); }
@@ -660,14 +661,14 @@ void tcn_block_bwd(Ctx& c, TcnBlk& b, Act xin, float* dxin)
     j.a_mode = PRO_BNSILU; j.a_scale = ba.scale(); j.a_shift = ba.shift();
     Mask m1 = tcn_mask(c.mask_ptr(b.mask0 + 1), b.cout), m0 = tcn_mask(c.mask_ptr(b.mask0), b.cout);
     j.mask = m1.p; j.m_sb = m1.sb; j.m_sc = m1.sc; j.m_st = m1.st;
-    j.dout = b.dX; j.da = pw2.dy;
+    j.dout = b.dX; j.da = pw2.dy; j.a_mean = ba.mean(); j.r_mean = nullptr;
     j.a_stat0 = ba.b0; j.a_stat1 = ba.b1;
     if (b.ds >= 0) {
         ConvUnit& ds = n.conv[b.ds];
         const BnUnit& br = n.bn[ds.bn];
         j.r = ds.raw; j.r_mode = PRO_AFFINE; j.r_scale = br.scale(); j.r_shift = br.shift();
         j.r_sc = c.N; j.r_sp = 0; j.r_sb = T;
-        j.dz = ds.dy; j.r_stat0 = br.b0; j.r_stat1 = br.b1;
+        j.dz = ds.dy; j.r_stat0 = br.b0; j.r_stat1 = br.b1; j.r_mean = br.mean();
     } else {
         j.r = xin.p; j.r_mode = PRO_NONE; j.r_sc = xin.sc; j.r_sp = 0; j.r_sb = xin.sb;
         j.dz = dxin ? dxin : b.dz;          // identity shortcut: dz IS the gradient reaching the block input
@@ -871,7 +872,7 @@ int run_backward(const wf_block_desc* d, const float* x, const float* params, co
             AxBlk& ah = n.ax.back();
             c.ck((g_launches.fetch_add(1), 0) ? cudaSuccess : wf_launch_permute(dy, ah.dsv, n.out_C, n.out_P, B, rs.sb, rs.sc, rs.sp, rs.st, 1, c.sms, st));
             const BnUnit& bo = n.bn[ah.bn_out];
-            c.ck(wf_launch_bn_bwd_stats(ah.dsv, ah.sv_raw, 64, 15LL * c.N, bo.b0, bo.b1, c.sms, st));
+            c.ck(wf_launch_bn_bwd_stats(ah.dsv, ah.sv_raw, bo.mean(), 64, 15LL * c.N, bo.b0, bo.b1, c.sms, st));
         } else {
             c.ck((g_launches.fetch_add(1), 0) ? cudaSuccess : wf_launch_permute(dy, n.dout_buf, n.out_C, n.out_P, B, rs.sb, rs.sc, rs.sp, rs.st, 1, c.sms, st));
             g_in = n.dout_buf;

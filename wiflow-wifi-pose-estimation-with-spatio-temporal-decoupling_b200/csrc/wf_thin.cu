@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) thin_conv_kernel(const ConvP p, int PC)
     lo = max(lo, 0); hi = min(hi, p.Pin - 1);
     const int npos = max(hi - lo + 1, 0);
 
-    TileSrc src{p.in, p.in2, p.in_sc, p.in_sp, p.in_sb, p.pro_mode, p.pro_a, p.pro_b, p.pro_c, p.mask, p.m_sb, p.m_sc, p.m_st, p.Cin, p.Pin};
+    TileSrc src{p.in, p.in2, p.in_sc, p.in_sp, p.in_sb, p.pro_mode, p.pro_a, p.pro_b, p.pro_c, p.pro_d, p.mask, p.m_sb, p.m_sc, p.m_st, p.Cin, p.Pin};
     wf_stage_tile<NT>(src, tile, p.Cin, lo, npos, n0, p.N, tid, nthreads);
     __syncthreads();
 
@@ -84,10 +84,11 @@ __global__ void __launch_bounds__(256) thin_conv_kernel(const ConvP p, int PC)
         if (co < p.Cout) {                         // uniform across the block
             if (valid) {
                 const float bias = p.bias ? p.bias[co] : 0.f;
-                float es = 0.f, et = 0.f;
+                float es = 0.f, et = 0.f, em = 0.f;
                 if (p.epi_mode == EPI_DSILU) { es = p.e_scale[co]; et = p.e_shift[co]; }
+                if (p.epi_mode == EPI_DSILU || p.epi_mode == EPI_DAFF) em = p.e_mean[co];
                 float v[4] = {acc[co][0] + bias, acc[co][1] + bias, acc[co][2] + bias, acc[co][3] + bias};
-                wf_epilogue_quad(p, co, opos, n, es, et, v, s0, s1);
+                wf_epilogue_quad(p, co, opos, n, es, et, em, v, s0, s1);
             }
             if (want_stats) {
                 const double d0 = warp_sum_d((double)s0), d1 = warp_sum_d((double)s1);
@@ -134,8 +135,8 @@ __global__ void __launch_bounds__(512) thin_wgrad_kernel(const WgradP p, int cou
 #pragma unroll
         for (int j = 0; j < CINP; ++j) acc[i][j] = 0.f;
 
-    TileSrc gs{p.g, p.g2, (long long)p.Pout * p.N, p.N, WF_T, p.g_pro, p.g_a, p.g_b, p.g_c, nullptr, 0, 0, 0, p.Cout, p.Pout};
-    TileSrc xs{p.in, p.in2, p.in_sc, p.in_sp, p.in_sb, p.pro_mode, p.pro_a, p.pro_b, p.pro_c, p.mask, p.m_sb, p.m_sc, p.m_st, p.Cin, p.Pin};
+    TileSrc gs{p.g, p.g2, (long long)p.Pout * p.N, p.N, WF_T, p.g_pro, p.g_a, p.g_b, p.g_c, p.g_d, nullptr, 0, 0, 0, p.Cout, p.Pout};
+    TileSrc xs{p.in, p.in2, p.in_sc, p.in_sp, p.in_sb, p.pro_mode, p.pro_a, p.pro_b, p.pro_c, p.pro_d, p.mask, p.m_sb, p.m_sc, p.m_st, p.Cin, p.Pin};
 
     for (int reg = blockIdx.x; reg < nregions; reg += gridDim.x) {
         const int n0 = (reg % ntile_n) * NT;

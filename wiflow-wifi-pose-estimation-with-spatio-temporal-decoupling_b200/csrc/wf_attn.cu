@@ -48,8 +48,8 @@ __global__ void __launch_bounds__(RT * 8 * L) attn_kernel(const AttnP p)
             float4 v = f4zero();
             if (row0 + r < nrows) {
                 v = ld4(p.qkv_raw + c * cstride + row_base(r) + q * 4);
-                const float a = p.qkv_scale[c], b = p.qkv_shift[c];
-                v.x = fmaf(a, v.x, b); v.y = fmaf(a, v.y, b); v.z = fmaf(a, v.z, b); v.w = fmaf(a, v.w, b);
+                const float a = p.qkv_scale[c], b = p.qkv_shift[c], mu = p.qkv_mean[c];
+                v.x = fmaf(a, v.x - mu, b); v.y = fmaf(a, v.y - mu, b); v.z = fmaf(a, v.z - mu, b); v.w = fmaf(a, v.w - mu, b);
             }
             st4(&T[tix(c, r, q * 4)], v);
         }
@@ -74,8 +74,8 @@ __global__ void __launch_bounds__(RT * 8 * L) attn_kernel(const AttnP p)
             float4 v = f4zero();
             if (s < L && row0 < nrows) {
                 v = ld4(p.qkv_raw + c * cstride + (long long)s * N + row0);
-                const float a = p.qkv_scale[c], b = p.qkv_shift[c];
-                v.x = fmaf(a, v.x, b); v.y = fmaf(a, v.y, b); v.z = fmaf(a, v.z, b); v.w = fmaf(a, v.w, b);
+                const float a = p.qkv_scale[c], b = p.qkv_shift[c], mu = p.qkv_mean[c];
+                v.x = fmaf(a, v.x - mu, b); v.y = fmaf(a, v.y - mu, b); v.z = fmaf(a, v.z - mu, b); v.w = fmaf(a, v.w - mu, b);
             }
             T[tix(c, 0, s)] = v.x; T[tix(c, 1, s)] = v.y; T[tix(c, 2, s)] = v.z; T[tix(c, 3, s)] = v.w;
         }
@@ -124,10 +124,10 @@ __global__ void __launch_bounds__(RT * 8 * L) attn_kernel(const AttnP p)
 #pragma unroll
         for (int j = 0; j < L; ++j) { st0 += lg[j]; st1 = fmaf(lg[j], lg[j], st1); }
     } else {
-        const float ss = p.sim_scale[g], ts = p.sim_shift[g];
+        const float ss = p.sim_scale[g], ts = p.sim_shift[g], ms = p.sim_mean[g];
         float mx = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < L; ++j) { pr[j] = fmaf(ss, lg[j], ts); mx = fmaxf(mx, pr[j]); }
+        for (int j = 0; j < L; ++j) { pr[j] = fmaf(ss, lg[j] - ms, ts); mx = fmaxf(mx, pr[j]); }
         float sum = 0.f;
 #pragma unroll
         for (int j = 0; j < L; ++j) { pr[j] = expf(pr[j] - mx); sum += pr[j]; }

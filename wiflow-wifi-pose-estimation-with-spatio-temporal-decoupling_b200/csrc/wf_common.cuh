@@ -10,16 +10,17 @@
 
 #define WF_T 20            // time steps per CSI window (models/pose_model.py:72)
 #define WF_MAX_TAPS 9
+#define TC_KC 32          // K elements per pipeline stage of the tcgen05 kernels (wf_tc.cu)
 
 // prologue modes: how an operand element is produced from what is stored in HBM
 enum { PRO_NONE = 0,       // x
-       PRO_BNSILU = 1,     // mask * silu(a[c]*x + b[c])           (BatchNorm + SiLU (+Dropout))
-       PRO_AFFINE = 2,     // a[c]*x + b[c]                         (BatchNorm only)
+       PRO_BNSILU = 1,     // mask * silu(a[c]*(x - d[c]) + b[c])  (BatchNorm + SiLU (+Dropout); d = mean, b = beta)
+       PRO_AFFINE = 2,     // a[c]*(x - d[c]) + b[c]                (BatchNorm only)
        PRO_BNBWD = 3 };    // a[c]*dy + b[c]*(raw - d[c]) + c[c]    (BatchNorm backward, two tensors; d = batch mean)
 // epilogue modes of the conv GEMM
 enum { EPI_STORE = 0,      // out = acc + bias
        EPI_STATS = 1,      // ... and accumulate sum / sum-of-squares per output channel
-       EPI_DSILU = 2,      // dy = acc * mask * silu'(s*raw+t); stats: sum dy, sum dy*(raw-mean)
+       EPI_DSILU = 2,      // dy = acc * mask * silu'(s*(raw-mean)+t); stats: sum dy, sum dy*(raw-mean)
        EPI_DAFF = 3 };     // dy = acc;                          stats: sum dy, sum dy*(raw-mean)
 
 struct ConvP {
@@ -34,6 +35,8 @@ struct ConvP {
     // A operand (packed weights [groups][ntaps][Kpad][Mpad], m contiguous, zero padded)
     const float* w;
     int Kpad, Mpad;
+    const float* wtc;                 // tcgen05 path (wf_tc.cu): hi/lo-split shared-memory images [M tile][K chunk], or nullptr
+    int tc_kt;                        //   number of K chunks (TC_KC channels each)
     // geometry
     int Cin, Cout, groups, Pin, Pout, N, ntaps;
     int pmul, pdiv;                   // ipos = (opos*pmul + dp[tap]) / pdiv, valid iff divisible and in range
@@ -64,7 +67,15 @@ struct WgradP {
 
 
 
-__device__ __forceinline__ float wf_sigmoid(float x) { return __fdividef(1.f, 1.f + expf(-x)); }
+// sigmoid through the SFU: 2^(-x*log2 e) and an approximate reciprocal (max relative error ~1e-6, far inside the 1e-4 budget;
+// the accurate expf/division sequences cost 4x the instructions in kernels that are issue bound)
+__device__ __forceinline__ float wf_sigmoid(float x)
+{
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+    return r;
+}
 __device__ __forceinline__ float wf_silu(float x) { return x * wf_sigmoid(x); }
 __device__ __forceinline__ float wf_dsilu(float x) { float s = wf_sigmoid(x); return s * (1.f + x * (1.f - s)); }
 
@@ -96,7 +107,7 @@ __device__ __forceinline__ void wf_epilogue_quad(const ConvP& p, int co, int opo
                 else { float mm = *mp; mk[0] = mk[1] = mk[2] = mk[3] = mm; }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = v[j] * mk[j] * wf_dsilu(fmaf(es, r[j], et));
+            for (int j = 0; j < 4; ++j) v[j] = v[j] * mk[j] * wf_dsilu(fmaf(es, r[j] - em, et));
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) { s0 += v[j]; s1 = fmaf(v[j], r[j] - em, s1); }
@@ -127,17 +138,17 @@ __device__ __forceinline__ void wf_stage_tile(const TileSrc& s, float* sm, int c
             const long long off = (long long)c * s.sc + (long long)pos * s.sp + (long long)b * s.sb + t;
             v = ld4(s.p + off);
             if (s.mode == PRO_BNSILU) {
-                const float ca = s.a[c], cb = s.b[c];
+                const float ca = s.a[c], cb = s.b[c], cm = s.d[c];
                 float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
                 if (s.mask) {
                     const float* mp = s.mask + (long long)b * s.m_sb + (long long)c * s.m_sc + (long long)t * s.m_st;
                     if (s.m_st == 1) m = ld4(mp); else { float mm = *mp; m = make_float4(mm, mm, mm, mm); }
                 }
-                v.x = wf_silu(fmaf(ca, v.x, cb)) * m.x; v.y = wf_silu(fmaf(ca, v.y, cb)) * m.y;
-                v.z = wf_silu(fmaf(ca, v.z, cb)) * m.z; v.w = wf_silu(fmaf(ca, v.w, cb)) * m.w;
+                v.x = wf_silu(fmaf(ca, v.x - cm, cb)) * m.x; v.y = wf_silu(fmaf(ca, v.y - cm, cb)) * m.y;
+                v.z = wf_silu(fmaf(ca, v.z - cm, cb)) * m.z; v.w = wf_silu(fmaf(ca, v.w - cm, cb)) * m.w;
             } else if (s.mode == PRO_AFFINE) {
-                const float ca = s.a[c], cb = s.b[c];
-                v.x = fmaf(ca, v.x, cb); v.y = fmaf(ca, v.y, cb); v.z = fmaf(ca, v.z, cb); v.w = fmaf(ca, v.w, cb);
+                const float ca = s.a[c], cb = s.b[c], cm = s.d[c];
+                v.x = fmaf(ca, v.x - cm, cb); v.y = fmaf(ca, v.y - cm, cb); v.z = fmaf(ca, v.z - cm, cb); v.w = fmaf(ca, v.w - cm, cb);
             } else if (s.mode == PRO_BNBWD) {
                 const float4 w = ld4(s.p2 + off);
                 const float ca = s.a[c], cb = s.b[c], cc = s.c[c], cd = s.d[c];

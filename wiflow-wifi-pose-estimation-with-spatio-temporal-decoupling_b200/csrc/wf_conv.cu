@@ -139,7 +139,8 @@ conv_gemm_kernel(const ConvP p)
                 if (p.pro_mode != PRO_NONE) {
                     ca[i] = p.pro_a[c];
                     cb[i] = p.pro_b[c];
-                    if (p.pro_mode == PRO_BNBWD) { cc[i] = p.pro_c[c]; cd[i] = p.pro_d[c]; }
+                    cd[i] = p.pro_d[c];
+                    if (p.pro_mode == PRO_BNBWD) cc[i] = p.pro_c[c];
                 }
             }
             rb[i] = v; rb2[i] = v2; okb[i] = ok;
@@ -164,10 +165,10 @@ conv_gemm_kernel(const ConvP p)
                 if (p.pro_mode == PRO_BNSILU) {
                     const bool hm = p.mask != nullptr;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { float y = wf_silu(fmaf(ca[i], e[j], cb[i])); e[j] = hm ? y * e2[j] : y; }
+                    for (int j = 0; j < 4; ++j) { float y = wf_silu(fmaf(ca[i], e[j] - cd[i], cb[i])); e[j] = hm ? y * e2[j] : y; }
                 } else if (p.pro_mode == PRO_AFFINE) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) e[j] = fmaf(ca[i], e[j], cb[i]);
+                    for (int j = 0; j < 4; ++j) e[j] = fmaf(ca[i], e[j] - cd[i], cb[i]);
                 } else if (p.pro_mode == PRO_BNBWD) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) e[j] = fmaf(ca[i], e[j], fmaf(cb[i], e2[j] - cd[i], cc[i]));
@@ -345,13 +346,13 @@ conv_wgrad_kernel(const WgradP p)
         }
         if (!ok) return f4zero();
         if (p.pro_mode == PRO_BNSILU) {
-            const float a = p.pro_a[c], bb = p.pro_b[c];
+            const float a = p.pro_a[c], bb = p.pro_b[c], mu = p.pro_d[c];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) e[j] = wf_silu(fmaf(a, e[j], bb)) * e2[j];
+            for (int j = 0; j < 4; ++j) e[j] = wf_silu(fmaf(a, e[j] - mu, bb)) * e2[j];
         } else if (p.pro_mode == PRO_AFFINE) {
-            const float a = p.pro_a[c], bb = p.pro_b[c];
+            const float a = p.pro_a[c], bb = p.pro_b[c], mu = p.pro_d[c];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) e[j] = fmaf(a, e[j], bb);
+            for (int j = 0; j < 4; ++j) e[j] = fmaf(a, e[j] - mu, bb);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) if (!((ok >> j) & 1u)) e[j] = 0.f;

@@ -6,7 +6,9 @@
 namespace {
 
 // ---------------------------------------------------------------------------------------------------------
-// BatchNorm finalisation (train mode).  Forward: batch mean / biased var -> (scale, shift, mean, rstd), running
+// BatchNorm finalisation (train mode).  Forward: batch mean / biased var -> (scale, shift, mean, rstd) with
+// y = scale*(x - mean) + shift, shift = beta: subtracting the mean BEFORE scaling (as torch does) keeps the normalised value
+// free of the per-channel rounding offset a folded `beta - mean*scale` would add to every element of the channel; running
 // stats with the unbiased variance and momentum 0.1 (torch BatchNorm semantics used by every BN
 // in models/*.py).  Backward: (sum dy, sum dy*raw) -> dgamma, dbeta and the affine (alpha, beta, delta) with
 // dx = alpha*dy + beta*raw + delta.
@@ -25,7 +27,7 @@ __global__ void bn_finalize_fwd_kernel(BnFwdFin a, BnFwdFin b, int n)
     float gam = d.gamma[c], bet = d.beta[c];
     float sc = (float)(gam * rstd);
     d.scale[c] = sc;
-    d.shift[c] = (float)(bet - mean * gam * rstd);
+    d.shift[c] = bet;
     d.mean[c] = (float)mean;
     d.rstd[c] = (float)rstd;
     if (d.run_mean) {
@@ -66,7 +68,7 @@ __global__ void bn_eval_coefs_kernel(BnEvalTable tab, const float* params, const
     float rstd = 1.0f / sqrtf(rv + 1e-5f);
     float sc = gam * rstd;
     coefs[e.coef_off + c] = sc;                       // scale
-    coefs[e.coef_off + e.Cpad + c] = bet - rm * sc;   // shift
+    coefs[e.coef_off + e.Cpad + c] = bet;             // shift (y = scale*(x - mean) + shift)
     coefs[e.coef_off + 2 * e.Cpad + c] = rm;          // mean
     coefs[e.coef_off + 3 * e.Cpad + c] = rstd;        // rstd
 }
@@ -83,7 +85,7 @@ __device__ __forceinline__ void join_eval(const JoinP& p, int c, long long i, in
     const int b = n / WF_T, t = n % WF_T;
     a4 = ld4(p.a + (long long)c * p.plane + i);
     r4 = ld4(p.r + (long long)c * p.r_sc + (long long)pos * p.r_sp + (long long)b * p.r_sb + t);
-    const float as = p.a_scale[c], at = p.a_shift[c];
+    const float as = p.a_scale[c], at = p.a_shift[c], am = p.a_mean[c];
     const float a[4] = {a4.x, a4.y, a4.z, a4.w};
     const float r[4] = {r4.x, r4.y, r4.z, r4.w};
     mk[0] = mk[1] = mk[2] = mk[3] = 1.f;
@@ -92,13 +94,13 @@ __device__ __forceinline__ void join_eval(const JoinP& p, int c, long long i, in
         if (p.m_st == 1) { float4 m4 = ld4(mp); mk[0] = m4.x; mk[1] = m4.y; mk[2] = m4.z; mk[3] = m4.w; }
         else { mk[0] = mk[1] = mk[2] = mk[3] = *mp; }
     }
-    float rs = 1.f, rt = 0.f;
-    if (p.r_mode == PRO_AFFINE) { rs = p.r_scale[c]; rt = p.r_shift[c]; }
+    float rs = 1.f, rt = 0.f, rm = 0.f;
+    if (p.r_mode == PRO_AFFINE) { rs = p.r_scale[c]; rt = p.r_shift[c]; rm = p.r_mean[c]; }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        ya[j] = fmaf(as, a[j], at);
+        ya[j] = fmaf(as, a[j] - am, at);
         av[j] = (p.a_mode == PRO_BNSILU) ? mk[j] * wf_silu(ya[j]) : ya[j];
-        z[j] = av[j] + fmaf(rs, r[j], rt);
+        z[j] = av[j] + fmaf(rs, r[j] - rm, rt);
     }
 }
 
@@ -163,18 +165,18 @@ __global__ void __launch_bounds__(NT) bn_bwd_stats_kernel(const float* dy, const
 // ---------------------------------------------------------------------------------------------------------
 // decoder tail: BN + SiLU + mean over the 20 time steps (pose_model.py:49-53,94-95).  raw [2][15][N] -> pred [B][15][2]
 // ---------------------------------------------------------------------------------------------------------
-__global__ void pool_fwd_kernel(const float* raw, const float* scale, const float* shift, float* pred, int B)
+__global__ void pool_fwd_kernel(const float* raw, const float* scale, const float* shift, const float* mean, float* pred, int B)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;       // (o, j, b)
     if (i >= 2 * 15 * B) return;
     const int b = i % B, j = (i / B) % 15, o = i / (15 * B);
     const float* src = raw + ((long long)(o * 15 + j) * B + b) * WF_T;
-    const float s = scale[o], t = shift[o];
+    const float s = scale[o], t = shift[o], mu = mean[o];
     float acc = 0.f;
 #pragma unroll
     for (int q = 0; q < WF_T / 4; ++q) {
         float4 v = ld4(src + q * 4);
-        acc += wf_silu(fmaf(s, v.x, t)) + wf_silu(fmaf(s, v.y, t)) + wf_silu(fmaf(s, v.z, t)) + wf_silu(fmaf(s, v.w, t));
+        acc += wf_silu(fmaf(s, v.x - mu, t)) + wf_silu(fmaf(s, v.y - mu, t)) + wf_silu(fmaf(s, v.z - mu, t)) + wf_silu(fmaf(s, v.w - mu, t));
     }
     pred[((long long)b * 15 + j) * 2 + o] = acc * (1.0f / WF_T);
 }
@@ -195,8 +197,8 @@ __global__ void __launch_bounds__(NT) pool_bwd_kernel(const float* raw, const fl
         for (int q = 0; q < WF_T / 4; ++q) {
             const float4 v = ld4(raw + off + q * 4);
             float4 d;
-            d.x = g * wf_dsilu(fmaf(s, v.x, t)); d.y = g * wf_dsilu(fmaf(s, v.y, t));
-            d.z = g * wf_dsilu(fmaf(s, v.z, t)); d.w = g * wf_dsilu(fmaf(s, v.w, t));
+            d.x = g * wf_dsilu(fmaf(s, v.x - mu, t)); d.y = g * wf_dsilu(fmaf(s, v.y - mu, t));
+            d.z = g * wf_dsilu(fmaf(s, v.z - mu, t)); d.w = g * wf_dsilu(fmaf(s, v.w - mu, t));
             a0 += d.x + d.y + d.z + d.w;
             a1 = fmaf(d.x, v.x - mu, fmaf(d.y, v.y - mu, fmaf(d.z, v.z - mu, fmaf(d.w, v.w - mu, a1))));
             st4(dy + off + q * 4, d);
@@ -396,7 +398,7 @@ __global__ void adamw_kernel(float* p, const float* g, float* m, float* v, long 
 //   internal (c, p, b, t)  <->  reference offset  b*r_sb + c*r_sc + p*r_sp + t*r_st
 // ---------------------------------------------------------------------------------------------------------
 __global__ void permute_kernel(const float* src, float* dst, int C, int P, int B, long long r_sb, long long r_sc, long long r_sp,
-                               long long r_st, int to_internal, const float* scale, const float* shift)
+                               long long r_st, int to_internal, const float* scale, const float* shift, const float* mean)
 {
     const long long total = (long long)C * P * B * WF_T;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -406,7 +408,7 @@ __global__ void permute_kernel(const float* src, float* dst, int C, int P, int B
         const int c = (int)(i / ((long long)WF_T * B * P));
         const long long ro = (long long)b * r_sb + (long long)c * r_sc + (long long)pp * r_sp + (long long)t * r_st;
         if (to_internal) dst[i] = src[ro];
-        else dst[ro] = scale ? fmaf(scale[c], src[i], shift[c]) : src[i];
+        else dst[ro] = scale ? fmaf(scale[c], src[i] - mean[c], shift[c]) : src[i];
     }
 }
 
@@ -463,9 +465,9 @@ cudaError_t wf_launch_bn_bwd_stats(const float* dy, const float* raw, const floa
     bn_bwd_stats_kernel<256><<<grid, 256, 0, st>>>(dy, raw, mean, plane, s0, s1);
     return cudaGetLastError();
 }
-cudaError_t wf_launch_pool_fwd(const float* raw, const float* scale, const float* shift, float* pred, int B, cudaStream_t st)
+cudaError_t wf_launch_pool_fwd(const float* raw, const float* scale, const float* shift, const float* mean, float* pred, int B, cudaStream_t st)
 {
-    pool_fwd_kernel<<<cdiv(30LL * B, 128), 128, 0, st>>>(raw, scale, shift, pred, B);
+    pool_fwd_kernel<<<cdiv(30LL * B, 128), 128, 0, st>>>(raw, scale, shift, mean, pred, B);
     return cudaGetLastError();
 }
 cudaError_t wf_launch_pool_bwd(const float* raw, const float* scale, const float* shift, const float* mean, const float* dpred, float* dy, int B,
@@ -506,12 +508,12 @@ cudaError_t wf_launch_adamw(float* p, const float* g, float* m, float* v, long l
 cudaError_t wf_launch_permute(const float* src, float* dst, int C, int P, int B, long long r_sb, long long r_sc, long long r_sp,
                               long long r_st, int to_internal, int num_sms, cudaStream_t st)
 {
-    permute_kernel<<<num_sms * 8, 256, 0, st>>>(src, dst, C, P, B, r_sb, r_sc, r_sp, r_st, to_internal, nullptr, nullptr);
+    permute_kernel<<<num_sms * 8, 256, 0, st>>>(src, dst, C, P, B, r_sb, r_sc, r_sp, r_st, to_internal, nullptr, nullptr, nullptr);
     return cudaGetLastError();
 }
 cudaError_t wf_launch_permute_affine(const float* src, float* dst, int C, int P, int B, long long r_sb, long long r_sc, long long r_sp,
-                                     long long r_st, const float* scale, const float* shift, int num_sms, cudaStream_t st)
+                                     long long r_st, const float* scale, const float* shift, const float* mean, int num_sms, cudaStream_t st)
 {
-    permute_kernel<<<num_sms * 8, 256, 0, st>>>(src, dst, C, P, B, r_sb, r_sc, r_sp, r_st, 0, scale, shift);
+    permute_kernel<<<num_sms * 8, 256, 0, st>>>(src, dst, C, P, B, r_sb, r_sc, r_sp, r_st, 0, scale, shift, mean);
     return cudaGetLastError();
 }

@@ -43,6 +43,9 @@ struct MetricThr { int n; float v[WF_MAX_THR]; };
 struct PackEntry { int param_off, cout, cin, groups, ntaps, f_kpad, f_mpad, b_kpad, b_mpad; long long fwd_off, bwd_off; };
 struct PackTable { int n; PackEntry e[WF_MAX_CONV]; };
 
+struct TcPackEntry { int param_off, cout, cin; long long fwd_off, bwd_off; };
+struct TcPackTable { int n; TcPackEntry e[WF_MAX_CONV]; };
+
 struct AdamState { double sumsq; long long step; float grad_norm, clip_coef, step_size, inv_bc2_sqrt; };
 
 // attention (wf_attn.cu)
@@ -50,7 +53,7 @@ struct AttnP {
     int width;                    // 1: sequences along time (L=20), rows=(h,b); 0: along slots (L=15), rows=n
     int B, N;                     // N = B*20
     const float* qkv_raw;         // [192][15][N]
-    const float *qkv_scale, *qkv_shift;            // bn_qkv affine (192)
+    const float *qkv_scale, *qkv_shift, *qkv_mean; // bn_qkv: scale*(x - mean) + shift (192)
     const float *sim_scale, *sim_shift, *sim_mean; // bn_similarity affine + batch mean (8)
     double *sim_s0, *sim_s1;                       // stats pass output
     float* sv_raw;                // [64][15][N]
@@ -68,6 +71,11 @@ bool wf_thin_conv_ok(const ConvP& p);
 cudaError_t wf_launch_thin_conv(const ConvP& p, cudaStream_t st);
 bool wf_thin_wgrad_ok(const WgradP& p);
 cudaError_t wf_launch_thin_wgrad(const WgradP& p, int num_sms, cudaStream_t st);
+// tcgen05 pointwise-conv path (wf_tc.cu)
+long long wf_tc_pack_floats(int m, int k);
+cudaError_t wf_launch_tc_pack(const TcPackTable& tab, const float* params, float* packed, cudaStream_t st);
+cudaError_t wf_launch_tc_conv(const ConvP& p, int num_sms, cudaStream_t st);
+cudaError_t wf_launch_tc_wgrad(const WgradP& p, int num_sms, cudaStream_t st);
 int wf_conv_bm_for(int M);
 int wf_conv_bk_for(int M);
 
@@ -77,7 +85,7 @@ cudaError_t wf_launch_bn_eval_coefs(const BnEvalTable& tab, const float* params,
 cudaError_t wf_launch_join_fwd(const JoinP& p, int num_sms, cudaStream_t st);
 cudaError_t wf_launch_join_bwd(const JoinP& p, int num_sms, cudaStream_t st);
 cudaError_t wf_launch_bn_bwd_stats(const float* dy, const float* raw, const float* mean, int C, long long plane, double* s0, double* s1, int num_sms, cudaStream_t st);
-cudaError_t wf_launch_pool_fwd(const float* raw, const float* scale, const float* shift, float* pred, int B, cudaStream_t st);
+cudaError_t wf_launch_pool_fwd(const float* raw, const float* scale, const float* shift, const float* mean, float* pred, int B, cudaStream_t st);
 cudaError_t wf_launch_pool_bwd(const float* raw, const float* scale, const float* shift, const float* mean, const float* dpred, float* dy, int B,
                                double* s0, double* s1, cudaStream_t st);
 cudaError_t wf_launch_pose_loss(const float* pred, const float* target, int B, int type, float pw, float bw, const float* gscale,
@@ -90,7 +98,7 @@ cudaError_t wf_launch_adamw(float* p, const float* g, float* m, float* v, long l
 cudaError_t wf_launch_permute(const float* src, float* dst, int C, int P, int B, long long r_sb, long long r_sc, long long r_sp,
                               long long r_st, int to_internal, int num_sms, cudaStream_t st);
 cudaError_t wf_launch_permute_affine(const float* src, float* dst, int C, int P, int B, long long r_sb, long long r_sc, long long r_sp,
-                                     long long r_st, const float* scale, const float* shift, int num_sms, cudaStream_t st);
+                                     long long r_st, const float* scale, const float* shift, const float* mean, int num_sms, cudaStream_t st);
 cudaError_t wf_launch_attn_fwd_stats(const AttnP& p, cudaStream_t st);
 cudaError_t wf_launch_attn_fwd(const AttnP& p, cudaStream_t st);
 cudaError_t wf_launch_attn_bwd_stats(const AttnP& p, cudaStream_t st);

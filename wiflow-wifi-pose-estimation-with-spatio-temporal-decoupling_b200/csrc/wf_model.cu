@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -26,6 +27,8 @@ struct ProfRec { std::string name; cudaEvent_t a, b; double flops; };
 thread_local std::vector<ProfRec> g_prof;
 std::atomic<long long> g_launches{0};
 constexpr int EVAL_CHUNK = 1024;
+// WF_DISABLE_TC=1 routes the pointwise convs through the CUDA-core GEMM instead of tcgen05 (A/B measurements only)
+const bool g_use_tc = [] { const char* e = std::getenv("WF_DISABLE_TC"); return !(e && e[0] == '1'); }();
 
 struct ParamEntry { std::string name; long long off, numel; };
 
@@ -55,6 +58,8 @@ struct ConvUnit {
     int bn;
     int f_kpad, f_mpad, b_kpad, b_mpad;
     long long fpack, bpack;   // float offsets into the packed-weight region
+    bool tc;                  // pointwise conv wide enough for the tcgen05 kernels (wf_tc.cu)
+    long long tc_fpack, tc_bpack;
     float *raw, *dy;          // [groups*cout_g][pout][N]
     long long numel_per_n() const { return (long long)groups * cout_g * pout; }
 };
@@ -84,6 +89,7 @@ struct Net {
     float *in_buf = nullptr, *din_buf = nullptr, *out_buf = nullptr, *dout_buf = nullptr;
     // workspace regions
     float* packed = nullptr; long long packed_floats = 0;
+    float* tcpacked = nullptr; long long tcpacked_floats = 0;
     char* fstats = nullptr; size_t fstats_bytes = 0;
     char* bstats = nullptr; size_t bstats_bytes = 0;
     float* dpred_buf = nullptr;
@@ -125,6 +131,7 @@ int add_conv(Net& n, const std::string& name, int cout_total, int cin_g, int gro
     c.f_mpad = round_up(c.cout_g, wf_conv_bm_for(c.cout_g));
     c.b_kpad = round_up(c.cout_g, wf_conv_bk_for(cin_g));
     c.b_mpad = round_up(cin_g, wf_conv_bm_for(cin_g));
+    c.tc = g_use_tc && groups == 1 && ntaps == 1 && stride == 1 && pin == pout && cin_g >= 64 && cout_total >= 64;
     n.conv.push_back(c);
     return (int)n.conv.size() - 1;
 }
@@ -282,6 +289,14 @@ size_t layout(Net& n, int B, int flags, char* base)
     }
     n.packed_floats = pf;
     n.packed = bp.take<float>(pf);
+    long long tf = 0;
+    for (auto& c : n.conv) {
+        if (!c.tc) continue;
+        c.tc_fpack = tf; tf += wf_tc_pack_floats(c.cout_g, c.cin_g);
+        c.tc_bpack = tf; tf += wf_tc_pack_floats(c.cin_g, c.cout_g);
+    }
+    n.tcpacked_floats = tf;
+    n.tcpacked = bp.take<float>(tf);
     // BN statistics (fp64) and coefficients
     size_t s0 = (bp.off + 255) & ~(size_t)255;
     for (auto& b : n.bn) { b.f0 = bp.take<double>(b.C); b.f1 = bp.take<double>(b.C); }
@@ -389,7 +404,7 @@ void fwd_conv(Ctx& c, int ui, Act in, Pro pro)
     ConvP p{};
     p.in = in.p; p.in_sc = in.sc; p.in_sp = in.sp; p.in_sb = in.sb;
     p.pro_mode = pro.mode;
-    if (pro.bn >= 0) { p.pro_a = c.n.bn[pro.bn].scale(); p.pro_b = c.n.bn[pro.bn].shift(); }
+    if (pro.bn >= 0) { p.pro_a = c.n.bn[pro.bn].scale(); p.pro_b = c.n.bn[pro.bn].shift(); p.pro_d = c.n.bn[pro.bn].mean(); }
     p.mask = pro.mask.p; p.m_sb = pro.mask.sb; p.m_sc = pro.mask.sc; p.m_st = pro.mask.st;
     p.w = c.n.packed + u.fpack; p.Kpad = u.f_kpad; p.Mpad = u.f_mpad;
     p.Cin = u.cin_g; p.Cout = u.cout_g; p.groups = u.groups; p.Pin = u.pin; p.Pout = u.pout; p.N = (int)c.N; p.ntaps = u.ntaps;
@@ -399,8 +414,9 @@ void fwd_conv(Ctx& c, int ui, Act in, Pro pro)
     p.bias = u.b_off >= 0 ? c.params + u.b_off : nullptr;
     p.epi_mode = c.train ? EPI_STATS : EPI_STORE;
     p.stat0 = bo.f0; p.stat1 = bo.f1;
-    Scope sc(c, "conv_fwd " + u.name, conv_flops(u, c.N));
-    c.ck(wf_launch_conv(p, c.st));
+    Scope sc(c, std::string(u.tc ? "tc_fwd " : "conv_fwd ") + u.name, conv_flops(u, c.N));
+    if (u.tc) { p.wtc = c.n.tcpacked + u.tc_fpack; p.tc_kt = (u.cin_g + TC_KC - 1) / TC_KC; c.ck(wf_launch_tc_conv(p, c.sms, c.st)); }
+    else c.ck(wf_launch_conv(p, c.st));
 }
 
 void fwd_fin(Ctx& c, int bn_a, int bn_b = -1)
@@ -467,8 +483,9 @@ void dgrad_conv(Ctx& c, int ui, float* out, int epi, int src_bn, const float* sr
         p.emask = emask.p; p.em_sb = emask.sb; p.em_sc = emask.sc; p.em_st = emask.st;
         p.stat0 = bs.b0; p.stat1 = bs.b1;
     }
-    Scope sc(c, "conv_dgrad " + u.name, conv_flops(u, c.N));
-    c.ck(wf_launch_conv(p, c.st));
+    Scope sc(c, std::string(u.tc ? "tc_dgrad " : "conv_dgrad ") + u.name, conv_flops(u, c.N));
+    if (u.tc) { p.wtc = c.n.tcpacked + u.tc_bpack; p.tc_kt = (u.cout_g + TC_KC - 1) / TC_KC; c.ck(wf_launch_tc_conv(p, c.sms, c.st)); }
+    else c.ck(wf_launch_conv(p, c.st));
 }
 
 void wgrad_conv(Ctx& c, int ui, Act in, Pro pro)
@@ -479,14 +496,15 @@ void wgrad_conv(Ctx& c, int ui, Act in, Pro pro)
     p.g = u.dy; p.g2 = u.raw; p.g_pro = PRO_BNBWD; p.g_a = bo.alpha(); p.g_b = bo.betac(); p.g_c = bo.delta(); p.g_d = bo.mean();
     p.in = in.p; p.in_sc = in.sc; p.in_sp = in.sp; p.in_sb = in.sb;
     p.pro_mode = pro.mode;
-    if (pro.bn >= 0) { p.pro_a = c.n.bn[pro.bn].scale(); p.pro_b = c.n.bn[pro.bn].shift(); }
+    if (pro.bn >= 0) { p.pro_a = c.n.bn[pro.bn].scale(); p.pro_b = c.n.bn[pro.bn].shift(); p.pro_d = c.n.bn[pro.bn].mean(); }
     p.mask = pro.mask.p; p.m_sb = pro.mask.sb; p.m_sc = pro.mask.sc; p.m_st = pro.mask.st;
     p.Cin = u.cin_g; p.Cout = u.cout_g; p.groups = u.groups; p.Pin = u.pin; p.Pout = u.pout; p.N = (int)c.N; p.ntaps = u.ntaps;
     p.pmul = u.stride;
     for (int t = 0; t < u.ntaps; ++t) { p.dp[t] = u.dpf[t]; p.dn[t] = u.dnf[t]; }
     p.dw = c.grads + u.w_off;
-    Scope sc(c, "conv_wgrad " + u.name, conv_flops(u, c.N));
-    c.ck(wf_launch_wgrad(p, c.sms, c.st));
+    Scope sc(c, std::string(u.tc ? "tc_wgrad " : "conv_wgrad ") + u.name, conv_flops(u, c.N));
+    if (u.tc) c.ck(wf_launch_tc_wgrad(p, c.sms, c.st));
+    else c.ck(wf_launch_wgrad(p, c.sms, c.st));
 }
 
 // ------------------------------- forward schedules -------------------------------
@@ -505,12 +523,12 @@ void tcn_block_fwd(Ctx& c, TcnBlk& b, Act xin)
     JoinP j{};
     const BnUnit& ba = n.bn[n.conv[b.pw2].bn];
     j.a = n.conv[b.pw2].raw; j.out = b.X; j.plane = c.N; j.N = (int)c.N; j.C = b.cout;
-    j.a_mode = PRO_BNSILU; j.a_scale = ba.scale(); j.a_shift = ba.shift();
+    j.a_mode = PRO_BNSILU; j.a_scale = ba.scale(); j.a_shift = ba.shift(); j.a_mean = ba.mean();
     Mask m = tcn_mask(c.mask_ptr(b.mask0 + 1), b.cout);
     j.mask = m.p; j.m_sb = m.sb; j.m_sc = m.sc; j.m_st = m.st;
     if (b.ds >= 0) {
         const BnUnit& br = n.bn[n.conv[b.ds].bn];
-        j.r = n.conv[b.ds].raw; j.r_mode = PRO_AFFINE; j.r_scale = br.scale(); j.r_shift = br.shift();
+        j.r = n.conv[b.ds].raw; j.r_mode = PRO_AFFINE; j.r_scale = br.scale(); j.r_shift = br.shift(); j.r_mean = br.mean();
         j.r_sc = c.N; j.r_sp = 0; j.r_sb = T;
     } else {
         j.r = xin.p; j.r_mode = PRO_NONE; j.r_sc = xin.sc; j.r_sp = 0; j.r_sb = xin.sb;
@@ -532,8 +550,8 @@ void conv_block_fwd(Ctx& c, CvBlk& b, Act xin)
     const BnUnit& ba = n.bn[n.conv[b.c3].bn];
     const BnUnit& br = n.bn[n.conv[b.ds].bn];
     j.a = n.conv[b.c3].raw; j.out = b.Y; j.plane = (long long)b.wout * c.N; j.N = (int)c.N; j.C = b.cout;
-    j.a_mode = PRO_AFFINE; j.a_scale = ba.scale(); j.a_shift = ba.shift();
-    j.r = n.conv[b.ds].raw; j.r_mode = PRO_AFFINE; j.r_scale = br.scale(); j.r_shift = br.shift();
+    j.a_mode = PRO_AFFINE; j.a_scale = ba.scale(); j.a_shift = ba.shift(); j.a_mean = ba.mean();
+    j.r = n.conv[b.ds].raw; j.r_mode = PRO_AFFINE; j.r_scale = br.scale(); j.r_shift = br.shift(); j.r_mean = br.mean();
     j.r_sc = j.plane; j.r_sp = c.N; j.r_sb = T;
     Scope sc(c, "join_fwd " + b.name);
     c.ck(wf_launch_join_fwd(j, c.sms, c.st));
@@ -546,7 +564,7 @@ AttnP attn_params(Ctx& c, AxBlk& a)
     const BnUnit &bq = n.bn[q.bn], &bs = n.bn[a.bn_sim], &bo = n.bn[a.bn_out];
     AttnP p{};
     p.width = a.width; p.B = c.B; p.N = (int)c.N;
-    p.qkv_raw = q.raw; p.qkv_scale = bq.scale(); p.qkv_shift = bq.shift();
+    p.qkv_raw = q.raw; p.qkv_scale = bq.scale(); p.qkv_shift = bq.shift(); p.qkv_mean = bq.mean();
     p.sim_scale = bs.scale(); p.sim_shift = bs.shift(); p.sim_mean = bs.mean();
     p.sim_s0 = bs.f0; p.sim_s1 = bs.f1;
     p.sv_raw = a.sv_raw;
@@ -581,7 +599,7 @@ void decoder_fwd(Ctx& c, Act xin, Pro pro, float* pred)
     fwd_fin(c, n.conv[n.dec.d2].bn);
     const BnUnit& b = n.bn[n.conv[n.dec.d2].bn];
     Scope sc(c, "pool_fwd");
-    c.ck(wf_launch_pool_fwd(n.conv[n.dec.d2].raw, b.scale(), b.shift(), pred, c.B, c.st));
+    c.ck(wf_launch_pool_fwd(n.conv[n.dec.d2].raw, b.scale(), b.shift(), b.mean(), pred, c.B, c.st));
 }
 
 // ------------------------------- backward schedules -------------------------------
@@ -712,6 +730,10 @@ void prepare_weights(Ctx& c)
         e.fwd_off = u.fpack; e.bwd_off = u.bpack;
     }
     c.ck(wf_launch_pack(tab, c.params, n.packed, c.st));
+    TcPackTable tt{};
+    for (const ConvUnit& u : n.conv)
+        if (u.tc) tt.e[tt.n++] = TcPackEntry{(int)u.w_off, u.cout_g, u.cin_g, u.tc_fpack, u.tc_bpack};
+    c.ck(wf_launch_tc_pack(tt, c.params, n.tcpacked, c.st));
 }
 
 void eval_coefs(Ctx& c)
@@ -824,7 +846,7 @@ int run_forward(const wf_block_desc* d, const float* x, const float* params, flo
             if (!n.ax.empty()) {
                 // output = bn_output(sv): apply the affine while permuting (JoinP-free path: use a conv-free affine permute)
                 const BnUnit& bo = n.bn[n.ax.back().bn_out];
-                c.ck((g_launches.fetch_add(1), 0) ? cudaSuccess : wf_launch_permute_affine(src, yc, n.out_C, n.out_P, bc, rs.sb, rs.sc, rs.sp, rs.st, bo.scale(), bo.shift(), c.sms, st));
+                c.ck((g_launches.fetch_add(1), 0) ? cudaSuccess : wf_launch_permute_affine(src, yc, n.out_C, n.out_P, bc, rs.sb, rs.sc, rs.sp, rs.st, bo.scale(), bo.shift(), bo.mean(), c.sms, st));
             } else {
                 c.ck((g_launches.fetch_add(1), 0) ? cudaSuccess : wf_launch_permute(src, yc, n.out_C, n.out_P, bc, rs.sb, rs.sc, rs.sp, rs.st, 0, c.sms, st));
             }

@@ -1,0 +1,534 @@
+// tcgen05 / TMEM kernels for the pointwise (1x1) convolutions of WiFlow -- the TCN channel-mixing GEMMs
+// (models/tcn.py:27,40,47: 48.8% of all FLOPs) and the attention QKV projection (models/attention.py:22-24,50).
+//
+//   forward / backward-data :  D[m][col] = sum_k W[m][k] * act(X[k][col])         (pw_tc_kernel)
+//   backward-weights        :  dW[m][c] += sum_col G[m][col] * act(X[c][col])     (pw_wgrad_tc_kernel)
+//
+// fp32 parity (1e-4 on outputs) rules out plain TF32, so every product is the 3xTF32 split
+//   a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi     (hi = rna_tf32(x), lo = rna_tf32(x - hi); error ~2^-21)
+// accumulated in fp32 in TMEM.  Operand staging (all operands K-major, UMMA no-swizzle core-matrix order: an operand tile is a
+// grid of 8-row x 16-byte core matrices, 128 contiguous bytes each):
+//   * weights are split and laid out ONCE per step by tc_pack_kernel as ready-to-use shared-memory images
+//     ([M tile][K chunk][hi|lo]) and arrive by one 32 KB bulk async copy (cp.async.bulk + mbarrier complete_tx) per stage;
+//   * activations go global -> registers -> (BatchNorm + SiLU + Dropout | BatchNorm-backward) -> hi/lo split -> shared
+//     memory, written by 8 producer warps so that 8 lanes always cover one 128-byte core matrix (conflict free),
+//     so the previous layer's normalisation never costs an HBM round trip.
+// One elected thread issues tcgen05.mma (M=128, N<=256, K=8 per instruction); tcgen05.commit releases the stage and
+// finally hands the accumulator to the same 8 warps, which run the epilogue (bias / SiLU' / BatchNorm statistics) out of
+// TMEM with one thread per output channel: the per-channel sums need no shuffles at all.
+#include "wf_tc.cuh"
+#include "wf_common.cuh"
+#include "wf_elem.h"
+
+namespace {
+
+using namespace tc;
+
+constexpr int KC = TC_KC;                 // K elements per pipeline stage
+constexpr int BM = 128;                   // UMMA M
+constexpr int NPROD = 512;                // producer / epilogue threads (warps 0-15)
+constexpr int NPW = NPROD / 32;
+constexpr int NTHREADS = NPROD + 64;      // + one warp issuing the MMAs + one warp for TMEM allocation and weight copies
+constexpr int A_HALF = BM * KC * 4;       // one of hi/lo of a 128 x KC K-major operand tile
+constexpr int A_LBO = 128, A_SBO = (KC / 4) * 128;      // K-major image: KC/4 core matrices along K, then the next 8 rows
+
+__device__ __forceinline__ float4 pro_apply(int mode, float4 v, float4 v2, float a, float b, float c, float d, bool has_mask)
+{
+    if (mode == PRO_BNSILU) {
+        v.x = wf_silu(fmaf(a, v.x - d, b)); v.y = wf_silu(fmaf(a, v.y - d, b)); v.z = wf_silu(fmaf(a, v.z - d, b)); v.w = wf_silu(fmaf(a, v.w - d, b));
+        if (has_mask) { v.x *= v2.x; v.y *= v2.y; v.z *= v2.z; v.w *= v2.w; }
+    } else if (mode == PRO_AFFINE) {
+        v.x = fmaf(a, v.x - d, b); v.y = fmaf(a, v.y - d, b); v.z = fmaf(a, v.z - d, b); v.w = fmaf(a, v.w - d, b);
+    } else if (mode == PRO_BNBWD) {
+        v.x = fmaf(a, v.x, fmaf(b, v2.x - d, c)); v.y = fmaf(a, v.y, fmaf(b, v2.y - d, c));
+        v.z = fmaf(a, v.z, fmaf(b, v2.z - d, c)); v.w = fmaf(a, v.w, fmaf(b, v2.w - d, c));
+    }
+    return v;
+}
+
+__device__ __forceinline__ void split_store(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, float4 v)
+{
+    float4 h, l;
+    tf32_split(v.x, h.x, l.x); tf32_split(v.y, h.y, l.y); tf32_split(v.z, h.z, l.z); tf32_split(v.w, h.w, l.w);
+    *reinterpret_cast<float4*>(hi_base + off) = h;
+    *reinterpret_cast<float4*>(lo_base + off) = l;
+}
+
+// =========================================================================================================
+// forward / backward-data
+// =========================================================================================================
+// TMEM holds two accumulators per tile: the a_hi*b_hi products go to columns [0, bn) and the two small correction products
+// to columns [bnp, bnp + bn).  The tensor core truncates when it adds into the fp32 accumulator, an error that grows with the
+// number of accumulations; keeping the 2^-11-sized corrections out of the main accumulator cuts that count by three and
+// makes their own truncation irrelevant.  The epilogue adds the two in fp32.
+struct TcGeom { int bn, bnp, nst, tmem_cols; };
+
+__global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const TcGeom g)
+{
+    const int BN = g.bn, STAGES = g.nst;
+    const int B_HALF = KC * BN * 4;                       // one of hi/lo of the BN x 16 K-major activation tile
+    const int STAGE_BYTES = 2 * A_HALF + 2 * B_HALF;
+    const int NQ = BN / 4;                                // column quads per tile
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_a = [&](int s) { return bar0 + 8u * s; };
+    auto full_b = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    auto empty = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+    const uint32_t accum_bar = bar0 + 8u * (3 * STAGES);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int KT = p.tc_kt;
+    const int m0 = blockIdx.y * BM;
+    const long long NC = (long long)p.Pout * p.N;
+    const long long col0 = (long long)blockIdx.x * BN;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_a(s), 1); mbar_init(full_b(s), NPROD / 32); mbar_init(empty(s), 1); }
+        mbar_init(accum_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == NPW + 1) { tmem_alloc(smem_u32(tmem_slot), g.tmem_cols); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < NPW) {
+        // ------------------------------ activation producers ------------------------------
+        // The tensor core wants the activation tile K-major (16 bytes = 4 consecutive channels of one column), HBM holds it
+        // column-contiguous.  A thread owns a 4-channel x 4-column micro block: four coalesced 128-bit loads (one per
+        // channel), prologue, a register transpose, four 128-bit shared stores (one per column).  Lane l stores its columns
+        // in the rotated order (s + l/2) mod 4 so that 8 consecutive lanes always hit 8 different rows of the 8x16-byte
+        // core matrices: no bank conflicts without padding.
+        const bool active = tid < (KC / 4) * NQ;
+        const int q = tid % NQ, kq = tid / NQ;
+        const long long col = col0 + q * 4;
+        const bool cval = active && col < NC;
+        long long off_b = 0, moff_b = 0;
+        {
+            long long pos = 0, n = col;
+            if (p.Pout > 1) { pos = col / p.N; n = col - pos * p.N; }
+            const long long b = n / WF_T; const int t = (int)(n - b * WF_T);
+            off_b = pos * p.in_sp + b * p.in_sb + t;
+            moff_b = b * p.m_sb + (long long)t * p.m_st;
+        }
+        const uint32_t sbase = (uint32_t)((q >> 1) * A_SBO + kq * A_LBO + (q & 1) * 64);
+        const int rot = (q >> 1) & 3;
+        const bool has_mask = (p.pro_mode == PRO_BNSILU) && (p.mask != nullptr);
+        auto issue = [&](int kc, float4 (&v)[4], float4 (&v2)[4]) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = kc * KC + kq * 4 + j;
+                v[j] = f4zero(); v2[j] = f4zero();
+                if (cval && c < p.Cin) {
+                    const long long off = (long long)c * p.in_sc + off_b;
+                    v[j] = ld4(p.in + off);
+                    if (p.pro_mode == PRO_BNBWD) v2[j] = ld4(p.in2 + off);
+                    else if (has_mask) {
+                        const float* mp = p.mask + moff_b + (long long)c * p.m_sc;
+                        if (p.m_st == 1) v2[j] = ld4(mp); else { const float mm = *mp; v2[j] = make_float4(mm, mm, mm, mm); }
+                    }
+                }
+            }
+        };
+        int s = 0; uint32_t ph = 0;
+        auto process = [&](int kc, float4 (&v)[4], float4 (&v2)[4]) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = kc * KC + kq * 4 + j;
+                if (cval && c < p.Cin) {
+                    float ca = 0.f, cb = 0.f, cc = 0.f, cd = 0.f;
+                    if (p.pro_mode != PRO_NONE) {
+                        ca = p.pro_a[c]; cb = p.pro_b[c]; cd = p.pro_d[c];
+                        if (p.pro_mode == PRO_BNBWD) cc = p.pro_c[c];
+                    }
+                    v[j] = pro_apply(p.pro_mode, v[j], v2[j], ca, cb, cc, cd, has_mask);
+                } else v[j] = f4zero();
+            }
+            mbar_wait(empty(s), ph ^ 1u);
+            if (active) {
+                uint8_t* bh = smem + s * STAGE_BYTES + 2 * A_HALF;
+                uint8_t* bl = bh + B_HALF;
+#pragma unroll
+                for (int st = 0; st < 4; ++st) {
+                    const int r = (st + rot) & 3;                  // column of the micro block written by this store
+                    float4 x;                                      // (channel 0..3) of column r
+                    x.x = r == 0 ? v[0].x : r == 1 ? v[0].y : r == 2 ? v[0].z : v[0].w;
+                    x.y = r == 0 ? v[1].x : r == 1 ? v[1].y : r == 2 ? v[1].z : v[1].w;
+                    x.z = r == 0 ? v[2].x : r == 1 ? v[2].y : r == 2 ? v[2].z : v[2].w;
+                    x.w = r == 0 ? v[3].x : r == 1 ? v[3].y : r == 2 ? v[3].z : v[3].w;
+                    split_store(bh, bl, sbase + (uint32_t)r * 16u, x);
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_b(s));
+            if (++s == STAGES) { s = 0; ph ^= 1u; }
+        };
+        // (16 producer warps hide the L2 latency of each other's loads; a register double buffer does not fit 576 threads)
+        for (int kc = 0; kc < KT; ++kc) {
+            float4 va[4], va2[4];
+            issue(kc, va, va2);
+            process(kc, va, va2);
+        }
+
+        // ------------------------------ epilogue: one thread per output channel ------------------------------
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int quarter = warp & 3, cgrp = warp >> 2;
+        const int m = m0 + quarter * 32 + lane;
+        const bool mv = m < p.Cout;
+        const int co = m;
+        float bias = 0.f, es = 0.f, et = 0.f, em = 0.f;
+        if (mv) {
+            if (p.bias) bias = p.bias[co];
+            if (p.epi_mode == EPI_DSILU) { es = p.e_scale[co]; et = p.e_shift[co]; }
+            if (p.epi_mode == EPI_DSILU || p.epi_mode == EPI_DAFF) em = p.e_mean[co];
+        }
+        float s0 = 0.f, s1 = 0.f;
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        for (int cb0 = 0; cb0 < BN; cb0 += 32) {
+            if (((cb0 >> 5) % (NPW / 4)) != cgrp) continue;
+            float acc[32], cor[32];
+            tmem_ld32(trow + (uint32_t)cb0, acc);
+            tmem_ld32(trow + (uint32_t)(g.bnp + cb0), cor);
+            tmem_ld_wait();
+            if (mv) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const long long col = col0 + cb0 + j * 4;
+                    if (cb0 + j * 4 < BN && col < NC) {
+                        int pos = 0; long long n = col;
+                        if (p.Pout > 1) { pos = (int)(col / p.N); n = col - (long long)pos * p.N; }
+                        float q4[4] = {acc[j * 4 + 0] + cor[j * 4 + 0] + bias, acc[j * 4 + 1] + cor[j * 4 + 1] + bias,
+                                       acc[j * 4 + 2] + cor[j * 4 + 2] + bias, acc[j * 4 + 3] + cor[j * 4 + 3] + bias};
+                        wf_epilogue_quad(p, co, pos, (int)n, es, et, em, q4, s0, s1);
+                    }
+                }
+            }
+        }
+        if (mv && p.epi_mode != EPI_STORE && p.stat0 != nullptr) {
+            atomicAdd(p.stat0 + co, (double)s0);
+            atomicAdd(p.stat1 + co, (double)s1);
+        }
+    } else if (warp == NPW) {
+        // ------------------------------ MMA issue (one thread) ------------------------------
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(BM, BN, 0, 0);
+            const uint32_t tmem_cor = tmem_base + (uint32_t)g.bnp;
+            int s = 0; uint32_t ph = 0;
+            for (int kc = 0; kc < KT; ++kc) {
+                mbar_wait(full_a(s), ph);
+                mbar_wait(full_b(s), ph);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_HALF;
+                const uint32_t b_hi = a_hi + 2 * A_HALF, b_lo = b_hi + B_HALF;
+#pragma unroll
+                for (int kk = 0; kk < KC / 8; ++kk) {
+                    const uint64_t dah = umma_desc(a_hi + kk * 2 * A_LBO, A_LBO, A_SBO), dal = umma_desc(a_lo + kk * 2 * A_LBO, A_LBO, A_SBO);
+                    const uint64_t dbh = umma_desc(b_hi + kk * 2 * A_LBO, A_LBO, A_SBO), dbl = umma_desc(b_lo + kk * 2 * A_LBO, A_LBO, A_SBO);
+                    const uint32_t accf = (kc | kk) != 0 ? 1u : 0u;
+                    umma_tf32(tmem_cor, dal, dbh, idesc, accf);
+                    umma_tf32(tmem_cor, dah, dbl, idesc, 1u);
+                    umma_tf32(tmem_base, dah, dbh, idesc, accf);
+                }
+                umma_commit(empty(s));
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
+            }
+            umma_commit(accum_bar);
+        }
+    } else {
+        // ------------------------------ weight tiles: one 32 KB bulk copy per stage ------------------------------
+        if (lane == 0) {
+            const float* wsrc = p.wtc + (size_t)blockIdx.y * KT * (2 * A_HALF / 4);
+            int s = 0; uint32_t ph = 0;
+            for (int kc = 0; kc < KT; ++kc) {
+                mbar_wait(empty(s), ph ^ 1u);
+                mbar_arrive_expect_tx(full_a(s), 2 * A_HALF);
+                bulk_g2s(smem_u32(smem + s * STAGE_BYTES), wsrc + (size_t)kc * (2 * A_HALF / 4), 2 * A_HALF, full_a(s));
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == NPW + 1) tmem_dealloc(tmem_base, g.tmem_cols);
+}
+
+// =========================================================================================================
+// backward-weights:  dW[co][ci] += sum over this CTA's column range of G[co][col] * X'[ci][col]
+// Both operands are K-major (K = columns) and are produced through registers; the column range is split across blockIdx.x.
+// =========================================================================================================
+constexpr int WG_BN_MAX = 256;
+constexpr int WG_STAGES = 2;
+constexpr int WG_STAGE_BYTES = 2 * A_HALF + 2 * WG_BN_MAX * KC * 4;
+
+__global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const WgradP p, int bn, int ntile_n, long long cols_per_split)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int B_HALF = WG_BN_MAX * KC * 4;
+    constexpr int TCOLS = 2 * WG_BN_MAX;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 1);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (WG_STAGES + s); };
+    const uint32_t accum_bar = bar0 + 8u * (2 * WG_STAGES);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = (blockIdx.y / ntile_n) * BM;
+    const int c0 = (blockIdx.y % ntile_n) * bn;
+    const long long NC = (long long)p.Pout * p.N;
+    const long long kbegin = (long long)blockIdx.x * cols_per_split;
+    long long kend = kbegin + cols_per_split;
+    if (kend > NC) kend = NC;
+    const int KT = kend > kbegin ? (int)((kend - kbegin + KC - 1) / KC) : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(full(s), NPROD / 32); mbar_init(empty(s), 1); }
+        mbar_init(accum_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == NPW + 1) { tmem_alloc(smem_u32(tmem_slot), TCOLS); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < NPW) {
+        // producers: a warp stages 8 rows x 16 columns (512 contiguous bytes of the K-major image) at a time; unit u of a
+        // stage = (row group u / (KC/16), 16-column part u % (KC/16))
+        constexpr int PARTS = KC / 16;
+        const int r8 = lane & 7, ql = lane >> 3;
+        const int nunits = (BM / 8 + bn / 8) * PARTS;
+        constexpr int MAXG = ((BM / 8 + WG_BN_MAX / 8) * PARTS + NPW - 1) / NPW;       // units per warp per stage
+        const bool has_mask = (p.pro_mode == PRO_BNSILU) && (p.mask != nullptr);
+        auto issue = [&](int kc, float4 (&v)[MAXG], float4 (&v2)[MAXG]) {
+#pragma unroll
+            for (int j = 0; j < MAXG; ++j) {
+                const int u = warp + j * NPW;
+                const int g = u / PARTS, q = (u % PARTS) * 4 + ql;
+                v[j] = f4zero(); v2[j] = f4zero();
+                const long long col = kbegin + (long long)kc * KC + q * 4;
+                if (u < nunits && col < kend) {
+                    long long pos = 0, n = col;
+                    if (p.Pout > 1) { pos = col / p.N; n = col - pos * p.N; }
+                    const long long b = n / WF_T; const int t = (int)(n - b * WF_T);
+                    if (g < BM / 8) {
+                        const int co = m0 + g * 8 + r8;
+                        if (co < p.Cout) {
+                            const long long off = (long long)co * p.Pout * p.N + pos * p.N + n;       // G is [C][Pout][N]
+                            v[j] = ld4(p.g + off);
+                            if (p.g_pro == PRO_BNBWD) v2[j] = ld4(p.g2 + off);
+                        }
+                    } else {
+                        const int ci = c0 + (g - BM / 8) * 8 + r8;
+                        if (ci < p.Cin) {
+                            v[j] = ld4(p.in + (long long)ci * p.in_sc + pos * p.in_sp + b * p.in_sb + t);
+                            if (has_mask) {
+                                const float* mp = p.mask + b * p.m_sb + (long long)t * p.m_st + (long long)ci * p.m_sc;
+                                if (p.m_st == 1) v2[j] = ld4(mp); else { const float mm = *mp; v2[j] = make_float4(mm, mm, mm, mm); }
+                            }
+                        }
+                    }
+                }
+            }
+        };
+        auto process = [&](int kc, float4 (&v)[MAXG], float4 (&v2)[MAXG]) {
+            const int s = kc % WG_STAGES;
+            const uint32_t ph = (uint32_t)(kc / WG_STAGES) & 1u;
+#pragma unroll
+            for (int j = 0; j < MAXG; ++j) {
+                const int u = warp + j * NPW;
+                const int g = u / PARTS, q = (u % PARTS) * 4 + ql;
+                if (u < nunits && kbegin + (long long)kc * KC + q * 4 < kend) {
+                    if (g < BM / 8) {
+                        const int co = m0 + g * 8 + r8;
+                        if (co < p.Cout && p.g_pro == PRO_BNBWD) v[j] = pro_apply(PRO_BNBWD, v[j], v2[j], p.g_a[co], p.g_b[co], p.g_c[co], p.g_d[co], false);
+                    } else {
+                        const int ci = c0 + (g - BM / 8) * 8 + r8;
+                        if (ci < p.Cin && p.pro_mode != PRO_NONE) v[j] = pro_apply(p.pro_mode, v[j], v2[j], p.pro_a[ci], p.pro_b[ci], 0.f, p.pro_d[ci], has_mask);
+                    }
+                }
+            }
+            mbar_wait(empty(s), ph ^ 1u);
+            uint8_t* ah = smem + s * WG_STAGE_BYTES;
+            uint8_t* bh = ah + 2 * A_HALF;
+#pragma unroll
+            for (int j = 0; j < MAXG; ++j) {
+                const int u = warp + j * NPW;
+                const int g = u / PARTS, q = (u % PARTS) * 4 + ql;
+                if (u < nunits) {
+                    const uint32_t off = (uint32_t)(q * A_LBO + r8 * 16);
+                    if (g < BM / 8) split_store(ah, ah + A_HALF, (uint32_t)(g * A_SBO) + off, v[j]);
+                    else split_store(bh, bh + B_HALF, (uint32_t)((g - BM / 8) * A_SBO) + off, v[j]);
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full(s));
+        };
+        for (int kc = 0; kc < KT; ++kc) {
+            float4 va[MAXG], va2[MAXG];
+            issue(kc, va, va2);
+            process(kc, va, va2);
+        }
+
+        // epilogue: thread = output channel co, columns = input channels ci; fp32 reductions into the gradient buffer
+        if (KT > 0) {
+            mbar_wait(accum_bar, 0);
+            tc_fence_after();
+            const int quarter = warp & 3, cgrp = warp >> 2;
+            const int co = m0 + quarter * 32 + lane;
+            const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+            for (int cb0 = 0; cb0 < bn; cb0 += 32) {
+                if (((cb0 >> 5) % (NPW / 4)) != cgrp) continue;
+                float acc[32], cor[32];
+                tmem_ld32(trow + (uint32_t)cb0, acc);
+                tmem_ld32(trow + (uint32_t)(WG_BN_MAX + cb0), cor);
+                tmem_ld_wait();
+                if (co < p.Cout) {
+                    float* drow = p.dw + (size_t)co * p.Cin;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int ci = c0 + cb0 + j;
+                        if (cb0 + j < bn && ci < p.Cin) atomicAdd(drow + ci, acc[j] + cor[j]);
+                    }
+                }
+            }
+        }
+    } else if (warp == NPW) {
+        if (lane == 0 && KT > 0) {
+            const uint32_t idesc = umma_idesc_tf32(BM, bn, 0, 0);
+            const uint32_t tmem_cor = tmem_base + WG_BN_MAX;
+            for (int kc = 0; kc < KT; ++kc) {
+                const int s = kc % WG_STAGES;
+                const uint32_t ph = (uint32_t)(kc / WG_STAGES) & 1u;
+                mbar_wait(full(s), ph);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + s * WG_STAGE_BYTES), a_lo = a_hi + A_HALF;
+                const uint32_t b_hi = a_hi + 2 * A_HALF, b_lo = b_hi + B_HALF;
+#pragma unroll
+                for (int kk = 0; kk < KC / 8; ++kk) {
+                    const uint64_t dah = umma_desc(a_hi + kk * 2 * A_LBO, A_LBO, A_SBO), dal = umma_desc(a_lo + kk * 2 * A_LBO, A_LBO, A_SBO);
+                    const uint64_t dbh = umma_desc(b_hi + kk * 2 * A_LBO, A_LBO, A_SBO), dbl = umma_desc(b_lo + kk * 2 * A_LBO, A_LBO, A_SBO);
+                    const uint32_t accf = (kc | kk) != 0 ? 1u : 0u;
+                    umma_tf32(tmem_cor, dal, dbh, idesc, accf);
+                    umma_tf32(tmem_cor, dah, dbl, idesc, 1u);
+                    umma_tf32(tmem_base, dah, dbh, idesc, accf);
+                }
+                umma_commit(empty(s));
+            }
+            umma_commit(accum_bar);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == NPW + 1) tmem_dealloc(tmem_base, TCOLS);
+}
+
+// =========================================================================================================
+// weight packing: reference [Cout][Cin] -> per (M tile, K chunk) shared-memory images, hi then lo, zero padded
+// =========================================================================================================
+__global__ void tc_pack_kernel(TcPackTable tab, const float* params, float* packed)
+{
+    const TcPackEntry e = tab.e[blockIdx.y];
+    const int f_mt = (e.cout + BM - 1) / BM, f_kt = (e.cin + KC - 1) / KC;
+    const int b_mt = (e.cin + BM - 1) / BM, b_kt = (e.cout + KC - 1) / KC;
+    const long long nf = (long long)f_mt * f_kt * (BM * KC), nb = (long long)b_mt * b_kt * (BM * KC);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nf + nb; i += (long long)gridDim.x * blockDim.x) {
+        const bool bwd = i >= nf;
+        const long long k = bwd ? i - nf : i;
+        const int kt = bwd ? b_kt : f_kt;
+        const int within = (int)(k % (BM * KC));
+        const long long blk = k / (BM * KC);
+        const int mt = (int)(blk / kt), kc = (int)(blk % kt);
+        // image order: [row group (16)][k quad (KC/4)][row in group (8)][k in quad (4)]
+        const int c4 = within & 3, r8 = (within >> 2) & 7, kq = (within >> 5) % (KC / 4), rg = within / (8 * KC);
+        const int row = mt * BM + rg * 8 + r8, kk = kc * KC + kq * 4 + c4;
+        float v = 0.f;
+        if (!bwd) { if (row < e.cout && kk < e.cin) v = params[e.param_off + (long long)row * e.cin + kk]; }     // M = cout, K = cin
+        else { if (row < e.cin && kk < e.cout) v = params[e.param_off + (long long)kk * e.cin + row]; }         // M = cin,  K = cout
+        float hi, lo;
+        tf32_split(v, hi, lo);
+        float* dst = packed + (bwd ? e.bwd_off : e.fwd_off) + blk * (2 * BM * KC);
+        dst[within] = hi;
+        dst[BM * KC + within] = lo;
+    }
+}
+
+}  // namespace
+
+long long wf_tc_pack_floats(int m, int k) { return (long long)((m + BM - 1) / BM) * ((k + KC - 1) / KC) * (2 * BM * KC); }
+
+cudaError_t wf_launch_tc_pack(const TcPackTable& tab, const float* params, float* packed, cudaStream_t st)
+{
+    if (tab.n == 0) return cudaSuccess;
+    dim3 grid(64, tab.n);
+    tc_pack_kernel<<<grid, 256, 0, st>>>(tab, params, packed);
+    return cudaGetLastError();
+}
+
+cudaError_t wf_launch_tc_conv(const ConvP& p, int num_sms, cudaStream_t st)
+{
+    constexpr int SMEM_MAX = 200 * 1024;
+    static bool cfg = false;
+    if (!cfg) {
+        cudaError_t e = cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+        if (e != cudaSuccess) return e;
+        cfg = true;
+    }
+    const long long NC = (long long)p.Pout * p.N;
+    const long long mt = (p.Cout + BM - 1) / BM;
+    // column-tile width: the multiple of 16 in [64, 256] that minimises (rounds of tiles per SM) x (cost of one tile)
+    int best_bn = 256; long long best_cost = -1;
+    for (int bn = 256; bn >= 64; bn -= 16) {
+        const long long tiles = mt * ((NC + bn - 1) / bn);
+        const long long cost = ((tiles + num_sms - 1) / num_sms) * (bn + 64);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_bn = bn; }
+    }
+    TcGeom g{};
+    g.bn = best_bn;
+    g.bnp = (best_bn + 31) / 32 * 32;
+    g.tmem_cols = 32;
+    while (g.tmem_cols < 2 * g.bnp) g.tmem_cols *= 2;
+    const int stage = 2 * A_HALF + 2 * KC * g.bn * 4;
+    const int budget = g.tmem_cols <= 256 ? 100 * 1024 : SMEM_MAX - 256;       // narrow tiles: leave room for a second CTA per SM
+    g.nst = budget / stage;
+    if (g.nst > 4) g.nst = 4;
+    if (g.nst < 2) g.nst = 2;
+    const int smem = g.nst * stage + (3 * g.nst + 1) * 8 + 16;
+    dim3 grid((unsigned)((NC + g.bn - 1) / g.bn), (unsigned)mt);
+    pw_tc_kernel<<<grid, NTHREADS, smem, st>>>(p, g);
+    return cudaGetLastError();
+}
+
+cudaError_t wf_launch_tc_wgrad(const WgradP& p, int num_sms, cudaStream_t st)
+{
+    constexpr int smem = WG_STAGES * WG_STAGE_BYTES + (2 * WG_STAGES + 1) * 8 + 16;
+    static bool cfg = false;
+    if (!cfg) {
+        cudaError_t e = cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        cfg = true;
+    }
+    // input-channel tile: an even split of Cin into <= 256-wide pieces, rounded up to the UMMA N granularity (16)
+    const int nt = (p.Cin + WG_BN_MAX - 1) / WG_BN_MAX;
+    int bn = ((p.Cin + nt - 1) / nt + 15) / 16 * 16;
+    if (bn < 16) bn = 16;
+    const int mtiles = (p.Cout + BM - 1) / BM;
+    const int tiles = mtiles * nt;
+    const long long NC = (long long)p.Pout * p.N;
+    long long splits = (2LL * num_sms + tiles - 1) / tiles;
+    const long long max_splits = (NC + 16 * KC - 1) / (16 * KC);           // at least 16 stages per CTA
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    long long per = (NC + splits - 1) / splits;
+    per = (per + KC - 1) / KC * KC;
+    splits = (NC + per - 1) / per;
+    dim3 grid((unsigned)splits, (unsigned)tiles);
+    pw_wgrad_tc_kernel<<<grid, NTHREADS, smem, st>>>(p, bn, nt, per);
+    return cudaGetLastError();
+}

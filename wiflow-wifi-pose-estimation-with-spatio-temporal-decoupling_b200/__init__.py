@@ -10,7 +10,7 @@ All arithmetic runs in libwiflow_b200.so (hand-written CUDA, C ABI in include/wi
 eager-PyTorch fallback: importing works anywhere, calling needs the built library and a B200."""
 from . import _lib, ops                      # noqa: F401
 from . import losses, models, utils           # noqa: F401
-from .engine import InferStep, TrainStep      # noqa: F401
+from .engine import InferStep, TrainStep, allreduce_gradients, shard_bounds      # noqa: F401
 from .losses import PoseLoss                  # noqa: F401
 from .models import (AsymmetricConvBlock, AxialAttention, ConvBlock1, DualAxialAttention, InnerGroupedTemporalBlock,  # noqa: F401
                      TemporalBlock, TemporalConvNet, WiFlow, WiFlowPoseModel)

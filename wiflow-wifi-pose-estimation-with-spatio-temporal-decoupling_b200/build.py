@@ -38,6 +38,13 @@ def build(force=False, verbose=False):
         raise RuntimeError(f'nvcc failed on {failed}')
     if force or procs or not os.path.exists(LIB):
         subprocess.check_call([nvcc, '-shared', '-o', LIB] + objs + ['-Xcompiler', '-fPIC', '-lcudart'])
+    # native self-test of the tcgen05 kernels (tests/test_gpu_native.py runs it on the GPU box)
+    st_src = os.path.join(HERE, '..', 'tests', 'native', 'tc_selftest.cu')
+    st_exe = os.path.join(HERE, '..', 'tests', 'native', 'tc_selftest')
+    tc_obj = os.path.join(CSRC, 'wf_tc.o')
+    if os.path.exists(st_src) and (force or procs or any(_newer(d, st_exe) for d in [st_src, tc_obj])):
+        subprocess.check_call([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O2', '-std=c++17', '-Wno-deprecated-gpu-targets',
+                               '-o', st_exe, st_src, tc_obj, '-lcudart'])
     return LIB
 
 

@@ -124,7 +124,8 @@ static int run_perf(int M, int K, int N, int pro)
     float ms; cudaEventElapsedTime(&ms, a, b);
     printf("perf conv  M=%d K=%d N=%d pro=%d: %.1f us  (%.1f TFLOP/s fp32-equivalent)\n", M, K, N, pro, ms * 200, 2.0 * M * K * N / (ms / 5 * 1e-3) / 1e12);
     WgradP w{};
-    w.g = dD; w.g_pro = PRO_NONE; w.in = dX; w.in_sc = N; w.in_sp = 0; w.in_sb = WF_T; w.pro_mode = pro; w.pro_a = dA; w.pro_b = dA + K; w.pro_d = dA + 3 * K;
+    w.g = dD; w.g2 = dD; w.g_pro = pro == PRO_NONE ? PRO_NONE : PRO_BNBWD; w.g_a = dA + 4 * K; w.g_b = dA + 4 * K + M; w.g_c = dA + 4 * K + 2 * M; w.g_d = dA + 4 * K + 3 * M;
+    w.in = dX; w.in_sc = N; w.in_sp = 0; w.in_sb = WF_T; w.pro_mode = pro; w.pro_a = dA; w.pro_b = dA + K; w.pro_d = dA + 3 * K;
     w.Cin = K; w.Cout = M; w.groups = 1; w.Pin = 1; w.Pout = 1; w.N = N; w.ntaps = 1; w.pmul = 1; w.dw = dW;
     for (int i = 0; i < 2; ++i) CK(wf_launch_tc_wgrad(w, 148, 0));
     cudaEventRecord(a);

@@ -35,3 +35,19 @@ for n,e in worst: print(f"{n:45s}", ' '.join(f'{v:.1e}' for v in e))
 allmax=np.array([max(e) for e in res.values()]); print('tensors with fp32-ref err > 5e-4:', (allmax>5e-4).sum(), ' >3e-4:', (allmax>3e-4).sum(), 'median', np.median(allmax))
 for n in ['up.block.1.bias','residual_blocks.0.block.5.bias','tcn.network.3.bn2_pw.weight','attention.width_axis.bn_qkv.weight']:
     print(n, ' '.join(f'{v:.1e}' for v in res[n]))
+
+# ---- global L2 error of the whole (live) gradient, per variant, relative to the first variant ----
+import math
+l2 = []
+for pi, perm in enumerate(perms):
+    torch.set_num_threads([8, 1, 2, 4, 3][pi])
+    g32 = run32(perm)
+    sq = 0.0
+    for n in g64:
+        if is_dead(n):
+            continue
+        sq += float(((g32[n].double() - g64[n]) ** 2).sum())
+    l2.append(math.sqrt(sq))
+print('global L2 error of the fp32 gradient per variant:', ' '.join(f'{v:.3e}' for v in l2), ' max/min = %.2f' % (max(l2) / min(l2)))
+for n in ['up.block.8.weight', 'residual_blocks.0.block.8.weight', 'residual_blocks.1.block.8.weight']:
+    print(n, ' '.join(f'{v:.1e}' for v in res[n]))

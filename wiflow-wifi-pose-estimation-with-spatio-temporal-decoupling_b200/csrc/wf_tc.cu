@@ -11,11 +11,13 @@
 //   * weights are split and laid out ONCE per step by tc_pack_kernel as ready-to-use shared-memory images
 //     ([M tile][K chunk][hi|lo]) and arrive by one 32 KB bulk async copy (cp.async.bulk + mbarrier complete_tx) per stage;
 //   * activations go global -> registers -> (BatchNorm + SiLU + Dropout | BatchNorm-backward) -> hi/lo split -> shared
-//     memory, written by 8 producer warps so that 8 lanes always cover one 128-byte core matrix (conflict free),
+//     memory, written by 16 producer warps so that 8 lanes always cover one 128-byte core matrix (conflict free),
 //     so the previous layer's normalisation never costs an HBM round trip.
 // One elected thread issues tcgen05.mma (M=128, N<=256, K=8 per instruction); tcgen05.commit releases the stage and
-// finally hands the accumulator to the same 8 warps, which run the epilogue (bias / SiLU' / BatchNorm statistics) out of
+// finally hands the accumulators to the same 16 warps, which run the epilogue (bias / SiLU' / BatchNorm statistics) out of
 // TMEM with one thread per output channel: the per-channel sums need no shuffles at all.
+// The kernels are issue bound on the producer warps (profiles/), so the prologue mode is a template parameter and all
+// addressing is strength-reduced out of the K loop.
 #include "wf_tc.cuh"
 #include "wf_common.cuh"
 #include "wf_elem.h"
@@ -32,14 +34,16 @@ constexpr int NTHREADS = NPROD + 64;      // + one warp issuing the MMAs + one w
 constexpr int A_HALF = BM * KC * 4;       // one of hi/lo of a 128 x KC K-major operand tile
 constexpr int A_LBO = 128, A_SBO = (KC / 4) * 128;      // K-major image: KC/4 core matrices along K, then the next 8 rows
 
-__device__ __forceinline__ float4 pro_apply(int mode, float4 v, float4 v2, float a, float b, float c, float d, bool has_mask)
+// prologue of one float4 (4 consecutive columns of one channel); MODE is a compile-time PRO_* value
+template <int MODE, bool MASK>
+__device__ __forceinline__ float4 pro4(float4 v, float4 v2, float a, float b, float c, float d)
 {
-    if (mode == PRO_BNSILU) {
+    if (MODE == PRO_BNSILU) {
         v.x = wf_silu(fmaf(a, v.x - d, b)); v.y = wf_silu(fmaf(a, v.y - d, b)); v.z = wf_silu(fmaf(a, v.z - d, b)); v.w = wf_silu(fmaf(a, v.w - d, b));
-        if (has_mask) { v.x *= v2.x; v.y *= v2.y; v.z *= v2.z; v.w *= v2.w; }
-    } else if (mode == PRO_AFFINE) {
+        if (MASK) { v.x *= v2.x; v.y *= v2.y; v.z *= v2.z; v.w *= v2.w; }
+    } else if (MODE == PRO_AFFINE) {
         v.x = fmaf(a, v.x - d, b); v.y = fmaf(a, v.y - d, b); v.z = fmaf(a, v.z - d, b); v.w = fmaf(a, v.w - d, b);
-    } else if (mode == PRO_BNBWD) {
+    } else if (MODE == PRO_BNBWD) {
         v.x = fmaf(a, v.x, fmaf(b, v2.x - d, c)); v.y = fmaf(a, v.y, fmaf(b, v2.y - d, c));
         v.z = fmaf(a, v.z, fmaf(b, v2.z - d, c)); v.w = fmaf(a, v.w, fmaf(b, v2.w - d, c));
     }
@@ -54,6 +58,11 @@ __device__ __forceinline__ void split_store(uint8_t* hi_base, uint8_t* lo_base, 
     *reinterpret_cast<float4*>(lo_base + off) = l;
 }
 
+__device__ __forceinline__ float4 sel4(bool c, float4 a, float4 b)
+{
+    return make_float4(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z, c ? a.w : b.w);
+}
+
 // =========================================================================================================
 // forward / backward-data
 // =========================================================================================================
@@ -63,10 +72,11 @@ __device__ __forceinline__ void split_store(uint8_t* hi_base, uint8_t* lo_base, 
 // makes their own truncation irrelevant.  The epilogue adds the two in fp32.
 struct TcGeom { int bn, bnp, nst, tmem_cols; };
 
+template <int PRO, bool MASK>
 __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const TcGeom g)
 {
     const int BN = g.bn, STAGES = g.nst;
-    const int B_HALF = KC * BN * 4;                       // one of hi/lo of the BN x 16 K-major activation tile
+    const int B_HALF = KC * BN * 4;                       // one of hi/lo of the BN x KC K-major activation tile
     const int STAGE_BYTES = 2 * A_HALF + 2 * B_HALF;
     const int NQ = BN / 4;                                // column quads per tile
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -85,7 +95,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
     const long long col0 = (long long)blockIdx.x * BN;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_a(s), 1); mbar_init(full_b(s), NPROD / 32); mbar_init(empty(s), 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_a(s), 1); mbar_init(full_b(s), NPW); mbar_init(empty(s), 1); }
         mbar_init(accum_bar, 1);
         fence_mbar_init();
     }
@@ -99,79 +109,85 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
         // ------------------------------ activation producers ------------------------------
         // The tensor core wants the activation tile K-major (16 bytes = 4 consecutive channels of one column), HBM holds it
         // column-contiguous.  A thread owns a 4-channel x 4-column micro block: four coalesced 128-bit loads (one per
-        // channel), prologue, a register transpose, four 128-bit shared stores (one per column).  Lane l stores its columns
-        // in the rotated order (s + l/2) mod 4 so that 8 consecutive lanes always hit 8 different rows of the 8x16-byte
+        // channel), prologue, a register transpose, four 128-bit shared stores (one per column).  Lane l stores column
+        // (s xor (l/2 mod 4)) in its s-th store so that 8 consecutive lanes always hit 8 different rows of the 8x16-byte
         // core matrices: no bank conflicts without padding.
         const bool active = tid < (KC / 4) * NQ;
         const int q = tid % NQ, kq = tid / NQ;
         const long long col = col0 + q * 4;
         const bool cval = active && col < NC;
-        long long off_b = 0, moff_b = 0;
+        const float *pin = p.in, *pin2 = p.in2, *pm = p.mask;
         {
             long long pos = 0, n = col;
             if (p.Pout > 1) { pos = col / p.N; n = col - pos * p.N; }
             const long long b = n / WF_T; const int t = (int)(n - b * WF_T);
-            off_b = pos * p.in_sp + b * p.in_sb + t;
-            moff_b = b * p.m_sb + (long long)t * p.m_st;
+            const long long off = pos * p.in_sp + b * p.in_sb + t + (long long)(kq * 4) * p.in_sc;
+            pin += off;
+            if (PRO == PRO_BNBWD) pin2 += off;
+            if (MASK) pm += b * p.m_sb + (long long)t * p.m_st + (long long)(kq * 4) * p.m_sc;
         }
-        const uint32_t sbase = (uint32_t)((q >> 1) * A_SBO + kq * A_LBO + (q & 1) * 64);
+        const long long in_sc = p.in_sc, m_sc = p.m_sc;
+        const int m_st = p.m_st, Cin = p.Cin;
+        const float *ca_p = p.pro_a + kq * 4, *cb_p = p.pro_b + kq * 4, *cc_p = p.pro_c + kq * 4, *cd_p = p.pro_d + kq * 4;
         const int rot = (q >> 1) & 3;
-        const bool has_mask = (p.pro_mode == PRO_BNSILU) && (p.mask != nullptr);
-        auto issue = [&](int kc, float4 (&v)[4], float4 (&v2)[4]) {
+        const bool b0 = rot & 1, b1 = rot & 2;
+        const uint32_t sbase = (uint32_t)((q >> 1) * A_SBO + kq * A_LBO + (q & 1) * 64);
+        uint32_t soff[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = kc * KC + kq * 4 + j;
-                v[j] = f4zero(); v2[j] = f4zero();
-                if (cval && c < p.Cin) {
-                    const long long off = (long long)c * p.in_sc + off_b;
-                    v[j] = ld4(p.in + off);
-                    if (p.pro_mode == PRO_BNBWD) v2[j] = ld4(p.in2 + off);
-                    else if (has_mask) {
-                        const float* mp = p.mask + moff_b + (long long)c * p.m_sc;
-                        if (p.m_st == 1) v2[j] = ld4(mp); else { const float mm = *mp; v2[j] = make_float4(mm, mm, mm, mm); }
+        for (int s4 = 0; s4 < 4; ++s4) soff[s4] = sbase + (uint32_t)((s4 ^ rot) * 16);
+        int s = 0; uint32_t ph = 0;
+        for (int kc = 0; kc < KT; ++kc) {
+            const int c0 = kc * KC + kq * 4;
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = f4zero();
+            if (cval && c0 < Cin) {
+                float4 v2[4];
+                float4 A4 = f4zero(), B4 = f4zero(), C4 = f4zero(), D4 = f4zero();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v2[j] = f4zero();
+                    if (c0 + j < Cin) {
+                        v[j] = ld4(pin + j * in_sc);
+                        if (PRO == PRO_BNBWD) v2[j] = ld4(pin2 + j * in_sc);
+                        if (MASK) {
+                            const float* mp = pm + j * m_sc;
+                            if (m_st == 1) v2[j] = ld4(mp); else { const float mm = *mp; v2[j] = make_float4(mm, mm, mm, mm); }
+                        }
                     }
                 }
-            }
-        };
-        int s = 0; uint32_t ph = 0;
-        auto process = [&](int kc, float4 (&v)[4], float4 (&v2)[4]) {
+                if (PRO != PRO_NONE) {       // per-channel coefficients of the 4 channels: one 128-bit load per array
+                    A4 = ld4(ca_p + kc * KC); B4 = ld4(cb_p + kc * KC); D4 = ld4(cd_p + kc * KC);
+                    if (PRO == PRO_BNBWD) C4 = ld4(cc_p + kc * KC);
+                    v[0] = pro4<PRO, MASK>(v[0], v2[0], A4.x, B4.x, C4.x, D4.x);
+                    v[1] = pro4<PRO, MASK>(v[1], v2[1], A4.y, B4.y, C4.y, D4.y);
+                    v[2] = pro4<PRO, MASK>(v[2], v2[2], A4.z, B4.z, C4.z, D4.z);
+                    v[3] = pro4<PRO, MASK>(v[3], v2[3], A4.w, B4.w, C4.w, D4.w);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = kc * KC + kq * 4 + j;
-                if (cval && c < p.Cin) {
-                    float ca = 0.f, cb = 0.f, cc = 0.f, cd = 0.f;
-                    if (p.pro_mode != PRO_NONE) {
-                        ca = p.pro_a[c]; cb = p.pro_b[c]; cd = p.pro_d[c];
-                        if (p.pro_mode == PRO_BNBWD) cc = p.pro_c[c];
-                    }
-                    v[j] = pro_apply(p.pro_mode, v[j], v2[j], ca, cb, cc, cd, has_mask);
-                } else v[j] = f4zero();
+                    for (int j = 0; j < 4; ++j) if (c0 + j >= Cin) v[j] = f4zero();
+                }
             }
+            pin += KC * in_sc;
+            if (PRO == PRO_BNBWD) pin2 += KC * in_sc;
+            if (MASK) pm += KC * m_sc;
+            // 4x4 transpose: column i of the micro block = (v[0].i, v[1].i, v[2].i, v[3].i); z[s] = column (s xor rot)
+            const float4 c0v = make_float4(v[0].x, v[1].x, v[2].x, v[3].x), c1v = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
+            const float4 c2v = make_float4(v[0].z, v[1].z, v[2].z, v[3].z), c3v = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
+            const float4 y0 = sel4(b0, c1v, c0v), y1 = sel4(b0, c0v, c1v), y2 = sel4(b0, c3v, c2v), y3 = sel4(b0, c2v, c3v);
+            const float4 z0 = sel4(b1, y2, y0), z1 = sel4(b1, y3, y1), z2 = sel4(b1, y0, y2), z3 = sel4(b1, y1, y3);
             mbar_wait(empty(s), ph ^ 1u);
             if (active) {
                 uint8_t* bh = smem + s * STAGE_BYTES + 2 * A_HALF;
                 uint8_t* bl = bh + B_HALF;
-#pragma unroll
-                for (int st = 0; st < 4; ++st) {
-                    const int r = (st + rot) & 3;                  // column of the micro block written by this store
-                    float4 x;                                      // (channel 0..3) of column r
-                    x.x = r == 0 ? v[0].x : r == 1 ? v[0].y : r == 2 ? v[0].z : v[0].w;
-                    x.y = r == 0 ? v[1].x : r == 1 ? v[1].y : r == 2 ? v[1].z : v[1].w;
-                    x.z = r == 0 ? v[2].x : r == 1 ? v[2].y : r == 2 ? v[2].z : v[2].w;
-                    x.w = r == 0 ? v[3].x : r == 1 ? v[3].y : r == 2 ? v[3].z : v[3].w;
-                    split_store(bh, bl, sbase + (uint32_t)r * 16u, x);
-                }
+                split_store(bh, bl, soff[0], z0);
+                split_store(bh, bl, soff[1], z1);
+                split_store(bh, bl, soff[2], z2);
+                split_store(bh, bl, soff[3], z3);
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(full_b(s));
             if (++s == STAGES) { s = 0; ph ^= 1u; }
-        };
-        // (16 producer warps hide the L2 latency of each other's loads; a register double buffer does not fit 576 threads)
-        for (int kc = 0; kc < KT; ++kc) {
-            float4 va[4], va2[4];
-            issue(kc, va, va2);
-            process(kc, va, va2);
         }
 
         // ------------------------------ epilogue: one thread per output channel ------------------------------
@@ -198,10 +214,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
             if (mv) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const long long col = col0 + cb0 + j * 4;
-                    if (cb0 + j * 4 < BN && col < NC) {
-                        int pos = 0; long long n = col;
-                        if (p.Pout > 1) { pos = (int)(col / p.N); n = col - (long long)pos * p.N; }
+                    const long long colj = col0 + cb0 + j * 4;
+                    if (cb0 + j * 4 < BN && colj < NC) {
+                        int pos = 0; long long n = colj;
+                        if (p.Pout > 1) { pos = (int)(colj / p.N); n = colj - (long long)pos * p.N; }
                         float q4[4] = {acc[j * 4 + 0] + cor[j * 4 + 0] + bias, acc[j * 4 + 1] + cor[j * 4 + 1] + bias,
                                        acc[j * 4 + 2] + cor[j * 4 + 2] + bias, acc[j * 4 + 3] + cor[j * 4 + 3] + bias};
                         wf_epilogue_quad(p, co, pos, (int)n, es, et, em, q4, s0, s1);
@@ -260,11 +276,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
 // =========================================================================================================
 // backward-weights:  dW[co][ci] += sum over this CTA's column range of G[co][col] * X'[ci][col]
 // Both operands are K-major (K = columns) and are produced through registers; the column range is split across blockIdx.x.
+// GPRO: prologue of G (PRO_NONE or PRO_BNBWD), XPRO/MASK: prologue of X.
 // =========================================================================================================
 constexpr int WG_BN_MAX = 256;
 constexpr int WG_STAGES = 2;
 constexpr int WG_STAGE_BYTES = 2 * A_HALF + 2 * WG_BN_MAX * KC * 4;
 
+template <int GPRO, int XPRO, bool MASK>
 __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const WgradP p, int bn, int ntile_n, long long cols_per_split)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -287,7 +305,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const WgradP p
     const int KT = kend > kbegin ? (int)((kend - kbegin + KC - 1) / KC) : 0;
 
     if (tid == 0) {
-        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(full(s), NPROD / 32); mbar_init(empty(s), 1); }
+        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(full(s), NPW); mbar_init(empty(s), 1); }
         mbar_init(accum_bar, 1);
         fence_mbar_init();
     }
@@ -298,58 +316,67 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const WgradP p
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < NPW) {
-        // producers: a warp stages 8 rows x 16 columns (512 contiguous bytes of the K-major image) at a time; unit u of a
-        // stage = (row group u / (KC/16), 16-column part u % (KC/16))
-        constexpr int PARTS = KC / 16;
-        const int r8 = lane & 7, ql = lane >> 3;
-        const int nunits = (BM / 8 + bn / 8) * PARTS;
-        constexpr int MAXG = ((BM / 8 + WG_BN_MAX / 8) * PARTS + NPW - 1) / NPW;       // units per warp per stage
-        const bool has_mask = (p.pro_mode == PRO_BNSILU) && (p.mask != nullptr);
-        auto issue = [&](int kc, float4 (&v)[MAXG], float4 (&v2)[MAXG]) {
+        // producers: a warp stages 8 rows x 16 columns (512 contiguous bytes of the K-major image) per unit; a stage has
+        // (16 + bn/8) row groups x 2 column halves = up to 96 units, unit u = warp + 16 j  ->  row group u/2, half = warp & 1
+        static_assert(KC == 32 && NPW % 2 == 0, "unit mapping assumes two 16-column halves per stage");
+        constexpr int MAXG = ((BM / 8 + WG_BN_MAX / 8) * 2 + NPW - 1) / NPW;
+        const int r8 = lane & 7;
+        const int q = (warp & 1) * 4 + (lane >> 3);           // column quad of this thread inside the 32-column stage
+        const int ngroups = BM / 8 + bn / 8;
+        // per-unit row: element offset of the row inside its tensor, coefficients, validity
+        unsigned rowoff[MAXG], moff[MAXG];
+        float ca[MAXG], cb[MAXG], cc[MAXG], cd[MAXG];
+        unsigned valid = 0;
 #pragma unroll
-            for (int j = 0; j < MAXG; ++j) {
-                const int u = warp + j * NPW;
-                const int g = u / PARTS, q = (u % PARTS) * 4 + ql;
-                v[j] = f4zero(); v2[j] = f4zero();
-                const long long col = kbegin + (long long)kc * KC + q * 4;
-                if (u < nunits && col < kend) {
-                    long long pos = 0, n = col;
-                    if (p.Pout > 1) { pos = col / p.N; n = col - pos * p.N; }
-                    const long long b = n / WF_T; const int t = (int)(n - b * WF_T);
-                    if (g < BM / 8) {
-                        const int co = m0 + g * 8 + r8;
-                        if (co < p.Cout) {
-                            const long long off = (long long)co * p.Pout * p.N + pos * p.N + n;       // G is [C][Pout][N]
-                            v[j] = ld4(p.g + off);
-                            if (p.g_pro == PRO_BNBWD) v2[j] = ld4(p.g2 + off);
-                        }
-                    } else {
-                        const int ci = c0 + (g - BM / 8) * 8 + r8;
-                        if (ci < p.Cin) {
-                            v[j] = ld4(p.in + (long long)ci * p.in_sc + pos * p.in_sp + b * p.in_sb + t);
-                            if (has_mask) {
-                                const float* mp = p.mask + b * p.m_sb + (long long)t * p.m_st + (long long)ci * p.m_sc;
-                                if (p.m_st == 1) v2[j] = ld4(mp); else { const float mm = *mp; v2[j] = make_float4(mm, mm, mm, mm); }
-                            }
-                        }
-                    }
+        for (int j = 0; j < MAXG; ++j) {
+            const int grp = (warp >> 1) + j * (NPW / 2);
+            rowoff[j] = 0; moff[j] = 0; ca[j] = cb[j] = cc[j] = cd[j] = 0.f;
+            if (grp < BM / 8) {
+                const int co = m0 + grp * 8 + r8;
+                if (co < p.Cout) {
+                    valid |= 1u << j;
+                    rowoff[j] = (unsigned)((long long)co * NC);
+                    if (GPRO == PRO_BNBWD) { ca[j] = p.g_a[co]; cb[j] = p.g_b[co]; cc[j] = p.g_c[co]; cd[j] = p.g_d[co]; }
+                }
+            } else if (grp < ngroups) {
+                const int ci = c0 + (grp - BM / 8) * 8 + r8;
+                if (ci < p.Cin) {
+                    valid |= 1u << j;
+                    rowoff[j] = (unsigned)((long long)ci * p.in_sc);
+                    if (MASK) moff[j] = (unsigned)((long long)ci * p.m_sc);
+                    if (XPRO != PRO_NONE) { ca[j] = p.pro_a[ci]; cb[j] = p.pro_b[ci]; cd[j] = p.pro_d[ci]; }
                 }
             }
-        };
-        auto process = [&](int kc, float4 (&v)[MAXG], float4 (&v2)[MAXG]) {
+        }
+        // column state of this thread, advanced by KC columns per stage
+        long long col = kbegin + q * 4;
+        long long pos = 0, n = col;
+        if (p.Pout > 1) { pos = col / p.N; n = col - pos * p.N; }
+        long long b = n / WF_T; int t = (int)(n - b * WF_T);
+        const uint32_t soff = (uint32_t)(q * A_LBO + r8 * 16);
+        const int m_st = p.m_st;
+        for (int kc = 0; kc < KT; ++kc) {
             const int s = kc % WG_STAGES;
             const uint32_t ph = (uint32_t)(kc / WG_STAGES) & 1u;
+            const bool colv = col < kend;
+            const float* gp = p.g + col;
+            const float* gp2 = p.g2 + col;
+            const float* xp = p.in + pos * p.in_sp + b * p.in_sb + t;
+            const float* mp = p.mask + b * p.m_sb + (long long)t * m_st;
+            float4 v[MAXG];
 #pragma unroll
             for (int j = 0; j < MAXG; ++j) {
-                const int u = warp + j * NPW;
-                const int g = u / PARTS, q = (u % PARTS) * 4 + ql;
-                if (u < nunits && kbegin + (long long)kc * KC + q * 4 < kend) {
-                    if (g < BM / 8) {
-                        const int co = m0 + g * 8 + r8;
-                        if (co < p.Cout && p.g_pro == PRO_BNBWD) v[j] = pro_apply(PRO_BNBWD, v[j], v2[j], p.g_a[co], p.g_b[co], p.g_c[co], p.g_d[co], false);
+                const int grp = (warp >> 1) + j * (NPW / 2);
+                v[j] = f4zero();
+                if (colv && ((valid >> j) & 1u)) {
+                    if (grp < BM / 8) {
+                        v[j] = ld4(gp + rowoff[j]);
+                        if (GPRO == PRO_BNBWD) v[j] = pro4<PRO_BNBWD, false>(v[j], ld4(gp2 + rowoff[j]), ca[j], cb[j], cc[j], cd[j]);
                     } else {
-                        const int ci = c0 + (g - BM / 8) * 8 + r8;
-                        if (ci < p.Cin && p.pro_mode != PRO_NONE) v[j] = pro_apply(p.pro_mode, v[j], v2[j], p.pro_a[ci], p.pro_b[ci], 0.f, p.pro_d[ci], has_mask);
+                        v[j] = ld4(xp + rowoff[j]);
+                        float4 mk = f4zero();
+                        if (MASK) { if (m_st == 1) mk = ld4(mp + moff[j]); else { const float mm = mp[moff[j]]; mk = make_float4(mm, mm, mm, mm); } }
+                        v[j] = pro4<XPRO, MASK>(v[j], mk, ca[j], cb[j], 0.f, cd[j]);
                     }
                 }
             }
@@ -358,22 +385,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const WgradP p
             uint8_t* bh = ah + 2 * A_HALF;
 #pragma unroll
             for (int j = 0; j < MAXG; ++j) {
-                const int u = warp + j * NPW;
-                const int g = u / PARTS, q = (u % PARTS) * 4 + ql;
-                if (u < nunits) {
-                    const uint32_t off = (uint32_t)(q * A_LBO + r8 * 16);
-                    if (g < BM / 8) split_store(ah, ah + A_HALF, (uint32_t)(g * A_SBO) + off, v[j]);
-                    else split_store(bh, bh + B_HALF, (uint32_t)((g - BM / 8) * A_SBO) + off, v[j]);
-                }
+                const int grp = (warp >> 1) + j * (NPW / 2);
+                if (grp < BM / 8) split_store(ah, ah + A_HALF, (uint32_t)(grp * A_SBO) + soff, v[j]);
+                else if (grp < ngroups) split_store(bh, bh + B_HALF, (uint32_t)((grp - BM / 8) * A_SBO) + soff, v[j]);
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(full(s));
-        };
-        for (int kc = 0; kc < KT; ++kc) {
-            float4 va[MAXG], va2[MAXG];
-            issue(kc, va, va2);
-            process(kc, va, va2);
+            // advance KC = 32 columns: t += 12, b += 1 (mod 20), wrapping to the next position at n == N
+            col += KC; n += KC; t += KC - WF_T; b += 1;
+            if (t >= WF_T) { t -= WF_T; b += 1; }
+            if (n >= p.N) { n -= p.N; pos += 1; b = n / WF_T; t = (int)(n - b * WF_T); }
         }
 
         // epilogue: thread = output channel co, columns = input channels ci; fp32 reductions into the gradient buffer
@@ -459,6 +481,35 @@ __global__ void tc_pack_kernel(TcPackTable tab, const float* params, float* pack
     }
 }
 
+constexpr int SMEM_MAX = 200 * 1024;
+
+template <int PRO, bool MASK>
+cudaError_t launch_conv_t(const ConvP& p, const TcGeom& g, dim3 grid, int smem, cudaStream_t st)
+{
+    static bool cfg = false;
+    if (!cfg) {
+        cudaError_t e = cudaFuncSetAttribute(pw_tc_kernel<PRO, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+        if (e != cudaSuccess) return e;
+        cfg = true;
+    }
+    pw_tc_kernel<PRO, MASK><<<grid, NTHREADS, smem, st>>>(p, g);
+    return cudaGetLastError();
+}
+
+template <int GPRO, int XPRO, bool MASK>
+cudaError_t launch_wgrad_t(const WgradP& p, int bn, int nt, long long per, dim3 grid, cudaStream_t st)
+{
+    constexpr int smem = WG_STAGES * WG_STAGE_BYTES + (2 * WG_STAGES + 1) * 8 + 16;
+    static bool cfg = false;
+    if (!cfg) {
+        cudaError_t e = cudaFuncSetAttribute(pw_wgrad_tc_kernel<GPRO, XPRO, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        cfg = true;
+    }
+    pw_wgrad_tc_kernel<GPRO, XPRO, MASK><<<grid, NTHREADS, smem, st>>>(p, bn, nt, per);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 long long wf_tc_pack_floats(int m, int k) { return (long long)((m + BM - 1) / BM) * ((k + KC - 1) / KC) * (2 * BM * KC); }
@@ -473,13 +524,6 @@ cudaError_t wf_launch_tc_pack(const TcPackTable& tab, const float* params, float
 
 cudaError_t wf_launch_tc_conv(const ConvP& p, int num_sms, cudaStream_t st)
 {
-    constexpr int SMEM_MAX = 200 * 1024;
-    static bool cfg = false;
-    if (!cfg) {
-        cudaError_t e = cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
-        if (e != cudaSuccess) return e;
-        cfg = true;
-    }
     const long long NC = (long long)p.Pout * p.N;
     const long long mt = (p.Cout + BM - 1) / BM;
     // column-tile width: the multiple of 16 in [64, 256] that minimises (rounds of tiles per SM) x (cost of one tile)
@@ -501,34 +545,45 @@ cudaError_t wf_launch_tc_conv(const ConvP& p, int num_sms, cudaStream_t st)
     if (g.nst < 2) g.nst = 2;
     const int smem = g.nst * stage + (3 * g.nst + 1) * 8 + 16;
     dim3 grid((unsigned)((NC + g.bn - 1) / g.bn), (unsigned)mt);
-    pw_tc_kernel<<<grid, NTHREADS, smem, st>>>(p, g);
-    return cudaGetLastError();
+    const bool mask = p.pro_mode == PRO_BNSILU && p.mask != nullptr;
+    switch (p.pro_mode) {
+        case PRO_NONE: return launch_conv_t<PRO_NONE, false>(p, g, grid, smem, st);
+        case PRO_BNSILU: return mask ? launch_conv_t<PRO_BNSILU, true>(p, g, grid, smem, st) : launch_conv_t<PRO_BNSILU, false>(p, g, grid, smem, st);
+        case PRO_AFFINE: return launch_conv_t<PRO_AFFINE, false>(p, g, grid, smem, st);
+        default: return launch_conv_t<PRO_BNBWD, false>(p, g, grid, smem, st);
+    }
 }
 
 cudaError_t wf_launch_tc_wgrad(const WgradP& p, int num_sms, cudaStream_t st)
 {
-    constexpr int smem = WG_STAGES * WG_STAGE_BYTES + (2 * WG_STAGES + 1) * 8 + 16;
-    static bool cfg = false;
-    if (!cfg) {
-        cudaError_t e = cudaFuncSetAttribute(pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        cfg = true;
-    }
+    const long long NC = (long long)p.Pout * p.N;
+    // 32-bit element offsets inside the kernel
+    if ((long long)p.Cout * NC >= (1LL << 31) || (long long)p.Cin * p.in_sc >= (1LL << 31) || (long long)p.Cin * p.m_sc >= (1LL << 31))
+        return cudaErrorInvalidValue;
     // input-channel tile: an even split of Cin into <= 256-wide pieces, rounded up to the UMMA N granularity (16)
     const int nt = (p.Cin + WG_BN_MAX - 1) / WG_BN_MAX;
     int bn = ((p.Cin + nt - 1) / nt + 15) / 16 * 16;
     if (bn < 16) bn = 16;
     const int mtiles = (p.Cout + BM - 1) / BM;
     const int tiles = mtiles * nt;
-    const long long NC = (long long)p.Pout * p.N;
-    long long splits = (2LL * num_sms + tiles - 1) / tiles;
-    const long long max_splits = (NC + 16 * KC - 1) / (16 * KC);           // at least 16 stages per CTA
+    long long splits = (2LL * num_sms) / tiles;                          // two full rounds of CTAs, never a ragged third
+    const long long max_splits = (NC + 8 * KC - 1) / (8 * KC);           // at least 8 stages per CTA
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     long long per = (NC + splits - 1) / splits;
     per = (per + KC - 1) / KC * KC;
     splits = (NC + per - 1) / per;
     dim3 grid((unsigned)splits, (unsigned)tiles);
-    pw_wgrad_tc_kernel<<<grid, NTHREADS, smem, st>>>(p, bn, nt, per);
-    return cudaGetLastError();
+    const bool mask = p.pro_mode == PRO_BNSILU && p.mask != nullptr;
+    if (p.g_pro == PRO_NONE) {
+        if (p.pro_mode == PRO_NONE) return launch_wgrad_t<PRO_NONE, PRO_NONE, false>(p, bn, nt, per, grid, st);
+        return cudaErrorInvalidValue;                                       // only the self-test uses a raw G
+    }
+    switch (p.pro_mode) {
+        case PRO_NONE: return launch_wgrad_t<PRO_BNBWD, PRO_NONE, false>(p, bn, nt, per, grid, st);
+        case PRO_BNSILU: return mask ? launch_wgrad_t<PRO_BNBWD, PRO_BNSILU, true>(p, bn, nt, per, grid, st)
+                                     : launch_wgrad_t<PRO_BNBWD, PRO_BNSILU, false>(p, bn, nt, per, grid, st);
+        case PRO_AFFINE: return launch_wgrad_t<PRO_BNBWD, PRO_AFFINE, false>(p, bn, nt, per, grid, st);
+        default: return cudaErrorInvalidValue;
+    }
 }

@@ -235,15 +235,16 @@ def run_ours(args, rank, world, local_rank):
             'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'final_loss': loss_val[0], 'grad_norm': loss_val[3]}
 
+    # ---- launches per step: one eager (un-graphed) step on EVERY rank (it contains the all-reduce) ----
+    c0 = _lib.lib().wf_launch_count()
+    ts.use_graph = False
+    ts.step(xs[0], ys[0])
+    torch.cuda.synchronize(dev)
+    per_step = _lib.lib().wf_launch_count() - c0
     if rank == 0:
         line['clocks'] = clk.summary()
         pk = peaks()
-        # ---- launches per step + per-kernel profile of one eager step (CUDA events around every launch) ----
-        c0 = _lib.lib().wf_launch_count()
-        ts.use_graph = False
-        ts.step(xs[0], ys[0])
-        torch.cuda.synchronize(dev)
-        per_step = _lib.lib().wf_launch_count() - c0
+        # ---- per-kernel profile of one forward+backward (CUDA events around every launch; no collective inside) ----
         line['gpu_launches'] = int(per_step * args.steps)
         line['gpu_launches_per_step'] = int(per_step)
         masks = model._wf_masks(B, dev)

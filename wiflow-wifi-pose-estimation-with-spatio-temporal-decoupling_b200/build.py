@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-SOURCES = ['wf_conv.cu', 'wf_tc.cu', 'wf_thin.cu', 'wf_elem.cu', 'wf_attn.cu', 'wf_model.cu']
+SOURCES = ['wf_conv.cu', 'wf_group.cu', 'wf_tc.cu', 'wf_thin.cu', 'wf_elem.cu', 'wf_attn.cu', 'wf_model.cu']
 LIB = os.path.join(HERE, 'libwiflow_b200.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']
@@ -36,8 +36,13 @@ def build(force=False, verbose=False):
             failed.append(src)
     if failed:
         raise RuntimeError(f'nvcc failed on {failed}')
-    if force or procs or not os.path.exists(LIB):
+    manifest = os.path.join(CSRC, '.link_manifest')          # relink when the list of objects changes, not only when one is rebuilt
+    want = ' '.join(SOURCES)
+    have = open(manifest).read() if os.path.exists(manifest) else ''
+    if force or procs or want != have or not os.path.exists(LIB) or any(_newer(o, LIB) for o in objs):
         subprocess.check_call([nvcc, '-shared', '-o', LIB] + objs + ['-Xcompiler', '-fPIC', '-lcudart'])
+        with open(manifest, 'w') as f:
+            f.write(want)
     # native self-test of the tcgen05 kernels (tests/test_gpu_native.py runs it on the GPU box)
     st_src = os.path.join(HERE, '..', 'tests', 'native', 'tc_selftest.cu')
     st_exe = os.path.join(HERE, '..', 'tests', 'native', 'tc_selftest')

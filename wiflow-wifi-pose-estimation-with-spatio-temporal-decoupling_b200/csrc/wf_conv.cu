@@ -465,6 +465,7 @@ static cudaError_t launch_conv_t(const ConvP& p, cudaStream_t st)
 cudaError_t wf_launch_conv(const ConvP& p, cudaStream_t st)
 {
     if (wf_thin_conv_ok(p)) return wf_launch_thin_conv(p, st);
+    if (wf_group_conv_ok(p)) return wf_launch_group_conv(p, st);
     switch (conv_cfg_for(p.Cout)) {
         case CFG_BIG: return launch_conv_t<64, 128, 8, 8, 8>(p, st);
         case CFG_MID: return launch_conv_t<32, 128, 8, 4, 8>(p, st);

@@ -493,6 +493,7 @@ static cudaError_t launch_wgrad_t(WgradP p, int target_ctas, cudaStream_t st)
 cudaError_t wf_launch_wgrad(const WgradP& p, int num_sms, cudaStream_t st)
 {
     if (wf_thin_wgrad_ok(p)) return wf_launch_thin_wgrad(p, num_sms, st);
+    if (wf_group_wgrad_ok(p)) return wf_launch_group_wgrad(p, num_sms, st);
     const int target = num_sms * 6;
     if (p.Cout >= 48 && p.Cin >= 48) return launch_wgrad_t<64, 64, 8, 4>(p, target, st);
     if (p.Cout >= 48) return launch_wgrad_t<64, 32, 4, 4>(p, target, st);

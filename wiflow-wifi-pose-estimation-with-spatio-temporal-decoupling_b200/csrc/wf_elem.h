@@ -69,6 +69,8 @@ cudaError_t wf_launch_conv(const ConvP& p, cudaStream_t st);
 cudaError_t wf_launch_wgrad(const WgradP& p, int num_sms, cudaStream_t st);
 bool wf_group_conv_ok(const ConvP& p);
 cudaError_t wf_launch_group_conv(const ConvP& p, cudaStream_t st);
+bool wf_group_wgrad_ok(const WgradP& p);
+cudaError_t wf_launch_group_wgrad(const WgradP& p, int num_sms, cudaStream_t st);
 bool wf_thin_conv_ok(const ConvP& p);
 cudaError_t wf_launch_thin_conv(const ConvP& p, cudaStream_t st);
 bool wf_thin_wgrad_ok(const WgradP& p);

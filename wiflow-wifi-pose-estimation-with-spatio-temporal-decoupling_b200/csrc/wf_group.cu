@@ -216,3 +216,220 @@ cudaError_t wf_launch_group_conv(const ConvP& p, cudaStream_t st)
 {
     return p.Mpad == 16 ? launch_group<16>(p, st) : launch_group<32>(p, st);
 }
+
+// =========================================================================================================
+// Backward-weights of the grouped causal convs:
+//   dW[co][ci][tap] = sum_n G[co][n] * X'[ci][n + dn(tap)]      (terms whose source column leaves the 20-step window dropped)
+// One CTA owns one group and a range of columns; per 64-column chunk it stages G (BatchNorm-backward applied) and X'
+// (BatchNorm+SiLU+Dropout applied, with a 16-column left halo) ONCE and produces all three taps from them: the tap shift is
+// a shifted fragment read of X', the window rule a per-column zeroing of the G fragment.  Each of the 8 warps takes one
+// 8-column slice of the chunk for the whole 32 x 32 x 3 output; the warps' partial sums meet in shared memory and leave as
+// one fp32 atomic per weight per CTA.
+// =========================================================================================================
+namespace {
+
+constexpr int GW_KCH = 64;                         // columns per chunk (8 warps x one k8 step)
+constexpr int GW_GS = GW_KCH + 4;                  // row strides (words): conflict-free fragment loads
+constexpr int GW_XS = G_HALO + GW_KCH + 4;
+constexpr int GW_STAGE = 2 * 32 * GW_GS + 2 * 32 * GW_XS;      // words per stage: G hi/lo + X hi/lo
+
+__global__ void __launch_bounds__(G_NT, 1) group_wgrad_kernel(const WgradP p, long long cols_per_split)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = blockIdx.z;
+    const long long kbegin = (long long)blockIdx.x * cols_per_split;
+    long long kend = kbegin + cols_per_split;
+    if (kend > p.N) kend = p.N;
+    const int nchunks = kend > kbegin ? (int)((kend - kbegin + GW_KCH - 1) / GW_KCH) : 0;
+    auto Gs = [&](int buf, int hl) { return smem + buf * GW_STAGE + hl * 32 * GW_GS; };
+    auto Xs = [&](int buf, int hl) { return smem + buf * GW_STAGE + 2 * 32 * GW_GS + hl * 32 * GW_XS; };
+
+    // loader assignment: G: 32 rows x 16 quads = 512 items (2 per thread); X: 32 rows x 20 quads = 640 items (3 passes)
+    float4 rg[2], rg2[2], rx[3], rm[3];
+    auto load_chunk = [&](int ch) {
+        const long long c0 = kbegin + (long long)ch * GW_KCH;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int idx = tid + i * G_NT, row = idx >> 4, q = idx & 15;
+            const long long col = c0 + q * 4;
+            rg[i] = f4zero(); rg2[i] = f4zero();
+            if (row < p.Cout && col < kend) {
+                const long long off = (long long)(g * p.Cout + row) * p.N + col;
+                rg[i] = ld4(p.g + off);
+                if (p.g_pro == PRO_BNBWD) rg2[i] = ld4(p.g2 + off);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int idx = tid + i * G_NT, row = idx / 20, q = idx % 20;
+            const long long col = c0 - G_HALO + q * 4;
+            rx[i] = f4zero(); rm[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (idx < 640 && row < p.Cin && col >= 0 && col < p.N) {
+                const long long b = col / WF_T; const int t = (int)(col - b * WF_T);
+                const int c = g * p.Cin + row;
+                rx[i] = ld4(p.in + (long long)c * p.in_sc + b * p.in_sb + t);
+                if (p.pro_mode == PRO_BNSILU && p.mask) {
+                    const float* mp = p.mask + b * p.m_sb + (long long)c * p.m_sc + (long long)t * p.m_st;
+                    if (p.m_st == 1) rm[i] = ld4(mp); else { const float mm = *mp; rm[i] = make_float4(mm, mm, mm, mm); }
+                }
+            }
+        }
+    };
+    auto store_chunk = [&](int buf, int ch) {
+        const long long c0 = kbegin + (long long)ch * GW_KCH;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int idx = tid + i * G_NT, row = idx >> 4, q = idx & 15;
+            float4 v = rg[i];
+            if (p.g_pro == PRO_BNBWD && row < p.Cout && c0 + q * 4 < kend) {
+                const int c = g * p.Cout + row;
+                const float a = p.g_a[c], b = p.g_b[c], d = p.g_c[c], mu = p.g_d[c];
+                v.x = fmaf(a, v.x, fmaf(b, rg2[i].x - mu, d)); v.y = fmaf(a, v.y, fmaf(b, rg2[i].y - mu, d));
+                v.z = fmaf(a, v.z, fmaf(b, rg2[i].z - mu, d)); v.w = fmaf(a, v.w, fmaf(b, rg2[i].w - mu, d));
+            }
+            float4 h, l;
+            split4(v, h, l);
+            st4(Gs(buf, 0) + row * GW_GS + q * 4, h);
+            st4(Gs(buf, 1) + row * GW_GS + q * 4, l);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int idx = tid + i * G_NT, row = idx / 20, q = idx % 20;
+            if (idx < 640) {
+                float4 v = rx[i];
+                const long long col = c0 - G_HALO + q * 4;
+                if (row < p.Cin && col >= 0 && col < p.N && p.pro_mode != PRO_NONE) {
+                    const int c = g * p.Cin + row;
+                    const float a = p.pro_a[c], bb = p.pro_b[c], mu = p.pro_d[c];
+                    if (p.pro_mode == PRO_BNSILU) {
+                        v.x = wf_silu(fmaf(a, v.x - mu, bb)) * rm[i].x; v.y = wf_silu(fmaf(a, v.y - mu, bb)) * rm[i].y;
+                        v.z = wf_silu(fmaf(a, v.z - mu, bb)) * rm[i].z; v.w = wf_silu(fmaf(a, v.w - mu, bb)) * rm[i].w;
+                    } else {
+                        v.x = fmaf(a, v.x - mu, bb); v.y = fmaf(a, v.y - mu, bb); v.z = fmaf(a, v.z - mu, bb); v.w = fmaf(a, v.w - mu, bb);
+                    }
+                }
+                float4 h, l;
+                split4(v, h, l);
+                st4(Xs(buf, 0) + row * GW_XS + q * 4, h);
+                st4(Xs(buf, 1) + row * GW_XS + q * 4, l);
+            }
+        }
+    };
+
+    float acc[3][2][4][4];
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[t][i][j][e] = 0.f;
+
+    const int fr = lane >> 2, fc = lane & 3;
+    const int kcol = warp * 8 + fc;                                  // this lane's fragment columns inside a chunk: kcol, kcol + 4
+    int t0 = (int)((kbegin + kcol) % WF_T);
+    if (nchunks > 0) { load_chunk(0); store_chunk(0, 0); }
+    __syncthreads();
+    int buf = 0;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const bool more = ch + 1 < nchunks;
+        if (more) load_chunk(ch + 1);
+        const uint32_t* gh = reinterpret_cast<const uint32_t*>(Gs(buf, 0));
+        const uint32_t* gl = reinterpret_cast<const uint32_t*>(Gs(buf, 1));
+        const uint32_t* xh = reinterpret_cast<const uint32_t*>(Xs(buf, 0));
+        const uint32_t* xl = reinterpret_cast<const uint32_t*>(Xs(buf, 1));
+        const int t1 = t0 + 4 >= WF_T ? t0 + 4 - WF_T : t0 + 4;
+        uint32_t fah[2][4], fal[2][4];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+            const int o0 = (mi * 16 + fr) * GW_GS + kcol, o1 = o0 + 8 * GW_GS;
+            fah[mi][0] = gh[o0]; fah[mi][1] = gh[o1]; fah[mi][2] = gh[o0 + 4]; fah[mi][3] = gh[o1 + 4];
+            fal[mi][0] = gl[o0]; fal[mi][1] = gl[o1]; fal[mi][2] = gl[o0 + 4]; fal[mi][3] = gl[o1 + 4];
+        }
+#pragma unroll
+        for (int tap = 0; tap < 3; ++tap) {
+            const int dn = p.dn[tap];
+            const bool v0 = (t0 + dn >= 0) && (t0 + dn < WF_T), v1 = (t1 + dn >= 0) && (t1 + dn < WF_T);
+            uint32_t ah[2][4], al[2][4];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) {
+                ah[mi][0] = v0 ? fah[mi][0] : 0u; ah[mi][1] = v0 ? fah[mi][1] : 0u; ah[mi][2] = v1 ? fah[mi][2] : 0u; ah[mi][3] = v1 ? fah[mi][3] : 0u;
+                al[mi][0] = v0 ? fal[mi][0] : 0u; al[mi][1] = v0 ? fal[mi][1] : 0u; al[mi][2] = v1 ? fal[mi][2] : 0u; al[mi][3] = v1 ? fal[mi][3] : 0u;
+            }
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                const int o0 = (ni * 8 + fr) * GW_XS + G_HALO + kcol + dn;
+                uint32_t bh[2] = {xh[o0], xh[o0 + 4]}, bl[2] = {xl[o0], xl[o0 + 4]};
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi) {
+                    mma_tf32(acc[tap][mi][ni], al[mi], bh);
+                    mma_tf32(acc[tap][mi][ni], ah[mi], bl);
+                    mma_tf32(acc[tap][mi][ni], ah[mi], bh);
+                }
+            }
+        }
+        if (more) store_chunk(buf ^ 1, ch + 1);
+        __syncthreads();
+        buf ^= 1;
+        t0 = t0 + (GW_KCH % WF_T) >= WF_T ? t0 + (GW_KCH % WF_T) - WF_T : t0 + (GW_KCH % WF_T);
+    }
+
+    // reduce the 8 warps' partial sums through shared memory (stage buffers are free now), then one atomic per weight
+    float* red = smem;                                               // [3][32][32]
+    for (int w = 0; w < 8; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int tap = 0; tap < 3; ++tap)
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int co = mi * 16 + fr + (e >= 2 ? 8 : 0), ci = ni * 8 + fc * 2 + (e & 1);
+                            float* dst = red + (tap * 32 + co) * 32 + ci;
+                            *dst = (w == 0 ? 0.f : *dst) + acc[tap][mi][ni][e];
+                        }
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < 3 * 32 * 32; idx += G_NT) {
+        const int ci = idx & 31, co = (idx >> 5) & 31, tap = idx >> 10;
+        if (tap < p.ntaps && co < p.Cout && ci < p.Cin)
+            atomicAdd(p.dw + ((size_t)(g * p.Cout + co) * p.Cin + ci) * p.ntaps + tap, red[idx]);
+    }
+}
+
+}  // namespace
+
+bool wf_group_wgrad_ok(const WgradP& p)
+{
+    if (p.Pin != 1 || p.Pout != 1 || p.pmul != 1 || p.ntaps != 3 || p.Cin > 32 || p.Cout > 32) return false;
+    for (int t = 0; t < p.ntaps; ++t)
+        if (p.dp[t] != 0 || p.dn[t] < -G_HALO || p.dn[t] > 0) return false;
+    return true;
+}
+
+cudaError_t wf_launch_group_wgrad(const WgradP& p, int num_sms, cudaStream_t st)
+{
+    constexpr int smem = 2 * GW_STAGE * 4;
+    static_assert(2 * GW_STAGE >= 3 * 32 * 32, "reduction buffer must fit the stage buffers");
+    static bool cfg = false;
+    if (!cfg) {
+        cudaError_t e = cudaFuncSetAttribute(group_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        cfg = true;
+    }
+    long long splits = (2LL * num_sms) / p.groups;                       // two rounds of one-CTA-per-SM
+    const long long max_splits = (p.N + 8LL * GW_KCH - 1) / (8LL * GW_KCH);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    long long per = (p.N + splits - 1) / splits;
+    per = (per + GW_KCH - 1) / GW_KCH * GW_KCH;
+    splits = (p.N + per - 1) / per;
+    dim3 grid((unsigned)splits, 1, p.groups);
+    group_wgrad_kernel<<<grid, G_NT, smem, st>>>(p, per);
+    return cudaGetLastError();
+}

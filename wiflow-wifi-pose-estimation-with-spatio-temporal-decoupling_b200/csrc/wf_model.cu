@@ -28,6 +28,8 @@ thread_local std::vector<ProfRec> g_prof;
 std::atomic<long long> g_launches{0};
 constexpr int EVAL_CHUNK = 1024;
 // WF_DISABLE_TC=1 routes the pointwise convs through the CUDA-core GEMM instead of tcgen05 (A/B measurements only)
+// WF_SERIAL_WGRAD=1 keeps the weight-gradient kernels on the caller's stream (A/B measurements only)
+const bool g_overlap_wgrad = [] { const char* e = std::getenv("WF_SERIAL_WGRAD"); return !(e && e[0] == '1'); }();
 const bool g_use_tc = [] { const char* e = std::getenv("WF_DISABLE_TC"); return !(e && e[0] == '1'); }();
 
 struct ParamEntry { std::string name; long long off, numel; };
@@ -370,9 +372,33 @@ struct Ctx {
     int B; long long N; bool train; bool save; cudaStream_t st; int sms;
     bool profile = false;
     cudaError_t err = cudaSuccess;
+    cudaStream_t side = nullptr;      // backward only: the weight-gradient kernels run here, concurrently with backward-data on `st`
+    cudaEvent_t fork = nullptr;
     void ck(cudaError_t e) { if (err == cudaSuccess && e != cudaSuccess) err = e; }
     const float* mask_ptr(int i) const { return (masks && train) ? masks[i] : nullptr; }
 };
+
+// One side stream + two events per host thread, created on first use (before any CUDA-graph capture: TrainStep warms up
+// eagerly).  A weight gradient depends only on finished tensors (dy, BatchNorm-backward coefficients, forward activations)
+// and nothing downstream in the step reads it before the optimizer, so it overlaps the backward-data chain; both families are
+// latency bound at low occupancy, which is why sharing the SMs pays.
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; int dev = -1; };
+thread_local SideStream g_side;
+bool side_stream(SideStream& out)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    if (g_side.s == nullptr || g_side.dev != dev) {
+        SideStream n{};
+        if (cudaStreamCreateWithFlags(&n.s, cudaStreamNonBlocking) != cudaSuccess) return false;
+        if (cudaEventCreateWithFlags(&n.fork, cudaEventDisableTiming) != cudaSuccess) return false;
+        if (cudaEventCreateWithFlags(&n.join, cudaEventDisableTiming) != cudaSuccess) return false;
+        n.dev = dev;
+        g_side = n;
+    }
+    out = g_side;
+    return true;
+}
 
 struct Scope {          // one kernel launch (or launch pair): counts it and, when profiling, brackets it with events
     Ctx& c; int idx = -1;
@@ -503,8 +529,14 @@ void wgrad_conv(Ctx& c, int ui, Act in, Pro pro)
     for (int t = 0; t < u.ntaps; ++t) { p.dp[t] = u.dpf[t]; p.dn[t] = u.dnf[t]; }
     p.dw = c.grads + u.w_off;
     Scope sc(c, std::string(u.tc ? "tc_wgrad " : "conv_wgrad ") + u.name, conv_flops(u, c.N));
-    if (u.tc) c.ck(wf_launch_tc_wgrad(p, c.sms, c.st));
-    else c.ck(wf_launch_wgrad(p, c.sms, c.st));
+    cudaStream_t ws = c.st;
+    if (c.side) {                     // fork: everything this kernel reads has been enqueued on the main stream by now
+        c.ck(cudaEventRecord(c.fork, c.st));
+        c.ck(cudaStreamWaitEvent(c.side, c.fork, 0));
+        ws = c.side;
+    }
+    if (u.tc) c.ck(wf_launch_tc_wgrad(p, c.sms, ws));
+    else c.ck(wf_launch_wgrad(p, c.sms, ws));
 }
 
 // ------------------------------- forward schedules -------------------------------
@@ -869,6 +901,8 @@ int run_backward(const wf_block_desc* d, const float* x, const float* params, co
     if (need > ws_bytes) return fail(WF_E_WORKSPACE, "workspace too small: need " + std::to_string(need) + " bytes");
     Ctx c{n, params, grads, nullptr, nullptr, masks, B, (long long)B * T, true, true, st, num_sms()};
     c.profile = (flags & WF_FLAG_PROFILE) != 0;
+    SideStream ss{};
+    if (!c.profile && g_overlap_wgrad && side_stream(ss)) { c.side = ss.s; c.fork = ss.fork; }     // profiling times every kernel alone
     c.ck(cudaMemsetAsync(n.bstats, 0, n.bstats_bytes, st));
     c.ck(cudaMemsetAsync(grads, 0, n.nparams * sizeof(float), st));
 
@@ -934,6 +968,10 @@ int run_backward(const wf_block_desc* d, const float* x, const float* params, co
             RefStrides rs = ref_strides(d, false, n);
             c.ck((g_launches.fetch_add(1), 0) ? cudaSuccess : wf_launch_permute(n.din_buf, dx, n.in_C, n.in_P, B, rs.sb, rs.sc, rs.sp, rs.st, 0, c.sms, st));
         }
+    }
+    if (c.side) {                     // join: the caller's stream owns the complete gradient again
+        c.ck(cudaEventRecord(ss.join, c.side));
+        c.ck(cudaStreamWaitEvent(st, ss.join, 0));
     }
     if (c.err != cudaSuccess) return fail((int)c.err, std::string("CUDA error in backward: ") + cudaGetErrorString(c.err));
     return 0;

@@ -17,7 +17,7 @@ constexpr int THIN_MAXPOS = 18;      // input positions staged per tile
 __device__ __forceinline__ int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 template <int COUTP>
-__global__ void __launch_bounds__(256) thin_conv_kernel(const ConvP p, int PC)
+__global__ void __launch_bounds__(256, COUTP == 8 ? 4 : 3) thin_conv_kernel(const ConvP p, int PC)
 {
     constexpr int NT = THIN_NT, Q = NT / 4;
     extern __shared__ __align__(16) float smem[];

@@ -58,5 +58,31 @@ def full(src, dst):
             f.write('\n')
 
 
-if __name__ == '__main__':
+
+
+def traffic(dst, *reports):
+    """average dram__bytes_read.sum + dram__bytes_write.sum per launch of every kernel in the given reports -> JSON for bench.py"""
+    import json
+    agg = {}
+    for src in reports:
+        out = subprocess.run(['ncu', '-i', src, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+        rows = list(csv.reader(out.splitlines()))
+        if len(rows) < 3:
+            continue
+        hdr, units = rows[0], rows[1]
+        ik, ir, iw = hdr.index('Kernel Name'), hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
+        scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+        for v in rows[2:]:
+            name = re.sub(r'[<(].*', '', v[ik].replace('void ', '').replace('<unnamed>::', ''))
+            b = float(v[ir].replace(',', '')) * scale[units[ir]] + float(v[iw].replace(',', '')) * scale[units[iw]]
+            a = agg.setdefault(name, [0.0, 0])
+            a[0] += b
+            a[1] += 1
+    with open(dst, 'w') as f:
+        json.dump({k: a[0] / a[1] for k, a in agg.items()}, f, indent=1)
+
+
+if __name__ == '__main__' and sys.argv[1] == 'traffic':
+    traffic(sys.argv[2], *sys.argv[3:])
+elif __name__ == '__main__':
     {'launches': launches, 'full': full}[sys.argv[1]](sys.argv[2], sys.argv[3])

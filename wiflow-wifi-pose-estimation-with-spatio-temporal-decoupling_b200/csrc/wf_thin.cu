@@ -112,7 +112,7 @@ constexpr int TW_NT = 128;           // columns per region: one float4 per lane
 constexpr int TW_PC = 4;             // output positions per region
 
 template <int CINP>
-__global__ void __launch_bounds__(512) thin_wgrad_kernel(const WgradP p, int coutp, int PS, int nregions)
+__global__ void __launch_bounds__(384, 2) thin_wgrad_kernel(const WgradP p, int coutp, int PS, int nregions)
 {
     constexpr int NT = TW_NT, PC = TW_PC;
     extern __shared__ __align__(16) float smem[];

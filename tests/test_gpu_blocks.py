@@ -1,0 +1,164 @@
+"""GPU parity of the sub-block drop-ins (level "unit/kernel"): every reference class of models/tcn.py,
+models/convnet.py and models/attention.py, forward and backward, train mode (batch-statistics BatchNorm, dropout p = 0 so no
+RNG alignment is needed) and eval mode, against an fp64 torch evaluation of the SAME child modules in the reference's forward
+order.  The drop-in modules keep the reference's children (nn.Conv1d / nn.BatchNorm... as parameter containers), so the fp64
+truth below is the reference forward restated line by line: tcn.py:51-74, convnet.py:33-38,69-74, attention.py:37-80,95-98."""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _silu(x):
+    return x * torch.sigmoid(x)
+
+
+def ref_inner_tcn(m, x):                      # models/tcn.py:51-74 (dropout p = 0)
+    res = x if isinstance(m.downsample, torch.nn.Identity) else m.downsample(x)
+    out = x
+    for s in ('1', '2'):
+        out = getattr(m, f'chomp{s}')(getattr(m, f'conv{s}_group')(out))
+        out = _silu(getattr(m, f'bn{s}_group')(out))
+        out = _silu(getattr(m, f'bn{s}_pw')(getattr(m, f'conv{s}_pw')(out)))
+    return _silu(out + res)
+
+
+def ref_temporal(m, x):                       # models/tcn.py:96-97
+    for blk in m.network:
+        x = ref_inner_tcn(blk, x)
+    return x
+
+
+def ref_row_conv(m, x):                       # models/convnet.py:33-38 / 69-74 (dropout p = 0)
+    idn = m.downsample(x)
+    out = x
+    for i in (0, 4, 8):
+        out = m.block[i + 1](m.block[i](out))
+        if i < 8:
+            out = _silu(out)
+    return _silu(out + idn)
+
+
+def ref_axial(m, x):                          # models/attention.py:37-80
+    x = x.permute(0, 2, 1, 3) if m.width else x.permute(0, 3, 1, 2)
+    N, W, C, H = x.shape
+    x = x.contiguous().view(N * W, C, H)
+    qkv = m.bn_qkv(m.qkv_transform(x))
+    qkv = qkv.reshape(N * W, 3, m.out_planes, H).permute(1, 0, 2, 3)            # q = channels 0..63, k = 64..127, v = 128..191 (:51-53)
+    q, k, v = (t.reshape(N * W, m.groups, m.group_planes, H) for t in (qkv[0], qkv[1], qkv[2]))
+    qk = torch.einsum('bgci,bgcj->bgij', q, k)
+    sim = F.softmax(m.bn_similarity(qk), dim=-1)
+    sv = torch.einsum('bgij,bgcj->bgci', sim, v).reshape(N * W, m.out_planes, H)
+    out = m.bn_output(sv).view(N, W, m.out_planes, H)
+    return out.permute(0, 2, 1, 3) if m.width else out.permute(0, 2, 3, 1)
+
+
+def ref_dual(m, x):                           # models/attention.py:95-98
+    return ref_axial(m.height_axis, ref_axial(m.width_axis, x))
+
+
+def _zero_dropout(m):
+    for mod in m.modules():
+        if isinstance(mod, (torch.nn.Dropout, torch.nn.Dropout2d)):
+            mod.p = 0.0
+
+
+def _randomise_bn(m, g):
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+            mod.weight.data = torch.rand(mod.weight.shape, generator=g) + 0.5
+            mod.bias.data = torch.randn(mod.bias.shape, generator=g) * 0.2
+            mod.running_mean.data = torch.randn(mod.running_mean.shape, generator=g) * 0.1
+            mod.running_var.data = torch.rand(mod.running_var.shape, generator=g) + 0.5
+
+
+def _cases():
+    import wiflow_b200 as wf
+    return [
+        ('inner_tcn_540_440_d2', lambda: wf.InnerGroupedTemporalBlock(540, 440, 3, 1, 2, 4, dropout=0.0), (540, 20), ref_inner_tcn),
+        ('inner_tcn_240_240_d8', lambda: wf.InnerGroupedTemporalBlock(240, 240, 3, 1, 8, 16, dropout=0.0), (240, 20), ref_inner_tcn),
+        ('inner_tcn_40_60_d1', lambda: wf.InnerGroupedTemporalBlock(40, 60, 3, 1, 1, 2, dropout=0.0), (40, 20), ref_inner_tcn),
+        ('temporal_block', lambda: wf.TemporalBlock(540, [540, 440, 340, 240], kernel_size=3, dropout=0.0), (540, 20), ref_temporal),
+        ('convblock1_1_8', lambda: wf.ConvBlock1(1, 8), (1, 20, 240), ref_row_conv),
+        ('asym_8_16', lambda: wf.AsymmetricConvBlock(8, 16), (8, 20, 120), ref_row_conv),
+        ('asym_32_64', lambda: wf.AsymmetricConvBlock(32, 64), (32, 20, 30), ref_row_conv),
+        ('axial_width', lambda: wf.AxialAttention(64, 64, groups=8, width=True), (64, 15, 20), ref_axial),
+        ('axial_height', lambda: wf.AxialAttention(64, 64, groups=8, width=False), (64, 15, 20), ref_axial),
+        ('dual_axial', lambda: wf.DualAxialAttention(64, 64, groups=8), (64, 15, 20), ref_dual),
+    ]
+
+
+@pytest.mark.parametrize('idx', range(10))
+@pytest.mark.parametrize('B', [3, 16])
+def test_block_train_forward_backward(idx, B):
+    name, make, shape, ref_fn = _cases()[idx]
+    g = torch.Generator().manual_seed(100 + idx)
+    torch.manual_seed(idx)
+    m = make()
+    _zero_dropout(m)
+    _randomise_bn(m, g)
+    ref = copy.deepcopy(m).double().train()
+    m = m.cuda().train()
+    x = torch.randn(B, *shape, generator=g)
+    with torch.no_grad():                                         # shape probe only: eval mode leaves the running statistics alone
+        go = torch.randn(ref_fn(ref.eval(), x.double()).shape, generator=g)
+    ref.train()
+    # fp64 truth
+    xr = x.double().requires_grad_(True)
+    yr = ref_fn(ref, xr)
+    yr.backward(go.double())
+    # CUDA drop-in
+    xc = x.cuda().requires_grad_(True)
+    yc = m(xc)
+    yc.backward(go.cuda())
+    torch.cuda.synchronize()
+    assert yc.shape == yr.shape, name
+    assert rel_err(yc.detach().cpu(), yr.detach()) < 1e-4, name
+    assert rel_err(xc.grad.cpu(), xr.grad) < 2e-3, name
+    for (n, p), (_, pr) in zip(m.named_parameters(), ref.named_parameters()):
+        scale = pr.grad.abs().max().item()
+        if scale < 1e-9 * max(1.0, go.abs().max().item()):         # parameters a following BatchNorm cancels (conv biases)
+            continue
+        assert rel_err(p.grad.cpu(), pr.grad) < 5e-3, f'{name}: {n}'
+    # running statistics were updated exactly like torch's (momentum 0.1, unbiased variance)
+    for (n, b), (_, br) in zip(m.named_buffers(), ref.named_buffers()):
+        if n.endswith('num_batches_tracked'):
+            assert int(b) == int(br) == 1, n
+        else:
+            assert rel_err(b.cpu(), br) < 1e-4, f'{name}: {n}'
+
+
+@pytest.mark.parametrize('idx', range(10))
+def test_block_eval_forward(idx):
+    name, make, shape, ref_fn = _cases()[idx]
+    g = torch.Generator().manual_seed(200 + idx)
+    torch.manual_seed(idx)
+    m = make()
+    _randomise_bn(m, g)
+    ref = copy.deepcopy(m).double().eval()
+    m = m.cuda().eval()
+    x = torch.randn(5, *shape, generator=g)
+    with torch.no_grad():
+        yc = m(x.cuda())
+        yr = ref_fn(ref, x.double())
+    assert rel_err(yc.cpu(), yr) < 1e-4, name
+
+
+def test_state_dict_round_trip_with_reference_keys():
+    """295 keys, reference names; loading a state dict keeps the flat parameter buffer coherent"""
+    import wiflow_b200 as wf
+    torch.manual_seed(0)
+    a, b = wf.WiFlowPoseModel(dropout=0.5).cuda(), wf.WiFlowPoseModel(dropout=0.5).cuda()
+    sd = a.state_dict()
+    assert len(sd) == 295
+    assert 'tcn.network.1.downsample.0.weight' in sd and 'attention.width_axis.bn_similarity.running_var' in sd
+    b.load_state_dict(sd)
+    x = torch.randn(4, 540, 20, generator=torch.Generator().manual_seed(1)).cuda()
+    a.eval(); b.eval()
+    with torch.no_grad():
+        assert torch.equal(a(x), b(x))

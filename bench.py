@@ -263,6 +263,8 @@ def run_ours(args, rank, world, local_rank):
         # kernels behind the family tags (csrc/wf_model.cu Scope names); fwd and dgrad launches of a conv share one kernel
         kernels = {'pw_tc_kernel (tcgen05 3xTF32 pointwise conv, fwd + dgrad)': ('tc_fwd', 'tc_dgrad'),
                    'pw_wgrad_tc_kernel (tcgen05 3xTF32 pointwise wgrad)': ('tc_wgrad',),
+                   'slide_conv_kernel (sliding-window mma.sync 3xTF32 position-tap conv, fwd + dgrad)': ('slide_fwd', 'slide_dgrad'),
+                   'slide_wgrad_kernel (sliding-window mma.sync 3xTF32 wgrad)': ('slide_wgrad',),
                    'conv_gemm_kernel (FP32 implicit-GEMM conv, fwd + dgrad)': ('conv_fwd', 'conv_dgrad'),
                    'conv_wgrad_kernel (FP32 conv wgrad)': ('conv_wgrad',),
                    'thin_conv_kernel (direct conv <=16 channels, fwd + dgrad)': ('thin_fwd', 'thin_dgrad'),

@@ -464,6 +464,7 @@ static cudaError_t launch_conv_t(const ConvP& p, cudaStream_t st)
 
 cudaError_t wf_launch_conv(const ConvP& p, cudaStream_t st)
 {
+    if (wf_slide_conv_ok(p)) return wf_launch_slide_conv(p, st);
     if (wf_thin_conv_ok(p)) return wf_launch_thin_conv(p, st);
     if (wf_group_conv_ok(p)) return wf_launch_group_conv(p, st);
     switch (conv_cfg_for(p.Cout)) {
@@ -492,6 +493,7 @@ static cudaError_t launch_wgrad_t(WgradP p, int target_ctas, cudaStream_t st)
 
 cudaError_t wf_launch_wgrad(const WgradP& p, int num_sms, cudaStream_t st)
 {
+    if (wf_slide_wgrad_ok(p)) return wf_launch_slide_wgrad(p, num_sms, st);
     if (wf_thin_wgrad_ok(p)) return wf_launch_thin_wgrad(p, num_sms, st);
     if (wf_group_wgrad_ok(p)) return wf_launch_group_wgrad(p, num_sms, st);
     const int target = num_sms * 6;

@@ -75,6 +75,11 @@ bool wf_thin_conv_ok(const ConvP& p);
 cudaError_t wf_launch_thin_conv(const ConvP& p, cudaStream_t st);
 bool wf_thin_wgrad_ok(const WgradP& p);
 cudaError_t wf_launch_thin_wgrad(const WgradP& p, int num_sms, cudaStream_t st);
+// sliding-window mma.sync path for position-tap convs (wf_slide.cu)
+bool wf_slide_conv_ok(const ConvP& p);
+cudaError_t wf_launch_slide_conv(const ConvP& p, cudaStream_t st);
+bool wf_slide_wgrad_ok(const WgradP& p);
+cudaError_t wf_launch_slide_wgrad(const WgradP& p, int num_sms, cudaStream_t st);
 // tcgen05 pointwise-conv path (wf_tc.cu)
 long long wf_tc_pack_floats(int m, int k);
 cudaError_t wf_launch_tc_pack(const TcPackTable& tab, const float* params, float* packed, cudaStream_t st);

@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(32 * MW * NW, MINB) slide_conv_kernel(const Co
         for (int idx = tid; idx < R * padw; idx += NT) ring[(idx / padw) * slab_words + p.Cin * XS + idx % padw] = 0.f;
     }
     if (tid < 2 * BM) red[tid / BM][tid % BM] = 0.0;
+    __syncthreads();                                    // the coefficient table is read by the stores that prime the ring
 
     // ---- loader descriptors (position independent) ----
     int goff[LD], sd[LD];
@@ -395,6 +396,7 @@ __global__ void __launch_bounds__(SW_NT, MINB) slide_wgrad_kernel(const WgradP p
         for (int c = tid; c < p.Cout; c += SW_NT) st4(gcoef + 4 * c, make_float4(p.g_a[c], p.g_b[c], p.g_c[c], p.g_d[c]));
     if (PRO != PRO_NONE)
         for (int c = tid; c < p.Cin; c += SW_NT) st4(xcoef + 4 * c, make_float4(p.pro_a[c], p.pro_b[c], 0.f, p.pro_d[c]));
+    __syncthreads();                                             // coefficient tables are read by the stores that prime the buffers
 
     float acc[NTAPS][MTW][NTW][4];
 #pragma unroll

@@ -632,6 +632,7 @@ __global__ void __launch_bounds__(SW_NT, MINB) slide_wgrad_kernel(const WgradP p
 const bool g_use_slide = [] { const char* e = std::getenv("WF_DISABLE_SLIDE"); return !(e && e[0] == '1'); }();
 // WF_SLIDE_MIN_CH: layers whose Cin and Cout are both below it stay on wf_thin.cu (A/B measurements)
 const int g_slide_min_ch = [] { const char* e = std::getenv("WF_SLIDE_MIN_CH"); return e ? std::atoi(e) : 16; }();
+const int g_slide_min_ch_wgrad = [] { const char* e = std::getenv("WF_SLIDE_MIN_CH_WGRAD"); return e ? std::atoi(e) : 8; }();
 constexpr int SMEM_MAX = 227 * 1024;
 constexpr int PS_MAX = 4;
 
@@ -754,6 +755,8 @@ cudaError_t slide_conv_pro(const ConvP& p, int num_sms, cudaStream_t st, bool dr
 cudaError_t slide_conv_dispatch(const ConvP& p, int num_sms, cudaStream_t st, bool dry)
 {
     if (p.Cout > 32) return slide_conv_pro<2, 2, 2, 8, 5, 1>(p, num_sms, st, dry);        // 64 x 128 tile, 16 warps of 32 x 16
+    if (p.Cout > 16 && p.Cin <= 32 && p.ntaps <= 3)
+        return slide_conv_pro<2, 2, 1, 8, 5, 2>(p, num_sms, st, dry);                     // same tile, <= 32 input channels: two CTAs per SM
     if (p.Cout > 16) return slide_conv_pro<2, 2, 1, 8, 9, 1>(p, num_sms, st, dry);        // 32 x 128 tile, 8 warps of 32 x 16
     return slide_conv_pro<1, 2, 1, 8, 5, 2>(p, num_sms, st, dry);                         // 16 x 128 tile, 8 warps of 16 x 16
 }
@@ -867,7 +870,7 @@ cudaError_t wf_launch_slide_conv(const ConvP& p, cudaStream_t st) { return slide
 bool wf_slide_wgrad_ok(const WgradP& p)
 {
     if (!g_use_slide || p.groups != 1 || p.Cout > 64 || p.Cin > 64 || p.Cin < 8) return false;
-    if (p.Cin < g_slide_min_ch && p.Cout < g_slide_min_ch) return false;
+    if (p.Cin < g_slide_min_ch_wgrad && p.Cout < g_slide_min_ch_wgrad) return false;
     if (p.Pin == 1 && p.Pout == 1) return false;
     if (p.mask && p.m_st != 0) return false;
     if (!fits_int32((long long)p.Cin * p.in_sc + (long long)p.Pin * p.in_sp) || !fits_int32((long long)p.Cout * p.Pout * p.N)) return false;

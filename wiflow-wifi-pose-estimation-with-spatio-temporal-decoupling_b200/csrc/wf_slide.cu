@@ -360,6 +360,246 @@ __global__ void __launch_bounds__(32 * MW * NW, MINB) slide_conv_kernel(const Co
 }
 
 // =========================================================================================================
+// forward / backward-data of the thin layers (<= 8 output channels, <= 16 input channels: ConvBlock1 `up`, residual block 0,
+// the input gradients of residual block 1).  Same sliding window, but the MMA operand roles are swapped: the COLUMNS are the
+// M dimension (16 per tile) and the <= 8 output channels the N dimension, so no half of a 16-row tile is padding and the
+// 3 x Cin x 8 weights live in registers (split once per CTA) instead of shared memory:
+//   D[col][co] = sum_tap sum_k X'[k][ipos(opos,tap)][col] * W[tap][k][co]
+// A warp owns MI tiles of 16 columns; accumulator lane layout: columns fr / fr+8, channels 2fc / 2fc+1.
+// =========================================================================================================
+template <int MI, int NTAPS, int K8S, int LD, int MINB, int PRO>
+__global__ void __launch_bounds__(256, MINB) slide_thin_kernel(const ConvP p, const SlideGeo g)
+{
+    constexpr int NT = 256, NW = 8, BN = 16 * MI * NW, XS = BN + 2 * SL_H, Q = XS / 4, K8 = 8 * K8S;
+    extern __shared__ __align__(16) float smem[];
+    __shared__ double red[2][8];
+    const int tid = threadIdx.x, lane = tid & 31, wn = tid >> 5;
+    const int fr = lane >> 2, fc = lane & 3;
+    const int R = g.R;
+    float* ring = smem;                                 // R x [K8][XS]
+    float* coef = ring + R * K8 * XS;                   // [K8] x (a, b, c, d)
+    constexpr int slab_words = K8 * XS;
+    const int n0 = blockIdx.x * BN;
+    const int op0 = blockIdx.y * g.PC, op1 = min(op0 + g.PC, p.Pout);
+    const int per = p.Cin * Q;
+
+    // ---- weights: B fragments (k = input channel, n = output channel) of every tap, split once ----
+    uint32_t bwh[NTAPS][K8S][2], bwl[NTAPS][K8S][2];
+#pragma unroll
+    for (int tap = 0; tap < NTAPS; ++tap)
+#pragma unroll
+        for (int ks = 0; ks < K8S; ++ks)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = ks * 8 + fc + 4 * h;
+                const float w = (k < p.Kpad && fr < p.Mpad) ? p.w[((size_t)tap * p.Kpad + k) * p.Mpad + fr] : 0.f;
+                split_tf32(w, bwh[tap][ks][h], bwl[tap][ks][h]);
+            }
+    if (PRO != PRO_NONE)
+        for (int k = tid; k < p.Cin; k += NT)
+            st4(coef + 4 * k, make_float4(p.pro_a[k], p.pro_b[k], PRO == PRO_BNBWD ? p.pro_c[k] : 0.f, p.pro_d[k]));
+    {
+        const int padw = (K8 - p.Cin) * XS;
+        for (int idx = tid; idx < R * padw; idx += NT) ring[(idx / padw) * slab_words + p.Cin * XS + idx % padw] = 0.f;
+    }
+    if (tid < 16) red[tid / 8][tid % 8] = 0.0;
+    __syncthreads();
+
+    // ---- loader (same scheme as slide_conv_kernel) ----
+    int goff[LD], sd[LD];
+    float mk[LD];
+    float4 rv[LD], rv2[PRO == PRO_BNBWD ? LD : 1];
+#pragma unroll
+    for (int i = 0; i < LD; ++i) {
+        const int idx = tid + i * NT;
+        goff[i] = -1; sd[i] = -1; mk[i] = 1.f;
+        if (idx < g.cap * per) {
+            const int s = idx / per, rem = idx - s * per, k = rem / Q, q = rem - k * Q;
+            sd[i] = (k * XS + 4 * q) | (s << 16) | (k << 20);
+            const int nn = n0 - SL_H + 4 * q;
+            if (nn >= 0 && nn < p.N) {
+                const int b = nn / WF_T, t = nn - b * WF_T;
+                goff[i] = (int)((long long)k * p.in_sc + (long long)s * p.in_sp + (long long)b * p.in_sb + t);
+                if (PRO == PRO_BNSILU && p.mask) mk[i] = p.mask[(long long)b * p.m_sb + (long long)k * p.m_sc];
+            }
+        }
+    }
+    const int in_sp = (int)p.in_sp;
+    int base_ipos = 0, base_slot = 0;
+    auto load_slabs = [&](int a, int cnt) {
+        const int aoff = a * in_sp;
+#pragma unroll
+        for (int i = 0; i < LD; ++i) {
+            rv[i] = f4zero();
+            if (PRO == PRO_BNBWD) rv2[PRO == PRO_BNBWD ? i : 0] = f4zero();
+            if (goff[i] >= 0 && desc_slab(sd[i]) < cnt) {
+                rv[i] = ld4(p.in + (goff[i] + aoff));
+                if (PRO == PRO_BNBWD) rv2[PRO == PRO_BNBWD ? i : 0] = ld4(p.in2 + (goff[i] + aoff));
+            }
+        }
+    };
+    auto store_slabs = [&](int a, int cnt) {
+        const int aslot = ring_slot(a, base_ipos, base_slot, R);
+#pragma unroll
+        for (int i = 0; i < LD; ++i) {
+            if (sd[i] >= 0 && desc_slab(sd[i]) < cnt) {
+                float4 v = rv[i];
+                if (PRO != PRO_NONE && goff[i] >= 0) v = apply_pro<PRO>(v, rv2[PRO == PRO_BNBWD ? i : 0], mk[i], ld4(coef + 4 * desc_chan(sd[i])));
+                int slot = aslot + desc_slab(sd[i]);
+                if (slot >= R) slot -= R;
+                st4(ring + slot * slab_words + desc_off(sd[i]), v);
+            }
+        }
+    };
+
+    // ---- epilogue: the accumulator layout (columns fr / fr+8, channels 2fc / 2fc+1) is turned into 4-column quads through a
+    //      per-warp scratch tile [8 channels][32 columns]; lane -> channels lane/8 and lane/8 + 4, column quad lane%8 ----
+    static_assert(MI == 2, "the epilogue scratch assumes 32 columns per warp");
+    constexpr int SS = 36;                               // scratch row stride: conflict-free scalar stores and 128-bit loads
+    float* scr = coef + 4 * K8 + wn * 8 * SS;
+    int rowoff[2];
+    bool chv[2];
+    float emk[2], bias[2], es[2], et[2], em[2];
+    double sd0[2], sd1[2];
+    const int qn = n0 + wn * 32 + (lane & 7) * 4;
+    const int qb = qn / WF_T, qt = qn - qb * WF_T;
+    const int ecol = qn < p.N ? (int)((long long)qb * p.out_sb + qt) : -1;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int m = (lane >> 3) + 4 * j;
+        chv[j] = m < p.Cout;
+        rowoff[j] = (int)((long long)m * p.out_sc);
+        sd0[j] = 0.0; sd1[j] = 0.0; bias[j] = 0.f; es[j] = 0.f; et[j] = 0.f; em[j] = 0.f; emk[j] = 1.f;
+        if (chv[j]) {
+            if (p.bias) bias[j] = p.bias[m];
+            if (p.epi_mode == EPI_DSILU) { es[j] = p.e_scale[m]; et[j] = p.e_shift[m]; }
+            if (p.epi_mode == EPI_DSILU || p.epi_mode == EPI_DAFF) em[j] = p.e_mean[m];
+            if (p.epi_mode == EPI_DSILU && p.emask && qn < p.N) emk[j] = p.emask[(long long)qb * p.em_sb + (long long)m * p.em_sc];
+        }
+    }
+    const int epi = p.epi_mode;
+    const bool accum = p.accumulate != 0;
+
+    auto do_pos = [&](int opos) {
+        float acc[MI][4], cor[MI][4];
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { acc[i][e] = 0.f; cor[i][e] = 0.f; }
+#pragma unroll
+        for (int tap = 0; tap < NTAPS; ++tap) {
+            int ipos = opos * p.pmul + p.dp[tap];
+            if (ipos < 0) continue;
+            if (p.pdiv == 2) { if (ipos & 1) continue; ipos >>= 1; }
+            if (ipos >= p.Pin) continue;
+            const float* xs = ring + ring_slot(ipos, base_ipos, base_slot, R) * slab_words + fc * XS + SL_H + wn * MI * 16 + fr;
+#pragma unroll
+            for (int ks = 0; ks < K8S; ++ks) {
+                uint32_t ah[MI][4], al[MI][4];
+#pragma unroll
+                for (int mi = 0; mi < MI; ++mi) {
+                    const float* x0 = xs + ks * 8 * XS + mi * 16;
+                    split_tf32(x0[0], ah[mi][0], al[mi][0]);
+                    split_tf32(x0[8], ah[mi][1], al[mi][1]);
+                    split_tf32(x0[4 * XS], ah[mi][2], al[mi][2]);
+                    split_tf32(x0[4 * XS + 8], ah[mi][3], al[mi][3]);
+                }
+#pragma unroll
+                for (int mi = 0; mi < MI; ++mi) mma_tf32(cor[mi], al[mi], bwh[tap][ks]);
+#pragma unroll
+                for (int mi = 0; mi < MI; ++mi) mma_tf32(acc[mi], ah[mi], bwh[tap][ks]);
+#pragma unroll
+                for (int mi = 0; mi < MI; ++mi) mma_tf32(cor[mi], ah[mi], bwl[tap][ks]);
+            }
+        }
+        // accumulators -> scratch (element e of tile mi: column mi*16 + fr + 8*(e>>1), channel 2fc + (e&1))
+        __syncwarp();
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) scr[(2 * fc + (e & 1)) * SS + mi * 16 + fr + 8 * (e >> 1)] = acc[mi][e] + cor[mi][e];
+        __syncwarp();
+        const int pbase = (int)((long long)opos * p.out_sp);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float s0 = 0.f, s1 = 0.f;
+            if (chv[j] && ecol >= 0) {
+                const float4 q4 = ld4(scr + ((lane >> 3) + 4 * j) * SS + (lane & 7) * 4);
+                float v[4] = {q4.x + bias[j], q4.y + bias[j], q4.z + bias[j], q4.w + bias[j]};
+                const int off = rowoff[j] + pbase + ecol;
+                if (accum) { const float4 o = ld4(p.out + off); v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w; }
+                if (epi == EPI_STATS) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { s0 += v[e]; s1 = fmaf(v[e], v[e], s1); }
+                } else if (epi == EPI_DSILU || epi == EPI_DAFF) {
+                    const float4 r4 = ld4(p.eraw + off);
+                    const float r[4] = {r4.x - em[j], r4.y - em[j], r4.z - em[j], r4.w - em[j]};
+                    if (epi == EPI_DSILU) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) v[e] = v[e] * emk[j] * wf_dsilu(fmaf(es[j], r[e], et[j]));
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { s0 += v[e]; s1 = fmaf(v[e], r[e], s1); }
+                }
+                st4(p.out + off, make_float4(v[0], v[1], v[2], v[3]));
+            }
+            sd0[j] += (double)s0; sd1[j] += (double)s1;
+        }
+    };
+
+    // ---- the walk (identical to slide_conv_kernel) ----
+    int staged_hi = -1;
+    {
+        int lo, hi;
+        step_range(p.pmul, p.pdiv, p.Pin, g.dpmin, g.dpmax, op0, min(op0 + g.PS, op1), lo, hi);
+        base_ipos = lo;
+        for (int a = lo; a <= hi; a += g.cap) {
+            const int cnt = min(g.cap, hi - a + 1);
+            load_slabs(a, cnt);
+            store_slabs(a, cnt);
+        }
+        if (hi >= lo) staged_hi = hi;
+    }
+    __syncthreads();
+    for (int op = op0; op < op1; op += g.PS) {
+        const int oe = min(op + g.PS, op1);
+        {
+            int lo, hi;
+            step_range(p.pmul, p.pdiv, p.Pin, g.dpmin, g.dpmax, op, oe, lo, hi);
+            if (hi >= lo && lo > base_ipos) { base_slot = ring_slot(lo, base_ipos, base_slot, R); base_ipos = lo; }
+        }
+        int na = 0, ncnt = 0;
+        if (oe < op1) {
+            int nlo, nhi;
+            step_range(p.pmul, p.pdiv, p.Pin, g.dpmin, g.dpmax, oe, min(oe + g.PS, op1), nlo, nhi);
+            na = max(staged_hi + 1, nlo);
+            ncnt = max(nhi - na + 1, 0);
+        }
+        if (ncnt) load_slabs(na, ncnt);
+        for (int opos = op; opos < oe; ++opos) do_pos(opos);
+        if (g.two_sync) __syncthreads();
+        if (ncnt) { store_slabs(na, ncnt); staged_hi = na + ncnt - 1; }
+        __syncthreads();
+    }
+
+    // ---- BatchNorm sums: the 8 lanes with equal lane/8 hold the same two channels ----
+    if (epi != EPI_STORE && p.stat0 != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            double a = sd0[j], b = sd1[j];
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+            if ((lane & 7) == 0) { atomicAdd(&red[0][(lane >> 3) + 4 * j], a); atomicAdd(&red[1][(lane >> 3) + 4 * j], b); }
+        }
+        __syncthreads();
+        if (tid < 8 && tid < p.Cout) {
+            atomicAdd(p.stat0 + tid, red[0][tid]);
+            atomicAdd(p.stat1 + tid, red[1][tid]);
+        }
+    }
+}
+
+// =========================================================================================================
 // backward-weights
 //   dW[co][ci][tap] = sum_{opos,n} G'[co][opos][n] * X'[ci][ipos(opos,tap)][n + dn(tap)]
 // G' = BatchNorm-backward of (dy, raw), X' = prologue of the layer input.  Persistent CTAs walk (column tile, position range)
@@ -632,6 +872,8 @@ __global__ void __launch_bounds__(SW_NT, MINB) slide_wgrad_kernel(const WgradP p
 const bool g_use_slide = [] { const char* e = std::getenv("WF_DISABLE_SLIDE"); return !(e && e[0] == '1'); }();
 // WF_SLIDE_MIN_CH: layers whose Cin and Cout are both below it stay on wf_thin.cu (A/B measurements)
 const int g_slide_min_ch = [] { const char* e = std::getenv("WF_SLIDE_MIN_CH"); return e ? std::atoi(e) : 16; }();
+// WF_DISABLE_SLIDE_THIN=1: <= 8-channel forward / backward-data layers stay on wf_thin.cu (A/B measurements)
+const bool g_slide_thin = [] { const char* e = std::getenv("WF_DISABLE_SLIDE_THIN"); return !(e && e[0] == '1'); }();
 const int g_slide_min_ch_wgrad = [] { const char* e = std::getenv("WF_SLIDE_MIN_CH_WGRAD"); return e ? std::atoi(e) : 8; }();
 constexpr int SMEM_MAX = 227 * 1024;
 constexpr int PS_MAX = 4;
@@ -752,8 +994,72 @@ cudaError_t slide_conv_pro(const ConvP& p, int num_sms, cudaStream_t st, bool dr
     }
 }
 
+template <int MI, int NTAPS, int K8S, int LD, int MINB, int PRO>
+cudaError_t launch_slide_thin(const ConvP& p, int num_sms, cudaStream_t st, bool dry)
+{
+    constexpr int NT = 256, BN = 16 * MI * 8, XS = BN + 2 * SL_H, Q = XS / 4, K8 = 8 * K8S;
+    SlideGeo g{};
+    tap_range(p.dp, p.ntaps, g.dpmin, g.dpmax);
+    g.cap = (LD * NT) / (p.Cin * Q);
+    if (g.cap > 15) g.cap = 15;
+    if (g.cap < 1) return cudaErrorInvalidConfiguration;
+    const size_t fixed = ((size_t)4 * K8 + 8 * 8 * 36) * 4, slab = (size_t)K8 * XS * 4;       // coefficients + per-warp epilogue scratch
+    int span = 0;
+    g.PS = 0;
+    for (int ps = PS_MAX; ps >= 1 && !g.PS; --ps) {
+        int ring, newmax;
+        window_geometry(p.pmul, p.pdiv, p.Pin, p.Pout, g.dpmin, g.dpmax, ps, span, ring, newmax);
+        if (newmax > g.cap) continue;
+        if (ps == 1 || ring * slab <= 56 * 1024) { g.PS = ps; g.R = ring; }
+    }
+    if (!g.PS) return cudaErrorInvalidConfiguration;
+    const size_t smem = fixed + g.R * slab;
+    if (dry) return cudaSuccess;
+    static size_t cfg = 0;
+    if (smem > cfg) {
+        cudaError_t e = cudaFuncSetAttribute(slide_thin_kernel<MI, NTAPS, K8S, LD, MINB, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        cfg = smem;
+    }
+    int occ = (int)((size_t)SMEM_MAX / (smem + 2048));
+    if (occ > MINB) occ = MINB;
+    if (occ < 1) occ = 1;
+    const int coltiles = (p.N + BN - 1) / BN;
+    const double c_slab = (double)p.Cin * XS * 3.0 / 128.0 * 4.0;
+    const double c_pos = (double)(BN / 16) * K8S * p.ntaps * 3 * 2.0 * 1.5 + (double)BN * 8 / 128.0 * 8.0 + 100.0;
+    g.PC = pick_pc(p.Pout, g.PS, coltiles, num_sms * occ, span, c_slab, c_pos, 400.0);
+    dim3 grid(coltiles, (p.Pout + g.PC - 1) / g.PC, 1);
+    slide_thin_kernel<MI, NTAPS, K8S, LD, MINB, PRO><<<grid, NT, smem, st>>>(p, g);
+    return cudaGetLastError();
+}
+
+template <int NTAPS, int K8S>
+cudaError_t slide_thin_pro(const ConvP& p, int num_sms, cudaStream_t st, bool dry)
+{
+    switch (p.pro_mode) {
+        case PRO_NONE: return launch_slide_thin<2, NTAPS, K8S, 5, 2, PRO_NONE>(p, num_sms, st, dry);
+        case PRO_BNSILU: return launch_slide_thin<2, NTAPS, K8S, 5, 2, PRO_BNSILU>(p, num_sms, st, dry);
+        case PRO_AFFINE: return launch_slide_thin<2, NTAPS, K8S, 5, 2, PRO_AFFINE>(p, num_sms, st, dry);
+        default: return launch_slide_thin<2, NTAPS, K8S, 5, 2, PRO_BNBWD>(p, num_sms, st, dry);
+    }
+}
+
+// <= 8 output channels, 8..16 input channels, position taps only
+bool slide_thin_shape(const ConvP& p)
+{
+    if (p.Cout > 8 || p.Cin > 16 || (p.ntaps != 1 && p.ntaps != 3) || p.Mpad > 8) return false;
+    for (int t = 0; t < p.ntaps; ++t) if (p.dn[t] != 0) return false;
+    return true;
+}
+cudaError_t slide_thin_dispatch(const ConvP& p, int num_sms, cudaStream_t st, bool dry)
+{
+    if (p.ntaps == 3) return p.Cin > 8 ? slide_thin_pro<3, 2>(p, num_sms, st, dry) : slide_thin_pro<3, 1>(p, num_sms, st, dry);
+    return p.Cin > 8 ? slide_thin_pro<1, 2>(p, num_sms, st, dry) : slide_thin_pro<1, 1>(p, num_sms, st, dry);
+}
+
 cudaError_t slide_conv_dispatch(const ConvP& p, int num_sms, cudaStream_t st, bool dry)
 {
+    if (g_slide_thin && slide_thin_shape(p)) return slide_thin_dispatch(p, num_sms, st, dry);
     if (p.Cout > 32) return slide_conv_pro<2, 2, 2, 8, 5, 1>(p, num_sms, st, dry);        // 64 x 128 tile, 16 warps of 32 x 16
     if (p.Cout > 16 && p.Cin <= 32 && p.ntaps <= 3)
         return slide_conv_pro<2, 2, 1, 8, 5, 2>(p, num_sms, st, dry);                     // same tile, <= 32 input channels: two CTAs per SM
@@ -856,7 +1162,7 @@ bool fits_int32(long long v) { return v >= 0 && v < (1LL << 31); }
 bool wf_slide_conv_ok(const ConvP& p)
 {
     if (!g_use_slide || p.groups != 1 || p.Cout > 64 || p.Cin > 64 || p.Cin < 8 || p.Mpad < p.Cout || (p.Mpad & 3)) return false;
-    if (p.Cin < g_slide_min_ch && p.Cout < g_slide_min_ch) return false;      // 8-channel layers: the direct kernels of wf_thin.cu are faster (measured)
+    if (p.Cin < g_slide_min_ch && p.Cout < g_slide_min_ch && !(g_slide_thin && slide_thin_shape(p))) return false;
     if (p.pdiv != 1 && p.pdiv != 2) return false;
     if (p.Pin == 1 && p.Pout == 1) return false;              // pure time-tap layers belong to wf_group.cu / wf_tc.cu
     if ((p.mask && p.m_st != 0) || (p.emask && p.em_st != 0)) return false;

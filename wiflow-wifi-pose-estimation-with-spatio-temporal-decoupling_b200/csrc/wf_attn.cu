@@ -15,7 +15,7 @@ namespace {
 enum { ATT_FWD_STATS = 0, ATT_FWD = 1, ATT_BWD_STATS = 2, ATT_BWD = 3 };
 
 template <int L, int LP, int RT, bool WIDTH, int MODE>
-__global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * L <= 320 ? 3 : 2) : 1) attn_kernel(const AttnP p)
+__global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * L <= 320 ? 3 : 2) : 0) attn_kernel(const AttnP p)
 {
     constexpr int NT = RT * 8 * L;
     constexpr int CS = RT * LP;                         // channel stride inside a tile

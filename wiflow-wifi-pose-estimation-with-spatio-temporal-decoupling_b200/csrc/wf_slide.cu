@@ -216,6 +216,8 @@ __global__ void __launch_bounds__(32 * MW * NW, MINB) slide_conv_kernel(const Co
 
     // ---- one output position: taps out of the ring, then the epilogue ----
     auto do_pos = [&](int opos) {
+        const int pbase = (int)((long long)opos * p.out_sp);
+        const bool need_raw = epi == EPI_DSILU || epi == EPI_DAFF;
         float acc[MI][NI][4], cor[MI][NI][4];
 #pragma unroll
         for (int i = 0; i < MI; ++i)
@@ -266,7 +268,6 @@ __global__ void __launch_bounds__(32 * MW * NW, MINB) slide_conv_kernel(const Co
             }
         }
         // lanes fc and fc^1 swap halves so each owns 4 consecutive columns of one output row
-        const int pbase = (int)((long long)opos * p.out_sp);
 #pragma unroll
         for (int mi = 0; mi < MI; ++mi) {
             float s0 = 0.f, s1 = 0.f;
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(32 * MW * NW, MINB) slide_conv_kernel(const Co
                     if (epi == EPI_STATS) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) { s0 += v[j]; s1 = fmaf(v[j], v[j], s1); }
-                    } else if (epi == EPI_DSILU || epi == EPI_DAFF) {
+                    } else if (need_raw) {
                         const float4 r4 = ld4(p.eraw + off);
                         const float r[4] = {r4.x - em[mi], r4.y - em[mi], r4.z - em[mi], r4.w - em[mi]};
                         if (epi == EPI_DSILU) {
@@ -481,6 +482,22 @@ __global__ void __launch_bounds__(256, MINB) slide_thin_kernel(const ConvP p, co
     const bool accum = p.accumulate != 0;
 
     auto do_pos = [&](int opos) {
+        // operands of the epilogue (raw tensor of the BatchNorm being differentiated, running input gradient) are requested
+        // before the MMAs so that their latency is covered
+        const int pbase = (int)((long long)opos * p.out_sp);
+        const bool need_raw = epi == EPI_DSILU || epi == EPI_DAFF;
+        constexpr bool PREF = PRO == PRO_BNBWD;          // backward-data launches
+        float4 praw[PREF ? 2 : 1], pacc[PREF ? 2 : 1];
+        if (PREF) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                praw[PREF ? j : 0] = f4zero(); pacc[PREF ? j : 0] = f4zero();
+                if (chv[j] && ecol >= 0) {
+                    if (need_raw) praw[PREF ? j : 0] = ld4(p.eraw + (rowoff[j] + pbase + ecol));
+                    if (accum) pacc[PREF ? j : 0] = ld4(p.out + (rowoff[j] + pbase + ecol));
+                }
+            }
+        }
         float acc[MI][4], cor[MI][4];
 #pragma unroll
         for (int i = 0; i < MI; ++i)
@@ -519,7 +536,6 @@ __global__ void __launch_bounds__(256, MINB) slide_thin_kernel(const ConvP p, co
 #pragma unroll
             for (int e = 0; e < 4; ++e) scr[(2 * fc + (e & 1)) * SS + mi * 16 + fr + 8 * (e >> 1)] = acc[mi][e] + cor[mi][e];
         __syncwarp();
-        const int pbase = (int)((long long)opos * p.out_sp);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             float s0 = 0.f, s1 = 0.f;
@@ -527,12 +543,12 @@ __global__ void __launch_bounds__(256, MINB) slide_thin_kernel(const ConvP p, co
                 const float4 q4 = ld4(scr + ((lane >> 3) + 4 * j) * SS + (lane & 7) * 4);
                 float v[4] = {q4.x + bias[j], q4.y + bias[j], q4.z + bias[j], q4.w + bias[j]};
                 const int off = rowoff[j] + pbase + ecol;
-                if (accum) { const float4 o = ld4(p.out + off); v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w; }
+                if (accum) { const float4 o = PREF ? pacc[PREF ? j : 0] : ld4(p.out + off); v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w; }
                 if (epi == EPI_STATS) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) { s0 += v[e]; s1 = fmaf(v[e], v[e], s1); }
-                } else if (epi == EPI_DSILU || epi == EPI_DAFF) {
-                    const float4 r4 = ld4(p.eraw + off);
+                } else if (need_raw) {
+                    const float4 r4 = PREF ? praw[PREF ? j : 0] : ld4(p.eraw + off);
                     const float r[4] = {r4.x - em[j], r4.y - em[j], r4.z - em[j], r4.w - em[j]};
                     if (epi == EPI_DSILU) {
 #pragma unroll

@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(SW_NT, MINB) slide_wgrad_kernel(const WgradP p
     const int gslab = BM * SW_GS, xslab = BCI * SW_XS;
     float* Gs = smem;                                            // 2 x PS x [BM][SW_GS]
     float* ring = Gs + 2 * PS * gslab;                           // R x [BCI][SW_XS]
-    float* gcoef = ring + R * xslab;                             // [BM] x (a, b, c, d)
+    float* gcoef = ring + (R + 1) * xslab;                       // slab R of the ring is never written: all zeros; then [BM] x (a, b, c, d)
     float* xcoef = gcoef + 4 * BM;                               // [BCI] x (a, b, 0, d)
     float* redw = xcoef + 4 * BCI;                               // [NTAPS][BM][BCI] when KWs > 1
     const int gper = p.Cout * SW_GQ, xper = p.Cin * SW_XQ;
@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(SW_NT, MINB) slide_wgrad_kernel(const WgradP p
     constexpr int TG = NTAPS < 3 ? NTAPS : 3;                    // taps whose MMAs are interleaved
 
     // zero everything once: padding rows / columns stay zero
-    for (int idx = tid; idx < 2 * PS * gslab + R * xslab + 4 * BM + 4 * BCI + (KWs > 1 ? NTAPS * BM * BCI : 0); idx += SW_NT) smem[idx] = 0.f;
+    for (int idx = tid; idx < 2 * PS * gslab + (R + 1) * xslab + 4 * BM + 4 * BCI + (KWs > 1 ? NTAPS * BM * BCI : 0); idx += SW_NT) smem[idx] = 0.f;
     __syncthreads();
     if (p.g_pro == PRO_BNBWD)
         for (int c = tid; c < p.Cout; c += SW_NT) st4(gcoef + 4 * c, make_float4(p.g_a[c], p.g_b[c], p.g_c[c], p.g_d[c]));
@@ -786,58 +786,68 @@ __global__ void __launch_bounds__(SW_NT, MINB) slide_wgrad_kernel(const WgradP p
                 if (ncnt) load_x(na, ncnt);
             }
 
-            for (int opos = op; opos < oe; ++opos) {
-                const float* gs = Gs + (cur * PS + (opos - op)) * gslab + (wm * MTW * 16 + fr) * SW_GS + fc;
-                for (int ks = wk; ks < SW_BN / 8; ks += KWs) {
-                    const int kc = ks * 8;
-                    uint32_t ah[MTW][4], al[MTW][4];
+            // K work of this step = (position, k8 step) units, dealt to the KWs k-slices in contiguous runs so that the per-position
+            // tap setup is shared by as many k8 steps as possible; taps that leave the tensor read the all-zero slab instead of
+            // being skipped, which keeps the MMA sequence free of divergence bookkeeping
+            const int nunits = (oe - op) * (SW_BN / 8);
+            const int upw = (nunits + KWs - 1) / KWs;
+            int cur_pos = -1;
+            int xb[NTAPS];
+            const float* gs = nullptr;
+            for (int unit = wk * upw; unit < min((wk + 1) * upw, nunits); ++unit) {
+                const int pi = unit >> 3, kc = (unit & 7) * 8;
+                if (pi != cur_pos) {
+                    cur_pos = pi;
+                    const int opos = op + pi;
+                    gs = Gs + (cur * PS + pi) * gslab + (wm * MTW * 16 + fr) * SW_GS + fc;
 #pragma unroll
-                    for (int mi = 0; mi < MTW; ++mi) {
-                        const float* g0 = gs + mi * 16 * SW_GS + kc;
-                        split_tf32(g0[0], ah[mi][0], al[mi][0]);
-                        split_tf32(g0[8 * SW_GS], ah[mi][1], al[mi][1]);
-                        split_tf32(g0[4], ah[mi][2], al[mi][2]);
-                        split_tf32(g0[8 * SW_GS + 4], ah[mi][3], al[mi][3]);
+                    for (int tap = 0; tap < NTAPS; ++tap) {
+                        const int ipos = opos * p.pmul + p.dp[tap];
+                        const int slot = (ipos >= 0 && ipos < p.Pin) ? ring_slot(ipos, base_ipos, base_slot, R) : R;      // slot R: zeros
+                        xb[tap] = slot * xslab + (wn * NTW * 8 + fr) * SW_XS + SL_H + fc + (HASDN ? p.dn[tap] : 0);
                     }
-                    int t0 = 0, t1 = 0;
-                    if (HASDN) { t0 = (tb + kc) % WF_T; t1 = t0 + 4 >= WF_T ? t0 + 4 - WF_T : t0 + 4; }
+                }
+                uint32_t ah[MTW][4], al[MTW][4];
 #pragma unroll
-                    for (int tg = 0; tg < NTAPS; tg += TG) {
-                        uint32_t bh[TG][NTW][2], bl[TG][NTW][2];
-                        bool tv[TG];
+                for (int mi = 0; mi < MTW; ++mi) {
+                    const float* g0 = gs + mi * 16 * SW_GS + kc;
+                    split_tf32(g0[0], ah[mi][0], al[mi][0]);
+                    split_tf32(g0[8 * SW_GS], ah[mi][1], al[mi][1]);
+                    split_tf32(g0[4], ah[mi][2], al[mi][2]);
+                    split_tf32(g0[8 * SW_GS + 4], ah[mi][3], al[mi][3]);
+                }
+                int t0 = 0, t1 = 0;
+                if (HASDN) { t0 = (tb + kc) % WF_T; t1 = t0 + 4 >= WF_T ? t0 + 4 - WF_T : t0 + 4; }
 #pragma unroll
-                        for (int tt = 0; tt < TG; ++tt) {
-                            const int tap = tg + tt;
-                            const int ipos = opos * p.pmul + p.dp[tap];
-                            tv[tt] = ipos >= 0 && ipos < p.Pin;
-                            if (!tv[tt]) continue;
-                            const int dn = HASDN ? p.dn[tap] : 0;
-                            // the window rule of a time tap zeroes columns whose source leaves the 20-step window
-                            const bool v0 = !HASDN || ((t0 + dn >= 0) && (t0 + dn < WF_T)), v1 = !HASDN || ((t1 + dn >= 0) && (t1 + dn < WF_T));
-                            const float* xs = ring + ring_slot(ipos, base_ipos, base_slot, R) * xslab + (wn * NTW * 8 + fr) * SW_XS + SL_H + kc + fc + dn;
+                for (int tg = 0; tg < NTAPS; tg += TG) {
+                    uint32_t bh[TG][NTW][2], bl[TG][NTW][2];
 #pragma unroll
-                            for (int ni = 0; ni < NTW; ++ni) {
-                                float x0 = xs[ni * 8 * SW_XS], x1 = xs[ni * 8 * SW_XS + 4];
-                                if (HASDN) { x0 = v0 ? x0 : 0.f; x1 = v1 ? x1 : 0.f; }
-                                split_tf32(x0, bh[tt][ni][0], bl[tt][ni][0]);
-                                split_tf32(x1, bh[tt][ni][1], bl[tt][ni][1]);
-                            }
+                    for (int tt = 0; tt < TG; ++tt) {
+                        const int tap = tg + tt;
+                        const int dn = HASDN ? p.dn[tap] : 0;
+                        // the window rule of a time tap zeroes columns whose source leaves the 20-step window
+                        const bool v0 = !HASDN || ((t0 + dn >= 0) && (t0 + dn < WF_T)), v1 = !HASDN || ((t1 + dn >= 0) && (t1 + dn < WF_T));
+                        const float* xs = ring + xb[tap] + kc;
+#pragma unroll
+                        for (int ni = 0; ni < NTW; ++ni) {
+                            float x0 = xs[ni * 8 * SW_XS], x1 = xs[ni * 8 * SW_XS + 4];
+                            if (HASDN) { x0 = v0 ? x0 : 0.f; x1 = v1 ? x1 : 0.f; }
+                            split_tf32(x0, bh[tt][ni][0], bl[tt][ni][0]);
+                            split_tf32(x1, bh[tt][ni][1], bl[tt][ni][1]);
                         }
-#pragma unroll
-                        for (int pass = 0; pass < 3; ++pass)
-#pragma unroll
-                            for (int tt = 0; tt < TG; ++tt) {
-                                if (!tv[tt]) continue;
-#pragma unroll
-                                for (int mi = 0; mi < MTW; ++mi)
-#pragma unroll
-                                    for (int ni = 0; ni < NTW; ++ni) {
-                                        if (pass == 0) mma_tf32(acc[tg + tt][mi][ni], al[mi], bh[tt][ni]);
-                                        else if (pass == 1) mma_tf32(acc[tg + tt][mi][ni], ah[mi], bl[tt][ni]);
-                                        else mma_tf32(acc[tg + tt][mi][ni], ah[mi], bh[tt][ni]);
-                                    }
-                            }
                     }
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass)
+#pragma unroll
+                        for (int tt = 0; tt < TG; ++tt)
+#pragma unroll
+                            for (int mi = 0; mi < MTW; ++mi)
+#pragma unroll
+                                for (int ni = 0; ni < NTW; ++ni) {
+                                    if (pass == 0) mma_tf32(acc[tg + tt][mi][ni], al[mi], bh[tt][ni]);
+                                    else if (pass == 1) mma_tf32(acc[tg + tt][mi][ni], ah[mi], bl[tt][ni]);
+                                    else mma_tf32(acc[tg + tt][mi][ni], ah[mi], bh[tt][ni]);
+                                }
                 }
             }
 
@@ -1116,11 +1126,11 @@ cudaError_t launch_slide_wgrad(const WgradP& p, const WgCfg& c, int num_sms, cud
         int ring, newmax;
         window_geometry(p.pmul, 1, p.Pin, p.Pout, g.dpmin, g.dpmax, ps, span, ring, newmax);
         if (newmax > g.cap || ps > gcap) continue;
-        const size_t need = fixed + 2 * ps * gsl + ring * xsl;
+        const size_t need = fixed + 2 * ps * gsl + (ring + 1) * xsl;
         if (need <= (size_t)SMEM_MAX - 1024 && (ps == 1 || need <= 64 * 1024)) { g.PS = ps; g.R = ring; }
     }
     if (!g.PS) return cudaErrorInvalidConfiguration;
-    const size_t smem = fixed + 2 * g.PS * gsl + g.R * xsl;
+    const size_t smem = fixed + 2 * g.PS * gsl + (g.R + 1) * xsl;
     if (dry) return cudaSuccess;
     static size_t cfg = 0;
     if (smem > cfg) {

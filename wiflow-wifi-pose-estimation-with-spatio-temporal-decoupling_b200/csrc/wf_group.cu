@@ -44,49 +44,80 @@ __global__ void __launch_bounds__(G_NT, 2) group_conv_kernel(const ConvP p)
     const int n0 = blockIdx.x * G_BN;
     const int K8 = (p.Cin + 7) / 8 * 8;                       // channels rounded up to the mma K step (rows >= Cin are zero)
 
-    // ---- stage the weights of this group: [tap][k][m] ----
-    for (int idx = tid; idx < 3 * K8 * (BM / 4); idx += G_NT) {
-        const int mq = idx % (BM / 4), k = (idx / (BM / 4)) % K8, tap = idx / ((BM / 4) * K8);
-        float4 v = f4zero();
-        if (k < p.Kpad && tap < p.ntaps) v = ld4(p.w + ((size_t)(g * p.ntaps + tap) * p.Kpad + k) * p.Mpad + mq * 4);
-        float4 h, l;
-        split4(v, h, l);
-        st4(Ws + (tap * G_KMAX + k) * WS + mq * 4, h);
-        st4(Ws + (3 * G_KMAX + tap * G_KMAX + k) * WS + mq * 4, l);
-    }
-    // ---- stage the activation tile once, prologue applied ----
-    for (int idx = tid; idx < K8 * (G_XW / 4); idx += G_NT) {
-        const int j = idx % (G_XW / 4), k = idx / (G_XW / 4);
-        const int nn = n0 - G_HALO + 4 * j;
-        float4 v = f4zero();
-        if (k < p.Cin && nn >= 0 && nn < p.N) {
-            const int b = nn / WF_T, t = nn - b * WF_T;
-            const int c = g * p.Cin + k;
-            const long long off = (long long)c * p.in_sc + (long long)b * p.in_sb + t;
-            v = ld4(p.in + off);
-            if (p.pro_mode == PRO_BNSILU) {
-                const float a = p.pro_a[c], bb = p.pro_b[c], mu = p.pro_d[c];
-                v.x = wf_silu(fmaf(a, v.x - mu, bb)); v.y = wf_silu(fmaf(a, v.y - mu, bb));
-                v.z = wf_silu(fmaf(a, v.z - mu, bb)); v.w = wf_silu(fmaf(a, v.w - mu, bb));
-                if (p.mask) {
+    // ---- stage the weights of this group: [tap][k][m]; all loads of a thread are in flight before the first is used ----
+    {
+        constexpr int WU = (3 * G_KMAX * (BM / 4) + G_NT - 1) / G_NT;
+        float4 wv[WU];
+#pragma unroll
+        for (int u = 0; u < WU; ++u) {
+            const int idx = tid + u * G_NT;
+            const int mq = idx % (BM / 4), k = (idx / (BM / 4)) % K8, tap = idx / ((BM / 4) * K8);
+            wv[u] = f4zero();
+            if (idx < 3 * K8 * (BM / 4) && k < p.Kpad && tap < p.ntaps) wv[u] = ld4(p.w + ((size_t)(g * p.ntaps + tap) * p.Kpad + k) * p.Mpad + mq * 4);
+        }
+        // ---- stage the activation tile once, prologue applied.  The tile is K8 x 72 quads = at most 9 per thread: the value
+        //      (and mask / second-tensor) loads of all of them are issued back to back, then transformed (the kernel used to pay
+        //      one DRAM round trip per quad, profiles/r1_group_conv_staging.txt) ----
+        constexpr int XU = (G_KMAX * (G_XW / 4) + G_NT - 1) / G_NT;
+        float4 xv[XU], xw[XU];
+        int xc[XU];
+#pragma unroll
+        for (int u = 0; u < XU; ++u) {
+            const int idx = tid + u * G_NT;
+            const int j = idx % (G_XW / 4), k = idx / (G_XW / 4);
+            const int nn = n0 - G_HALO + 4 * j;
+            xv[u] = f4zero(); xw[u] = make_float4(1.f, 1.f, 1.f, 1.f); xc[u] = -1;
+            if (idx < K8 * (G_XW / 4) && k < p.Cin && nn >= 0 && nn < p.N) {
+                const int b = nn / WF_T, t = nn - b * WF_T;
+                const int c = g * p.Cin + k;
+                const long long off = (long long)c * p.in_sc + (long long)b * p.in_sb + t;
+                xc[u] = c;
+                xv[u] = ld4(p.in + off);
+                if (p.pro_mode == PRO_BNBWD) xw[u] = ld4(p.in2 + off);
+                else if (p.pro_mode == PRO_BNSILU && p.mask) {
                     const float* mp = p.mask + (long long)b * p.m_sb + (long long)c * p.m_sc + (long long)t * p.m_st;
-                    if (p.m_st == 1) { const float4 m = ld4(mp); v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w; }
-                    else { const float m = *mp; v.x *= m; v.y *= m; v.z *= m; v.w *= m; }
+                    if (p.m_st == 1) xw[u] = ld4(mp); else { const float m = *mp; xw[u] = make_float4(m, m, m, m); }
                 }
-            } else if (p.pro_mode == PRO_AFFINE) {
-                const float a = p.pro_a[c], bb = p.pro_b[c], mu = p.pro_d[c];
-                v.x = fmaf(a, v.x - mu, bb); v.y = fmaf(a, v.y - mu, bb); v.z = fmaf(a, v.z - mu, bb); v.w = fmaf(a, v.w - mu, bb);
-            } else if (p.pro_mode == PRO_BNBWD) {
-                const float4 r = ld4(p.in2 + off);
-                const float a = p.pro_a[c], bb = p.pro_b[c], cc = p.pro_c[c], mu = p.pro_d[c];
-                v.x = fmaf(a, v.x, fmaf(bb, r.x - mu, cc)); v.y = fmaf(a, v.y, fmaf(bb, r.y - mu, cc));
-                v.z = fmaf(a, v.z, fmaf(bb, r.z - mu, cc)); v.w = fmaf(a, v.w, fmaf(bb, r.w - mu, cc));
             }
         }
-        float4 h, l;
-        split4(v, h, l);
-        st4(Xs + k * G_XS + 4 * j, h);
-        st4(Xs + (G_KMAX + k) * G_XS + 4 * j, l);
+#pragma unroll
+        for (int u = 0; u < WU; ++u) {
+            const int idx = tid + u * G_NT;
+            if (idx < 3 * K8 * (BM / 4)) {
+                const int mq = idx % (BM / 4), k = (idx / (BM / 4)) % K8, tap = idx / ((BM / 4) * K8);
+                float4 h, l;
+                split4(wv[u], h, l);
+                st4(Ws + (tap * G_KMAX + k) * WS + mq * 4, h);
+                st4(Ws + (3 * G_KMAX + tap * G_KMAX + k) * WS + mq * 4, l);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < XU; ++u) {
+            const int idx = tid + u * G_NT;
+            if (idx < K8 * (G_XW / 4)) {
+                const int j = idx % (G_XW / 4), k = idx / (G_XW / 4);
+                float4 v = xv[u];
+                if (xc[u] >= 0) {
+                    const int c = xc[u];
+                    if (p.pro_mode == PRO_BNSILU) {
+                        const float a = p.pro_a[c], bb = p.pro_b[c], mu = p.pro_d[c];
+                        v.x = wf_silu(fmaf(a, v.x - mu, bb)) * xw[u].x; v.y = wf_silu(fmaf(a, v.y - mu, bb)) * xw[u].y;
+                        v.z = wf_silu(fmaf(a, v.z - mu, bb)) * xw[u].z; v.w = wf_silu(fmaf(a, v.w - mu, bb)) * xw[u].w;
+                    } else if (p.pro_mode == PRO_AFFINE) {
+                        const float a = p.pro_a[c], bb = p.pro_b[c], mu = p.pro_d[c];
+                        v.x = fmaf(a, v.x - mu, bb); v.y = fmaf(a, v.y - mu, bb); v.z = fmaf(a, v.z - mu, bb); v.w = fmaf(a, v.w - mu, bb);
+                    } else if (p.pro_mode == PRO_BNBWD) {
+                        const float a = p.pro_a[c], bb = p.pro_b[c], cc = p.pro_c[c], mu = p.pro_d[c];
+                        v.x = fmaf(a, v.x, fmaf(bb, xw[u].x - mu, cc)); v.y = fmaf(a, v.y, fmaf(bb, xw[u].y - mu, cc));
+                        v.z = fmaf(a, v.z, fmaf(bb, xw[u].z - mu, cc)); v.w = fmaf(a, v.w, fmaf(bb, xw[u].w - mu, cc));
+                    }
+                }
+                float4 h, l;
+                split4(v, h, l);
+                st4(Xs + k * G_XS + 4 * j, h);
+                st4(Xs + (G_KMAX + k) * G_XS + 4 * j, l);
+            }
+        }
     }
     __syncthreads();
 

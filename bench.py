@@ -264,14 +264,17 @@ def run_ours(args, rank, world, local_rank):
         kernels = {'pw_tc_kernel (tcgen05 3xTF32 pointwise conv, fwd + dgrad)': ('tc_fwd', 'tc_dgrad'),
                    'pw_wgrad_tc_kernel (tcgen05 3xTF32 pointwise wgrad)': ('tc_wgrad',),
                    'slide_conv_kernel (sliding-window mma.sync 3xTF32 position-tap conv, fwd + dgrad)': ('slide_fwd', 'slide_dgrad'),
+                   'slide_thin_kernel (sliding-window mma.sync 3xTF32 conv, <= 8 output channels, fwd + dgrad)': ('slidethin_fwd', 'slidethin_dgrad'),
                    'slide_wgrad_kernel (sliding-window mma.sync 3xTF32 wgrad)': ('slide_wgrad',),
                    'conv_gemm_kernel (FP32 implicit-GEMM conv, fwd + dgrad)': ('conv_fwd', 'conv_dgrad'),
                    'conv_wgrad_kernel (FP32 conv wgrad)': ('conv_wgrad',),
                    'thin_conv_kernel (direct conv <=16 channels, fwd + dgrad)': ('thin_fwd', 'thin_dgrad'),
                    'thin_wgrad_kernel': ('thin_wgrad',),
                    'group_conv_kernel (grouped causal conv, mma.sync 3xTF32, fwd + dgrad)': ('group_fwd', 'group_dgrad'),
-                   'group_wgrad_kernel': ('group_wgrad',)}
-        tf32_peak = pk['bf16_tflops'] / 2.0            # dense tf32 = half the measured bf16 tensor peak
+                   'group_wgrad_kernel (grouped causal conv wgrad, mma.sync 3xTF32)': ('group_wgrad',)}
+        tf32_peak = pk['bf16_tflops'] / 2.0            # dense tf32 (tcgen05) = half the measured bf16 tensor peak
+        # warp-level mma.sync tf32: 1024 flop/clk/SM (ncu sm__ops_path_tensor_op_hmma_src_tf32 peak_sustained, profiles/README.md)
+        mma_peak = 148 * 1024 * pk['sm_max_mhz'] * 1e6 / 1e12
         traffic = {}
         try:
             with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
@@ -286,15 +289,18 @@ def run_ours(args, rank, world, local_rank):
             if not k_n:
                 continue
             ach = k_fl / (k_ms * 1e-3) / 1e12
-            tensor = 'tcgen05' in kname
-            r = {'kernel': kname, 'bound': 'tensor' if tensor else 'fp32_fma', 'unit': 'TFLOP/s', 'launches_per_step': k_n,
+            tcgen = 'tcgen05' in kname
+            mma = 'mma.sync' in kname
+            r = {'kernel': kname, 'bound': 'tensor' if (tcgen or mma) else 'fp32_fma', 'unit': 'TFLOP/s', 'launches_per_step': k_n,
                  'avg_launch_ms': k_ms / k_n, 'share_of_step': k_ms / total_ms, 'algorithmic_flops_per_launch_avg': k_fl / k_n,
                  'traffic': traffic.get(kname.split(' ')[0])}
-            if tensor:      # the tensor pipe executes 3 tf32 MMAs per algorithmic fp32 MAC (3xTF32 split)
-                r.update(achieved=3 * ach, peak=tf32_peak, frac=3 * ach / tf32_peak, fp32_equivalent_tflops=ach,
+            if tcgen or mma:      # the tensor pipe executes 3 tf32 MMAs per algorithmic fp32 multiply-add (3xTF32 split)
+                peak = tf32_peak if tcgen else mma_peak
+                src = (f"tcgen05 tf32 peak = measured bf16 {pk['bf16_tflops']} TFLOP/s / 2 ({pk['source']})" if tcgen else
+                       f"mma.sync tf32 peak = 148 SM x 1024 flop/clk (ncu hmma tf32 peak_sustained) x {pk['sm_max_mhz']:.0f} MHz")
+                r.update(achieved=3 * ach, peak=peak, frac=3 * ach / peak, fp32_equivalent_tflops=ach,
                          frac_of_fp32_fma_peak=ach / pk['fp32_tflops'],
-                         peak_source=f"tf32 tensor peak = measured bf16 {pk['bf16_tflops']} TFLOP/s / 2 ({pk['source']}); achieved counts the 3 "
-                                     'tf32 MMAs issued per fp32 multiply-add')
+                         peak_source=src + '; achieved counts the 3 tf32 MMAs issued per fp32 multiply-add')
             else:
                 r.update(achieved=ach, peak=pk['fp32_tflops'], frac=ach / pk['fp32_tflops'],
                          peak_source=f"148 SM x 128 FP32 lanes x 2 x {pk['sm_max_mhz']:.0f} MHz ({pk['source']} sm_max_mhz)")

@@ -15,7 +15,7 @@ namespace {
 enum { ATT_FWD_STATS = 0, ATT_FWD = 1, ATT_BWD_STATS = 2, ATT_BWD = 3 };
 
 template <int L, int LP, int RT, bool WIDTH, int MODE>
-__global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * L <= 320 ? 3 : 2) : 0) attn_kernel(const AttnP p)
+__global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * L <= 320 ? 3 : 2) : (MODE == ATT_BWD ? 1 : 0)) attn_kernel(const AttnP p)
 {
     constexpr int NT = RT * 8 * L;
     constexpr int CS = RT * LP;                         // channel stride inside a tile
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * 
         for (int j = 0; j < L; ++j) { pr[j] = fmaf(ss, lg[j] - ms, ts); mx = fmaxf(mx, pr[j]); }
         float sum = 0.f;
 #pragma unroll
-        for (int j = 0; j < L; ++j) { pr[j] = expf(pr[j] - mx); sum += pr[j]; }
+        for (int j = 0; j < L; ++j) { pr[j] = __expf(pr[j] - mx); sum += pr[j]; }        // ex2.approx: relative error ~2^-21
         const float inv = 1.f / sum;
 #pragma unroll
         for (int j = 0; j < L; ++j) pr[j] *= inv;

@@ -78,6 +78,7 @@ cudaError_t wf_launch_thin_wgrad(const WgradP& p, int num_sms, cudaStream_t st);
 // sliding-window mma.sync path for position-tap convs (wf_slide.cu)
 bool wf_slide_conv_ok(const ConvP& p);
 cudaError_t wf_launch_slide_conv(const ConvP& p, cudaStream_t st);
+bool wf_slide_conv_is_thin(const ConvP& p);
 bool wf_slide_wgrad_ok(const WgradP& p);
 cudaError_t wf_launch_slide_wgrad(const WgradP& p, int num_sms, cudaStream_t st);
 // tcgen05 pointwise-conv path (wf_tc.cu)

@@ -440,7 +440,7 @@ void fwd_conv(Ctx& c, int ui, Act in, Pro pro)
     p.bias = u.b_off >= 0 ? c.params + u.b_off : nullptr;
     p.epi_mode = c.train ? EPI_STATS : EPI_STORE;
     p.stat0 = bo.f0; p.stat1 = bo.f1;
-    Scope sc(c, std::string(u.tc ? "tc_fwd " : wf_slide_conv_ok(p) ? "slide_fwd " : wf_thin_conv_ok(p) ? "thin_fwd " : wf_group_conv_ok(p) ? "group_fwd " : "conv_fwd ") + u.name, conv_flops(u, c.N));
+    Scope sc(c, std::string(u.tc ? "tc_fwd " : wf_slide_conv_ok(p) ? (wf_slide_conv_is_thin(p) ? "slidethin_fwd " : "slide_fwd ") : wf_thin_conv_ok(p) ? "thin_fwd " : wf_group_conv_ok(p) ? "group_fwd " : "conv_fwd ") + u.name, conv_flops(u, c.N));
     if (u.tc) { p.wtc = c.n.tcpacked + u.tc_fpack; p.tc_kt = (u.cin_g + TC_KC - 1) / TC_KC; c.ck(wf_launch_tc_conv(p, c.sms, c.st)); }
     else c.ck(wf_launch_conv(p, c.st));
 }
@@ -509,7 +509,7 @@ void dgrad_conv(Ctx& c, int ui, float* out, int epi, int src_bn, const float* sr
         p.emask = emask.p; p.em_sb = emask.sb; p.em_sc = emask.sc; p.em_st = emask.st;
         p.stat0 = bs.b0; p.stat1 = bs.b1;
     }
-    Scope sc(c, std::string(u.tc ? "tc_dgrad " : wf_slide_conv_ok(p) ? "slide_dgrad " : wf_thin_conv_ok(p) ? "thin_dgrad " : wf_group_conv_ok(p) ? "group_dgrad " : "conv_dgrad ") + u.name, conv_flops(u, c.N));
+    Scope sc(c, std::string(u.tc ? "tc_dgrad " : wf_slide_conv_ok(p) ? (wf_slide_conv_is_thin(p) ? "slidethin_dgrad " : "slide_dgrad ") : wf_thin_conv_ok(p) ? "thin_dgrad " : wf_group_conv_ok(p) ? "group_dgrad " : "conv_dgrad ") + u.name, conv_flops(u, c.N));
     if (u.tc) { p.wtc = c.n.tcpacked + u.tc_bpack; p.tc_kt = (u.cout_g + TC_KC - 1) / TC_KC; c.ck(wf_launch_tc_conv(p, c.sms, c.st)); }
     else c.ck(wf_launch_conv(p, c.st));
 }

@@ -1198,6 +1198,8 @@ bool wf_slide_conv_ok(const ConvP& p)
     return slide_conv_dispatch(p, 148, nullptr, true) == cudaSuccess;
 }
 cudaError_t wf_launch_slide_conv(const ConvP& p, cudaStream_t st) { return slide_conv_dispatch(p, device_sms(), st, false); }
+// true when wf_launch_slide_conv runs slide_thin_kernel for this layer (profiling labels)
+bool wf_slide_conv_is_thin(const ConvP& p) { return g_slide_thin && slide_thin_shape(p); }
 
 bool wf_slide_wgrad_ok(const WgradP& p)
 {

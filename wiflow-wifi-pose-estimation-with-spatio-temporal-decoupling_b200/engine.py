@@ -41,9 +41,11 @@ class TrainStep:
 
     def __init__(self, model: WiFlowPoseModel, batch_size: int, lr=1e-4, weight_decay=5e-5, betas=(0.9, 0.999), eps=1e-8,
                  max_norm=1.0, position_weight=1.0, bone_weight=0.2, loss_type='smooth_l1', process_group=None,
-                 use_cuda_graph=True, dropout=True):
+                 use_cuda_graph=True, dropout=True, accumulation_steps=1, metric_thresholds=None):
         self.model = model
         self.B = int(batch_size)
+        self.k = max(1, int(accumulation_steps))            # micro-batches per optimizer step (train.py:80, :243-249)
+        self.thresholds = tuple(float(t) for t in metric_thresholds) if metric_thresholds else ()
         self.hp = dict(lr=lr, wd=weight_decay, b1=betas[0], b2=betas[1], eps=eps, max_norm=max_norm)
         self.loss = (_lib.LOSS_TYPES[loss_type], float(position_weight), float(bone_weight))
         self.pg = process_group
@@ -70,27 +72,53 @@ class TrainStep:
         self.use_graph = use_cuda_graph
         self._graph_a = self._graph_b = None
         self.kernel_launches = 0
+        self.micro = 0                                       # micro-batches accumulated since the last optimizer step
+        self.acc = torch.zeros(n, device=dev) if self.k > 1 else None
+        # device-side epoch accumulators (train.py:221-230 keeps them on the host with 7 .item() syncs per step):
+        # [total, position, bone, mpjpe, pck(thr_0), ..., windows], each weighted by the batch size
+        self.sums = torch.zeros(5 + len(self.thresholds), device=dev, dtype=torch.float64)
+        self._metric_scratch = torch.zeros(16, device=dev, dtype=torch.float64)
 
     # -- pieces -----------------------------------------------------------------------------------------
-    def _fwd_bwd(self):
+    def _fwd_bwd_on(self, x, y):
+        """forward + PoseLoss + backward of one micro-batch (any B <= self.B: the workspace was sized for self.B)"""
         m = self.model
-        masks = m._wf_masks(self.B, self.dev) if self.dropout else []
-        self.pred = ops.block_forward(self.x, self.params, self.running, self.nbt, masks, MODEL_DESC, self.flags, self.ws)
-        out3, dpred = ops.pose_loss(self.pred, self.y, self.loss[0], self.loss[1], self.loss[2], self.loss_scratch, True)
+        B = x.shape[0]
+        masks = m._wf_masks(B, self.dev) if self.dropout else []
+        self.pred = ops.block_forward(x, self.params, self.running, self.nbt, masks, MODEL_DESC, self.flags, self.ws)
+        out3, dpred = ops.pose_loss(self.pred, y, self.loss[0], self.loss[1], self.loss[2], self.loss_scratch, True)
         self.out[:3].copy_(out3)
-        grads, _ = ops.block_backward(self.x, self.params, masks, dpred, MODEL_DESC, self.flags, self.ws, False)
-        self.grads.copy_(grads) if grads.data_ptr() != self.grads.data_ptr() else None
+        grads, _ = ops.block_backward(x, self.params, masks, dpred, MODEL_DESC, self.flags, self.ws, False)
+        if self.acc is not None:
+            self.acc.add_(grads)
+        else:
+            self.grads.copy_(grads)
+        # epoch statistics stay on the device
+        self.sums[:3].add_(out3.double(), alpha=float(B))
+        if self.thresholds:
+            mt = ops.pose_metrics(self.pred.detach(), y, list(self.thresholds), True, self._metric_scratch)
+            self.sums[3:4].add_(mt[-1:].double(), alpha=float(B))
+            self.sums[4:4 + len(self.thresholds)].add_(mt[:-1].double(), alpha=float(B))
+        self.sums[-1:].add_(float(B))
+
+    def _fwd_bwd(self):
+        self._fwd_bwd_on(self.x, self.y)
 
     def _optim(self):
         h = self.hp
-        ops.clip_adamw(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.adam_state, h['lr'], h['b1'], h['b2'],
-                       h['eps'], h['wd'], h['max_norm'], 1.0 / self.world)
+        g = self.acc if self.acc is not None else self.grads
+        # the reference divides every micro-batch loss by k (train.py:200), also in an incomplete last group
+        ops.clip_adamw(self.params, g, self.exp_avg, self.exp_avg_sq, self.adam_state, h['lr'], h['b1'], h['b2'],
+                       h['eps'], h['wd'], h['max_norm'], 1.0 / (self.world * self.k))
         self.out[3:4].copy_(self.adam_state.view(torch.float32)[4:5])
+        if self.acc is not None:
+            self.acc.zero_()
 
     def _allreduce(self):
-        allreduce_gradients(self.grads, self.pg, self.world)
+        allreduce_gradients(self.acc if self.acc is not None else self.grads, self.pg, self.world)
 
     def _capture(self):
+        saved_sums = self.sums.clone()
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(s):
@@ -101,27 +129,73 @@ class TrainStep:
         self._graph_a = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph_a):
             self._fwd_bwd()
+        if self.acc is not None:
+            self.acc.zero_()
+        self.sums.copy_(saved_sums)
+
+    def _capture_optim(self):
         self._graph_b = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph_b):
             self._optim()
 
-    # -- public -----------------------------------------------------------------------------------------
-    def step(self, x, y):
-        self.x.copy_(x, non_blocking=True)
-        self.y.copy_(y, non_blocking=True)
+    def set_lr(self, lr: float):
+        """new learning rate for the following optimizer steps (ReduceLROnPlateau lives on the host); the optimizer graph is
+        re-captured lazily because lr is a kernel argument"""
+        if float(lr) != self.hp['lr']:
+            self.hp['lr'] = float(lr)
+            self._graph_b = None
+
+    def reset_sums(self):
+        self.sums.zero_()
+
+    def read_sums(self):
+        """one device->host copy: dict of epoch means (total, position, bone, mpjpe, pck@thr..., windows)"""
+        v = self.sums.tolist()
+        n = v[-1]
+        names = ['loss', 'position', 'bone', 'mpjpe'] + [f'pck@{t:g}' for t in self.thresholds]
+        out = {k: (x / n if n > 0 else float('inf')) for k, x in zip(names, v[:-1])}
+        out['windows'] = int(n)
+        return out
+
+    def _apply(self):
+        """all-reduce + clip + AdamW on what has been accumulated"""
+        self._allreduce()
         if self.use_graph:
-            if self._graph_a is None:
-                # the warm-up iterations inside _capture must not disturb the weights: they only run fwd/bwd
-                saved = (self.running.clone(), self.nbt.clone())
-                self._capture()
-                self.running.copy_(saved[0]); self.nbt.copy_(saved[1])
-            self._graph_a.replay()
-            self._allreduce()
+            if self._graph_b is None:
+                self._capture_optim()          # capture runs nothing: replay below does the step
             self._graph_b.replay()
         else:
-            self._fwd_bwd()
-            self._allreduce()
             self._optim()
+        self.micro = 0
+
+    def flush(self):
+        """optimizer step on an incomplete accumulation group (train.py:251-257)"""
+        if self.micro > 0:
+            self._apply()
+
+    # -- public -----------------------------------------------------------------------------------------
+    def step(self, x, y):
+        """one micro-batch; every `accumulation_steps`-th call also runs the exchange + optimizer step"""
+        B = x.shape[0]
+        if B != self.B:                       # ragged last batch of an epoch: same kernels, eager launches
+            if B > self.B:
+                raise RuntimeError(f'batch of {B} windows exceeds the workspace sized for {self.B}')
+            self._fwd_bwd_on(x.to(self.dev, non_blocking=True).contiguous(), y.to(self.dev, non_blocking=True).contiguous())
+        else:
+            self.x.copy_(x, non_blocking=True)
+            self.y.copy_(y, non_blocking=True)
+            if self.use_graph:
+                if self._graph_a is None:
+                    # the warm-up iterations inside _capture must not disturb the weights: they only run fwd/bwd
+                    saved = (self.running.clone(), self.nbt.clone())
+                    self._capture()
+                    self.running.copy_(saved[0]); self.nbt.copy_(saved[1])
+                self._graph_a.replay()
+            else:
+                self._fwd_bwd()
+        self.micro += 1
+        if self.micro >= self.k:
+            self._apply()
         return self.out
 
 

@@ -900,6 +900,7 @@ const bool g_use_slide = [] { const char* e = std::getenv("WF_DISABLE_SLIDE"); r
 const int g_slide_min_ch = [] { const char* e = std::getenv("WF_SLIDE_MIN_CH"); return e ? std::atoi(e) : 16; }();
 // WF_DISABLE_SLIDE_THIN=1: <= 8-channel forward / backward-data layers stay on wf_thin.cu (A/B measurements)
 const bool g_slide_thin = [] { const char* e = std::getenv("WF_DISABLE_SLIDE_THIN"); return !(e && e[0] == '1'); }();
+const int g_slide_min_cin_wgrad = [] { const char* e = std::getenv("WF_SLIDE_MIN_CIN_WGRAD"); return e ? std::atoi(e) : 8; }();   // 1-channel layers: wf_thin.cu is faster (measured)
 const int g_slide_min_ch_wgrad = [] { const char* e = std::getenv("WF_SLIDE_MIN_CH_WGRAD"); return e ? std::atoi(e) : 8; }();
 constexpr int SMEM_MAX = 227 * 1024;
 constexpr int PS_MAX = 4;
@@ -1203,7 +1204,7 @@ bool wf_slide_conv_is_thin(const ConvP& p) { return g_slide_thin && slide_thin_s
 
 bool wf_slide_wgrad_ok(const WgradP& p)
 {
-    if (!g_use_slide || p.groups != 1 || p.Cout > 64 || p.Cin > 64 || p.Cin < 8) return false;
+    if (!g_use_slide || p.groups != 1 || p.Cout > 64 || p.Cin > 64 || p.Cin < g_slide_min_cin_wgrad) return false;
     if (p.Cin < g_slide_min_ch_wgrad && p.Cout < g_slide_min_ch_wgrad) return false;
     if (p.Pin == 1 && p.Pout == 1) return false;
     if (p.mask && p.m_st != 0) return false;

@@ -162,3 +162,18 @@ def test_state_dict_round_trip_with_reference_keys():
     a.eval(); b.eval()
     with torch.no_grad():
         assert torch.equal(a(x), b(x))
+
+
+def test_empty_batch_follows_the_reference():
+    """reference semantics on B = 0: eval returns an empty [0,15,2] tensor, train-mode BatchNorm raises ValueError"""
+    import wiflow_b200 as wf
+    m = wf.WiFlowPoseModel().cuda()
+    x = torch.zeros(0, 540, 20, device='cuda')
+    m.eval()
+    y = m(x)
+    assert tuple(y.shape) == (0, 15, 2) and y.is_cuda
+    m.train()
+    with pytest.raises(ValueError):
+        m(x)
+    blk = wf.AsymmetricConvBlock(8, 16).cuda().eval()
+    assert tuple(blk(torch.zeros(0, 8, 20, 240, device='cuda')).shape) == (0, 16, 20, 120)

@@ -122,4 +122,9 @@ class WFBlock(nn.Module):
         exp = tuple(self._wf_input_shape())
         if tuple(x.shape[1:]) != exp:
             raise RuntimeError(f'{type(self).__name__}: expected input [B, {", ".join(map(str, exp))}], got {list(x.shape)}')
+        if x.shape[0] == 0:
+            # the reference's modules on an empty batch: eval mode returns an empty tensor, train-mode BatchNorm refuses
+            if self.training:
+                raise ValueError('Expected more than 1 value per channel when training, got an empty batch')
+            return x.new_empty(ops.out_shape(list(self._wf_desc_key()), 0))
         return _BlockFunction.apply(self, x, *self.parameters())

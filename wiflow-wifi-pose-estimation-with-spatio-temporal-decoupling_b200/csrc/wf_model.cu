@@ -26,7 +26,8 @@ constexpr int T = WF_T;
 struct ProfRec { std::string name; cudaEvent_t a, b; double flops; };
 thread_local std::vector<ProfRec> g_prof;
 std::atomic<long long> g_launches{0};
-constexpr int EVAL_CHUNK = 1024;
+// windows per pass of an eval-mode forward (bounds the workspace); WF_EVAL_CHUNK overrides it for measurements
+const int EVAL_CHUNK = [] { const char* e = std::getenv("WF_EVAL_CHUNK"); const int v = e ? std::atoi(e) : 0; return v >= 64 ? v : 4096; }();
 // WF_DISABLE_TC=1 routes the pointwise convs through the CUDA-core GEMM instead of tcgen05 (A/B measurements only)
 // WF_SERIAL_WGRAD=1 keeps the weight-gradient kernels on the caller's stream (A/B measurements only)
 const bool g_overlap_wgrad = [] { const char* e = std::getenv("WF_SERIAL_WGRAD"); return !(e && e[0] == '1'); }();

@@ -413,10 +413,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const WgradP p
                 tmem_ld_wait();
                 if (co < p.Cout) {
                     float* drow = p.dw + (size_t)co * p.Cin;
+                    // 128-bit reductions (sm_90+ float4 atomicAdd) where the row pitch allows it: a thread owns 32 consecutive
+                    // input channels of one output channel, i.e. 8 aligned quads instead of 32 scalar reductions
+                    if ((p.Cin & 3) == 0) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int ci = c0 + cb0 + j;
-                        if (cb0 + j < bn && ci < p.Cin) atomicAdd(drow + ci, acc[j] + cor[j]);
+                        for (int j = 0; j < 32; j += 4) {
+                            const int ci = c0 + cb0 + j;
+                            if (cb0 + j < bn && ci < p.Cin)
+                                atomicAdd(reinterpret_cast<float4*>(drow + ci),
+                                          make_float4(acc[j] + cor[j], acc[j + 1] + cor[j + 1], acc[j + 2] + cor[j + 2], acc[j + 3] + cor[j + 3]));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int ci = c0 + cb0 + j;
+                            if (cb0 + j < bn && ci < p.Cin) atomicAdd(drow + ci, acc[j] + cor[j]);
+                        }
                     }
                 }
             }

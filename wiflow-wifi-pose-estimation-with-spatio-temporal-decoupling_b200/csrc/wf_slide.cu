@@ -640,13 +640,12 @@ __global__ void __launch_bounds__(SW_NT, MINB) slide_wgrad_kernel(const WgradP p
     float* ring = Gs + 2 * PS * gslab;                           // R x [BCI][SW_XS]
     float* gcoef = ring + (R + 1) * xslab;                       // slab R of the ring is never written: all zeros; then [BM] x (a, b, c, d)
     float* xcoef = gcoef + 4 * BM;                               // [BCI] x (a, b, 0, d)
-    float* redw = xcoef + 4 * BCI;                               // [NTAPS][BM][BCI] when KWs > 1
     const int gper = p.Cout * SW_GQ, xper = p.Cin * SW_XQ;
     constexpr bool HASDN = NTAPS == 9;
     constexpr int TG = NTAPS < 3 ? NTAPS : 3;                    // taps whose MMAs are interleaved
 
     // zero everything once: padding rows / columns stay zero
-    for (int idx = tid; idx < 2 * PS * gslab + (R + 1) * xslab + 4 * BM + 4 * BCI + (KWs > 1 ? NTAPS * BM * BCI : 0); idx += SW_NT) smem[idx] = 0.f;
+    for (int idx = tid; idx < 2 * PS * gslab + (R + 1) * xslab + 4 * BM + 4 * BCI; idx += SW_NT) smem[idx] = 0.f;
     __syncthreads();
     if (p.g_pro == PRO_BNBWD)
         for (int c = tid; c < p.Cout; c += SW_NT) st4(gcoef + 4 * c, make_float4(p.g_a[c], p.g_b[c], p.g_c[c], p.g_d[c]));
@@ -860,37 +859,32 @@ __global__ void __launch_bounds__(SW_NT, MINB) slide_wgrad_kernel(const WgradP p
         }
     }
 
-    // ---- leave: one fp32 atomic per weight per CTA ----
-    if (KWs > 1) {
+    // ---- leave: the CTA's sums are assembled in shared memory as an image of dW ([co][ci][tap], the reference layout) and leave
+    //      as 128-bit reductions, one per four weights per CTA ----
+    __syncthreads();                                             // ring / G' buffers are dead: reuse them
+    const int ntot = p.Cout * p.Cin * p.ntaps;
+    float* img = smem;
+    for (int idx = tid; idx < ntot; idx += SW_NT) img[idx] = 0.f;
+    __syncthreads();
 #pragma unroll
-        for (int tap = 0; tap < NTAPS; ++tap)
+    for (int tap = 0; tap < NTAPS; ++tap)
 #pragma unroll
-            for (int mi = 0; mi < MTW; ++mi)
+        for (int mi = 0; mi < MTW; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < NTW; ++ni)
+            for (int ni = 0; ni < NTW; ++ni)
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int co = (wm * MTW + mi) * 16 + fr + (e >= 2 ? 8 : 0), ci = (wn * NTW + ni) * 8 + fc * 2 + (e & 1);
-                        atomicAdd(redw + (tap * BM + co) * BCI + ci, acc[tap][mi][ni][e]);
+                for (int e = 0; e < 4; ++e) {
+                    const int co = (wm * MTW + mi) * 16 + fr + (e >= 2 ? 8 : 0), ci = (wn * NTW + ni) * 8 + fc * 2 + (e & 1);
+                    if (tap < p.ntaps && co < p.Cout && ci < p.Cin) {
+                        float* dst = img + ((size_t)co * p.Cin + ci) * p.ntaps + tap;
+                        if (KWs > 1) atomicAdd(dst, acc[tap][mi][ni][e]); else *dst = acc[tap][mi][ni][e];
                     }
-        __syncthreads();
-        for (int idx = tid; idx < NTAPS * BM * BCI; idx += SW_NT) {
-            const int ci = idx % BCI, co = (idx / BCI) % BM, tap = idx / (BCI * BM);
-            if (tap < p.ntaps && co < p.Cout && ci < p.Cin) atomicAdd(p.dw + ((size_t)co * p.Cin + ci) * p.ntaps + tap, redw[idx]);
-        }
+                }
+    __syncthreads();
+    if ((ntot & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dw) & 15) == 0) {
+        for (int q = tid; q < ntot / 4; q += SW_NT) atomicAdd(reinterpret_cast<float4*>(p.dw) + q, ld4(img + 4 * q));
     } else {
-#pragma unroll
-        for (int tap = 0; tap < NTAPS; ++tap)
-#pragma unroll
-            for (int mi = 0; mi < MTW; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < NTW; ++ni)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int co = (wm * MTW + mi) * 16 + fr + (e >= 2 ? 8 : 0), ci = (wn * NTW + ni) * 8 + fc * 2 + (e & 1);
-                        if (tap < p.ntaps && co < p.Cout && ci < p.Cin)
-                            atomicAdd(p.dw + ((size_t)co * p.Cin + ci) * p.ntaps + tap, acc[tap][mi][ni][e]);
-                    }
+        for (int idx = tid; idx < ntot; idx += SW_NT) atomicAdd(p.dw + idx, img[idx]);
     }
 }
 
@@ -1119,7 +1113,7 @@ cudaError_t launch_slide_wgrad(const WgradP& p, const WgCfg& c, int num_sms, cud
     if (g.cap > 15) g.cap = 15;
     const int gcap = (LDG * SW_NT) / (p.Cout * SW_GQ);
     if (g.cap < 1 || gcap < 1) return cudaErrorInvalidConfiguration;
-    const size_t fixed = ((size_t)4 * BM + 4 * BCI + (c.kws > 1 ? (size_t)NTAPS * BM * BCI : 0)) * 4;
+    const size_t fixed = ((size_t)4 * BM + 4 * BCI) * 4;
     const size_t gsl = (size_t)BM * SW_GS * 4, xsl = (size_t)BCI * SW_XS * 4;
     int span = 0;
     g.PS = 0;
@@ -1131,7 +1125,10 @@ cudaError_t launch_slide_wgrad(const WgradP& p, const WgCfg& c, int num_sms, cud
         if (need <= (size_t)SMEM_MAX - 1024 && (ps == 1 || need <= 64 * 1024)) { g.PS = ps; g.R = ring; }
     }
     if (!g.PS) return cudaErrorInvalidConfiguration;
-    const size_t smem = fixed + 2 * g.PS * gsl + (g.R + 1) * xsl;
+    size_t smem = fixed + 2 * g.PS * gsl + (g.R + 1) * xsl;
+    const size_t image = (size_t)p.Cout * p.Cin * p.ntaps * 4;          // the dW image assembled at the end reuses the staging buffers
+    if (smem < image) smem = image;
+    if (smem > (size_t)SMEM_MAX - 1024) return cudaErrorInvalidConfiguration;
     if (dry) return cudaSuccess;
     static size_t cfg = 0;
     if (smem > cfg) {

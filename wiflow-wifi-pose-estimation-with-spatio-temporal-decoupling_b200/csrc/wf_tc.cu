@@ -18,6 +18,7 @@
 // TMEM with one thread per output channel: the per-channel sums need no shuffles at all.
 // The kernels are issue bound on the producer warps (profiles/), so the prologue mode is a template parameter and all
 // addressing is strength-reduced out of the K loop.
+#include <cstdlib>
 #include "wf_tc.cuh"
 #include "wf_common.cuh"
 #include "wf_elem.h"
@@ -415,7 +416,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const WgradP p
                     float* drow = p.dw + (size_t)co * p.Cin;
                     // 128-bit reductions (sm_90+ float4 atomicAdd) where the row pitch allows it: a thread owns 32 consecutive
                     // input channels of one output channel, i.e. 8 aligned quads instead of 32 scalar reductions
-                    if ((p.Cin & 3) == 0) {
+                    if ((p.Cin & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dw) & 15) == 0) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const int ci = c0 + cb0 + j;
@@ -578,7 +579,8 @@ cudaError_t wf_launch_tc_wgrad(const WgradP& p, int num_sms, cudaStream_t st)
     if (bn < 16) bn = 16;
     const int mtiles = (p.Cout + BM - 1) / BM;
     const int tiles = mtiles * nt;
-    long long splits = (2LL * num_sms) / tiles;                          // two full rounds of CTAs, never a ragged third
+    static const int rounds = [] { const char* e = std::getenv("WF_TC_WGRAD_ROUNDS"); const int v = e ? std::atoi(e) : 0; return v > 0 ? v : 1; }();       // measured: 1 round 2.16 ms, 2 rounds 2.27 ms, 3 rounds 2.39 ms per step
+    long long splits = ((long long)rounds * num_sms) / tiles;            // full rounds of CTAs, never a ragged extra one
     const long long max_splits = (NC + 8 * KC - 1) / (8 * KC);           // at least 8 stages per CTA
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;

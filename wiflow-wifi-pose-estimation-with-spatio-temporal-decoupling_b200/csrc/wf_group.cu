@@ -426,10 +426,14 @@ __global__ void __launch_bounds__(G_NT, 1) group_wgrad_kernel(const WgradP p, lo
         }
         __syncthreads();
     }
-    for (int idx = tid; idx < 3 * 32 * 32; idx += G_NT) {
-        const int ci = idx & 31, co = (idx >> 5) & 31, tap = idx >> 10;
-        if (tap < p.ntaps && co < p.Cout && ci < p.Cin)
-            atomicAdd(p.dw + ((size_t)(g * p.Cout + co) * p.Cin + ci) * p.ntaps + tap, red[idx]);
+    // the group's weights are one contiguous block of dW ([co][ci][tap]): consecutive threads reduce into consecutive addresses
+    {
+        const int per_co = p.Cin * p.ntaps, total = p.Cout * per_co;
+        float* dwg = p.dw + (size_t)g * total;
+        for (int idx = tid; idx < total; idx += G_NT) {
+            const int co = idx / per_co, rem = idx - co * per_co, ci = rem / p.ntaps, tap = rem - ci * p.ntaps;
+            atomicAdd(dwg + idx, red[(tap * 32 + co) * 32 + ci]);
+        }
     }
 }
 

@@ -94,7 +94,7 @@ def _cases():
 
 
 @pytest.mark.parametrize('idx', range(10))
-@pytest.mark.parametrize('B', [3, 16])
+@pytest.mark.parametrize('B', [3, 7, 16])
 def test_block_train_forward_backward(idx, B):
     name, make, shape, ref_fn = _cases()[idx]
     g = torch.Generator().manual_seed(100 + idx)

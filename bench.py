@@ -339,6 +339,42 @@ def run_ours(args, rank, world, local_rank):
             ms3 = timed_loop(lambda i: inf.step(x3), 5, dev)
             also['C3_infer_b8192'] = {'samples_per_s': 8192 * 5 / (ms3 / 1e3), 'ms_per_step': ms3 / 5,
                                       'frac_of_fp32_roofline': 8192 * 5 / (ms3 / 1e3) * FWD_FLOPS / 1e12 / pk['fp32_tflops']}
+            # input side: resident-window gather and the train.py:187-193 augmentation, HBM-bound
+            from wiflow_b200.utils import augmentation as A
+            from oracle import data_oracle as DO
+            nwin = 8192
+            resident = torch.randn(nwin, 540, 20, device=dev)
+            gidx = [torch.randint(0, nwin, (B,), device=dev) for _ in range(8)]
+            noise = torch.randn(B, 540, 20, device=dev)
+            gout = torch.empty(B, 540, 20, device=dev)
+            stats = torch.zeros(2, device=dev, dtype=torch.float64)
+            spans_h = A.draw_time_masks(B, 540, 0.3)
+            spans_d = A._spans_to_device(spans_h, dev)
+            wbytes = B * 43200
+            inp = {}
+            for name, fn, nbytes in (
+                    ('gather', lambda i: ops.window_load(resident, gidx[i % 8], gout), 2 * wbytes),
+                    ('gather_mask_stats', lambda i: ops.window_load(resident, gidx[i % 8], gout, spans_d, stats), 2 * wbytes),
+                    ('noise_scale', lambda i: ops.noise_scale(gout, noise, 0.02, 1.05, stats, gout), 3 * wbytes)):
+                for i in range(3):
+                    fn(i)
+                msk = timed_loop(fn, 50, dev) / 50
+                inp[name] = {'ms': msk, 'windows_per_s': B / (msk / 1e3), 'algorithmic_bytes': nbytes,
+                             'achieved_gbs': nbytes / (msk / 1e3) / 1e9, 'frac_of_hbm_peak': nbytes / (msk / 1e3) / 1e9 / pk['hbm_gbs']}
+            xc = resident[:64].cpu()
+            nc = noise[:64].cpu()
+            torch.manual_seed(0)
+            t0 = time.perf_counter()
+            reps = 0
+            while time.perf_counter() - t0 < 3.0:
+                DO.augment_step(xc, nc)
+                reps += 1
+            inp['cpu_port_augment_windows_per_s'] = 64 * reps / (time.perf_counter() - t0)
+            inp['note'] = (f'B={B} windows gathered out of a resident array of {nwin} (354 MB > L2); gather_mask_stats = gather + time masking '
+                           '(30 % of the windows) + sum/sumsq for add_noise; noise_scale = add_noise + random_scaling in place; '
+                           'cpu port = oracle augment_step (the reference\'s Python loops) on 64 windows')
+            also['input_side'] = inp
+            del resident, noise, gout
             line['also'] = also
             rate, n, dt, cores = cpu_train_step_rate(64, args.cpu_seconds, 2)
             line['cpu_baseline'] = {'value': rate, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',

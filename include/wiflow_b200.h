@@ -96,6 +96,26 @@ WF_API int wf_clip_adamw(float* params, const float* grads, float* exp_avg, floa
                   float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
                   wf_stream_t stream);
 
+/* ---- input side: dataset.py + utils/augmentation.py ----
+ * wf_window_load: x[b] = windows[idx[b]] (idx NULL: identity; may run in place with x == windows), the gather that
+ *   dataset.py:206 __getitem__ + the DataLoader collate do on the host, fused with utils/augmentation.py:3-19 time_masking
+ *   as train.py:189 applies it: a window is C*T dense floats, t_major != 0 means stored [T][C] (the model's [540][20] input,
+ *   i.e. time_masking called on x.permute(0,2,1)), else [C][T].  spans: NULL or B x {start0,len0,start1,len1} int32 (len 0 =
+ *   unused) drawn by the host; every c-row's mean over T replaces [start,start+len), the second span after the first.
+ *   stats: NULL or 2 doubles (zeroed by the caller) that receive sum(x), sum(x*x) of the OUTPUT, for wf_noise_scale.
+ * wf_noise_scale: utils/augmentation.py:22-35 add_noise + random_scaling, y = (x + (noise*level)*std(x)) * scale with
+ *   std = unbiased standard deviation from `stats` over n_stat elements; noise NULL: scaling only.  In place allowed.
+ * wf_keypoint_batch: dataset.py:80-120 _get_keypoint_npy + _clean_single_frame_zeros: y[b] = frames[idx[b]] ([K][2]),
+ *   zeros when idx[b] is outside [0,n_frames); clean != 0: all-zero joints take the mean of the frame's other joints.
+ * wf_keypoint_sequences: dataset.py:159-206 _clean_zero_keypoints over sequences seq_off[s]..seq_off[s+1] of frames, in place. */
+WF_API int wf_window_load(const float* windows, long long n_windows, const long long* idx, float* x, int B, int C, int T, int t_major,
+                   const int* spans, double* stats, wf_stream_t stream);
+WF_API int wf_noise_scale(const float* x, const float* noise, float* y, long long n, float noise_level, float scale, const double* stats,
+                   long long n_stat, wf_stream_t stream);
+WF_API int wf_keypoint_batch(const float* frames, long long n_frames, const long long* idx, float* y, int B, int K, int clean,
+                      wf_stream_t stream);
+WF_API int wf_keypoint_sequences(float* frames, const long long* seq_off, int n_seq, int K, wf_stream_t stream);
+
 /* ---- measurement hooks (bench.py) ----
  * wf_launch_count: kernels launched by the library since load.  wf_profile_*: per-launch CUDA-event timings of the calls this
  * thread made with WF_FLAG_PROFILE (name = kernel family + layer), read after the work has been enqueued. */

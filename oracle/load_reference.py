@@ -50,3 +50,22 @@ def load():
                 del sys.modules[mk]
             if saved[k] is not None:
                 sys.modules[k] = saved[k]
+
+
+def load_data():
+    """The reference's input side, loaded by file path (no package imports, nothing left in sys.modules): a namespace with
+    time_masking, add_noise, random_scaling (utils/augmentation.py:3-35), PreprocessedCSIKeypointsDataset and
+    create_preprocessed_train_val_test_loaders (dataset.py:16,256)."""
+    if not available():
+        raise RuntimeError(f'reference not found under {REF_ROOT}')
+    import importlib.util
+    out = {}
+    for name, rel in (('ref_augmentation', 'utils/augmentation.py'), ('ref_dataset', 'dataset.py')):
+        spec = importlib.util.spec_from_file_location('_wiflow_' + name, os.path.join(REF_ROOT, rel))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        out[name] = mod
+    a, d = out['ref_augmentation'], out['ref_dataset']
+    return types.SimpleNamespace(time_masking=a.time_masking, add_noise=a.add_noise, random_scaling=a.random_scaling,
+                                 PreprocessedCSIKeypointsDataset=d.PreprocessedCSIKeypointsDataset,
+                                 create_preprocessed_train_val_test_loaders=d.create_preprocessed_train_val_test_loaders)

@@ -6,6 +6,8 @@
     from wiflow_b200.utils import calculate_pck, calculate_mpjpe
     from wiflow_b200.engine import TrainStep, InferStep
     from wiflow_b200.train_loop import Trainer
+    from wiflow_b200.data import PreprocessedCSIKeypointsDataset, create_preprocessed_train_val_test_loaders, DeviceBatchLoader
+    from wiflow_b200.utils import time_masking, add_noise, random_scaling, augment_batch
 
 All arithmetic runs in libwiflow_b200.so (hand-written CUDA, C ABI in include/wiflow_b200.h).  There is no CPU, Triton or
 eager-PyTorch fallback: importing works anywhere, calling needs the built library and a B200."""
@@ -13,6 +15,7 @@ from . import _lib, ops                      # noqa: F401
 from . import losses, models, utils           # noqa: F401
 from .engine import InferStep, TrainStep, allreduce_gradients, shard_bounds      # noqa: F401
 from .train_loop import Trainer              # noqa: F401
+from .data import DeviceBatchLoader, PreprocessedCSIKeypointsDataset, create_preprocessed_train_val_test_loaders      # noqa: F401
 from .losses import PoseLoss                  # noqa: F401
 from .models import (AsymmetricConvBlock, AxialAttention, ConvBlock1, DualAxialAttention, InnerGroupedTemporalBlock,  # noqa: F401
                      TemporalBlock, TemporalConvNet, WiFlow, WiFlowPoseModel)

@@ -58,6 +58,14 @@ def lib():
     L.wf_pose_metrics.argtypes = [vp, vp, ip, ctypes.POINTER(f), ip, ip, vp, vp, vp]
     L.wf_clip_adamw.restype = ip
     L.wf_clip_adamw.argtypes = [vp, vp, vp, vp, ll, vp, f, f, f, f, f, f, f, vp]
+    L.wf_window_load.restype = ip
+    L.wf_window_load.argtypes = [vp, ll, vp, vp, ip, ip, ip, ip, vp, vp, vp]
+    L.wf_noise_scale.restype = ip
+    L.wf_noise_scale.argtypes = [vp, vp, vp, ll, f, f, vp, ll, vp]
+    L.wf_keypoint_batch.restype = ip
+    L.wf_keypoint_batch.argtypes = [vp, ll, vp, vp, ip, ip, ip, vp]
+    L.wf_keypoint_sequences.restype = ip
+    L.wf_keypoint_sequences.argtypes = [vp, vp, ip, ip, vp]
     L.wf_debug_tensor.restype = ip
     L.wf_debug_tensor.argtypes = [dp, ip, ip, ip, ctypes.c_char_p, ip, ctypes.POINTER(ll), ctypes.POINTER(ip), ctypes.POINTER(ip)]
     L.wf_launch_count.restype = ll

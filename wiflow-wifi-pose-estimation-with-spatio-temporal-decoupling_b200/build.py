@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-SOURCES = ['wf_conv.cu', 'wf_group.cu', 'wf_slide.cu', 'wf_tc.cu', 'wf_thin.cu', 'wf_elem.cu', 'wf_attn.cu', 'wf_model.cu']
+SOURCES = ['wf_conv.cu', 'wf_group.cu', 'wf_slide.cu', 'wf_tc.cu', 'wf_thin.cu', 'wf_elem.cu', 'wf_attn.cu', 'wf_data.cu', 'wf_model.cu']
 LIB = os.path.join(HERE, 'libwiflow_b200.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']

@@ -113,3 +113,11 @@ cudaError_t wf_launch_attn_fwd_stats(const AttnP& p, cudaStream_t st);
 cudaError_t wf_launch_attn_fwd(const AttnP& p, cudaStream_t st);
 cudaError_t wf_launch_attn_bwd_stats(const AttnP& p, cudaStream_t st);
 cudaError_t wf_launch_attn_bwd(const AttnP& p, cudaStream_t st);
+// input side (wf_data.cu)
+cudaError_t wf_launch_window_load(const float* src, const long long* idx, long long n_src, float* dst, int B, int C, int T, int sc, int st,
+                                  const int* spans, double* stats, cudaStream_t stream);
+cudaError_t wf_launch_noise_scale(const float* x, const float* noise, float* y, long long n, float level, float scale, const double* stats,
+                                  long long n_stat, int num_sms, cudaStream_t stream);
+cudaError_t wf_launch_keypoint_repair(const float* frames, long long n_frames, const long long* idx, float* out, int B, int K, int clean,
+                                      cudaStream_t stream);
+cudaError_t wf_launch_keypoint_seq(float* frames, const long long* seq_off, int n_seq, int K, cudaStream_t stream);

@@ -1095,4 +1095,51 @@ int wf_clip_adamw(float* params, const float* grads, float* m, float* v, long lo
     return e == cudaSuccess ? 0 : fail((int)e, cudaGetErrorString(e));
 }
 
+int wf_window_load(const float* windows, long long n_windows, const long long* idx, float* x, int B, int C, int T, int t_major,
+                   const int* spans, double* stats, wf_stream_t stream)
+{
+    if (int e = check_device()) return e;
+    if (!windows || !x || B < 0 || C <= 0 || T <= 0 || n_windows <= 0) return fail(WF_E_ARG, "null pointer or bad window geometry");
+    if (((long long)C * T) % 4 != 0 || ((uintptr_t)windows & 15) || ((uintptr_t)x & 15)) return fail(WF_E_ARG, "windows must be 16-byte aligned with C*T a multiple of 4");
+    if (spans && (size_t)C * T * sizeof(float) > 200 * 1024) return fail(WF_E_UNSUPPORTED, "window larger than 200 KB of shared memory");
+    if (B == 0) return 0;
+    g_launches.fetch_add(1);
+    cudaError_t e = wf_launch_window_load(windows, idx, n_windows, x, B, C, T, t_major ? 1 : T, t_major ? C : 1, spans, stats, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail((int)e, cudaGetErrorString(e));
+}
+
+int wf_noise_scale(const float* x, const float* noise, float* y, long long n, float noise_level, float scale, const double* stats,
+                   long long n_stat, wf_stream_t stream)
+{
+    if (int e = check_device()) return e;
+    if (!x || !y || n < 0 || (noise && (!stats || n_stat < 2))) return fail(WF_E_ARG, "null pointer, or noise without the statistics of x");
+    if (((uintptr_t)x & 15) || ((uintptr_t)y & 15) || ((uintptr_t)noise & 15)) return fail(WF_E_ARG, "buffers must be 16-byte aligned");
+    if (n == 0) return 0;
+    g_launches.fetch_add(1);
+    cudaError_t e = wf_launch_noise_scale(x, noise, y, n, noise_level, scale, stats, n_stat, num_sms(), (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail((int)e, cudaGetErrorString(e));
+}
+
+int wf_keypoint_batch(const float* frames, long long n_frames, const long long* idx, float* y, int B, int K, int clean, wf_stream_t stream)
+{
+    if (int e = check_device()) return e;
+    if (!frames || !y || B < 0 || K <= 0 || n_frames < 0) return fail(WF_E_ARG, "null pointer or bad geometry");
+    if (((uintptr_t)frames & 7) || ((uintptr_t)y & 7)) return fail(WF_E_ARG, "keypoint buffers must be 8-byte aligned");
+    if (B == 0) return 0;
+    g_launches.fetch_add(1);
+    cudaError_t e = wf_launch_keypoint_repair(frames, n_frames, idx, y, B, K, clean, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail((int)e, cudaGetErrorString(e));
+}
+
+int wf_keypoint_sequences(float* frames, const long long* seq_off, int n_seq, int K, wf_stream_t stream)
+{
+    if (int e = check_device()) return e;
+    if (!frames || !seq_off || n_seq < 0 || K <= 0) return fail(WF_E_ARG, "null pointer or bad geometry");
+    if ((uintptr_t)frames & 7) return fail(WF_E_ARG, "keypoint buffer must be 8-byte aligned");
+    if (n_seq == 0) return 0;
+    g_launches.fetch_add(1);
+    cudaError_t e = wf_launch_keypoint_seq(frames, seq_off, n_seq, K, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail((int)e, cudaGetErrorString(e));
+}
+
 }  // extern "C"

@@ -154,3 +154,71 @@ def clip_adamw(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor,
         rc = _lib.lib().wf_clip_adamw(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(), _ptr(state),
                                       lr, beta1, beta2, eps, weight_decay, max_norm, grad_scale, _stream())
     _lib.check(rc, 'wf_clip_adamw')
+
+
+# ---- input side: plain functions, no autograd (data preparation has no gradient) ----
+def window_load(windows: torch.Tensor, idx, out: torch.Tensor = None, spans: torch.Tensor = None, stats: torch.Tensor = None,
+                t_major: bool = True) -> torch.Tensor:
+    """out[b] = windows[idx[b]] (idx None: identity, `out` may be `windows` itself) with the optional time-masking spans applied and
+    sum / sum-of-squares of the result accumulated into `stats` (2 doubles).  windows: [N, T, C] (t_major) or [N, C, T]."""
+    _need_cuda(windows, idx, out, spans, stats)
+    if windows.dim() != 3 or windows.dtype != torch.float32:
+        raise RuntimeError(f'window_load needs a float32 [N, {"T, C" if t_major else "C, T"}] tensor, got {list(windows.shape)} {windows.dtype}')
+    N = windows.shape[0]
+    T, C = (windows.shape[1], windows.shape[2]) if t_major else (windows.shape[2], windows.shape[1])
+    B = N if idx is None else idx.numel()
+    if idx is not None and idx.dtype != torch.int64:
+        raise RuntimeError('window indices must be int64')
+    if out is None:
+        out = torch.empty((B,) + tuple(windows.shape[1:]), device=windows.device, dtype=torch.float32)
+    elif out.shape[0] != B or out.shape[1:] != windows.shape[1:] or out.dtype != torch.float32:
+        raise RuntimeError(f'window_load: output of shape {list(out.shape)} does not hold {B} windows of {list(windows.shape[1:])}')
+    if spans is not None and (spans.dtype != torch.int32 or spans.numel() != 4 * B):
+        raise RuntimeError('spans must be an int32 [B, 2, 2] tensor of (start, length)')
+    if stats is not None and (stats.dtype != torch.float64 or stats.numel() < 2):
+        raise RuntimeError('stats must hold 2 doubles')
+    with torch.cuda.device(windows.device):
+        rc = _lib.lib().wf_window_load(_ptr(windows), N, _ptr(idx), _ptr(out), B, C, T, 1 if t_major else 0, _ptr(spans), _ptr(stats), _stream())
+    _lib.check(rc, 'wf_window_load')
+    return out
+
+
+def noise_scale(x: torch.Tensor, noise, level: float, scale: float, stats, out: torch.Tensor = None) -> torch.Tensor:
+    """(x + (noise*level)*std(x)) * scale; noise None: scaling only.  stats: the 2 doubles window_load filled for x."""
+    _need_cuda(x, noise, stats, out)
+    if x.dtype != torch.float32 or (noise is not None and (noise.dtype != torch.float32 or noise.numel() != x.numel())):
+        raise RuntimeError('noise_scale needs float32 tensors of equal size')
+    if out is None:
+        out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().wf_noise_scale(_ptr(x), _ptr(noise), _ptr(out), x.numel(), float(level), float(scale), _ptr(stats), x.numel(), _stream())
+    _lib.check(rc, 'wf_noise_scale')
+    return out
+
+
+def keypoint_batch(frames: torch.Tensor, idx, clean: bool = True, out: torch.Tensor = None) -> torch.Tensor:
+    """y[b] = frames[idx[b]] ([K,2]; zeros for indices outside the array) with all-zero joints replaced by the mean of the others."""
+    _need_cuda(frames, idx, out)
+    if frames.dim() != 3 or frames.shape[2] != 2 or frames.dtype != torch.float32:
+        raise RuntimeError(f'keypoint_batch needs a float32 [F, K, 2] tensor, got {list(frames.shape)} {frames.dtype}')
+    if idx is not None and idx.dtype != torch.int64:
+        raise RuntimeError('frame indices must be int64')
+    B = frames.shape[0] if idx is None else idx.numel()
+    K = frames.shape[1]
+    if out is None:
+        out = torch.empty(B, K, 2, device=frames.device, dtype=torch.float32)
+    with torch.cuda.device(frames.device):
+        rc = _lib.lib().wf_keypoint_batch(_ptr(frames), frames.shape[0], _ptr(idx), _ptr(out), B, K, 1 if clean else 0, _stream())
+    _lib.check(rc, 'wf_keypoint_batch')
+    return out
+
+
+def keypoint_sequences_(frames: torch.Tensor, seq_off: torch.Tensor) -> torch.Tensor:
+    """in place: zero joints interpolated along each sequence frames[seq_off[s]:seq_off[s+1]] (dataset.py:159-206)"""
+    _need_cuda(frames, seq_off)
+    if frames.dim() != 3 or frames.shape[2] != 2 or frames.dtype != torch.float32 or seq_off.dtype != torch.int64:
+        raise RuntimeError('keypoint_sequences_ needs float32 [F, K, 2] frames and int64 offsets')
+    with torch.cuda.device(frames.device):
+        rc = _lib.lib().wf_keypoint_sequences(_ptr(frames), _ptr(seq_off), seq_off.numel() - 1, frames.shape[1], _stream())
+    _lib.check(rc, 'wf_keypoint_sequences')
+    return frames

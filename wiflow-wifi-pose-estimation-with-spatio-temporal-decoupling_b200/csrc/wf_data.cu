@@ -66,8 +66,16 @@ window_load_kernel(const float* src, const long long* __restrict__ idx, long lon
                 s0 += a; s1 += c2;
             }
         }
+        if (4 * Q + tid < W) {           // scalar tail (W not a multiple of 4: single-window calls only)
+            const float* s1p = reinterpret_cast<const float*>(sp);
+            float* d1p = reinterpret_cast<float*>(dp);
+            const float v = have ? s1p[4 * Q + tid] : 0.f;
+            if (static_cast<const float*>(d1p) != s1p) d1p[4 * Q + tid] = v;
+            if (stats) { s0 += v; s1 += v * v; }
+        }
     } else {
         for (int q = tid; q < Q; q += DATA_THREADS) win4[q] = have ? sp[q] : f4zero();
+        if (4 * Q + tid < W) win[4 * Q + tid] = have ? reinterpret_cast<const float*>(sp)[4 * Q + tid] : 0.f;
         __syncthreads();
         const int warp = tid >> 5, lane = tid & 31;
         for (int k = 0; k < 2; ++k) {
@@ -91,6 +99,11 @@ window_load_kernel(const float* src, const long long* __restrict__ idx, long lon
                 float c2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
                 s0 += a; s1 += c2;
             }
+        }
+        if (4 * Q + tid < W) {
+            const float v = win[4 * Q + tid];
+            reinterpret_cast<float*>(dp)[4 * Q + tid] = v;
+            if (stats) { s0 += v; s1 += v * v; }
         }
     }
     if (stats) block_accum2_d(s0, s1, stats);
@@ -209,7 +222,7 @@ cudaError_t wf_launch_window_load(const float* src, const long long* idx, long l
                                   const int* spans, double* stats, cudaStream_t stream)
 {
     const int W = C * T;
-    const size_t smem = spans ? (size_t)W * sizeof(float) : 0;     // only masked windows are staged in shared memory
+    const size_t smem = spans ? (size_t)((W + 3) / 4 * 4) * sizeof(float) : 0;     // only masked windows are staged in shared memory
     static size_t opted = 0;
     if (smem > 48 * 1024 && smem > opted) {
         cudaError_t e = cudaFuncSetAttribute(window_load_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

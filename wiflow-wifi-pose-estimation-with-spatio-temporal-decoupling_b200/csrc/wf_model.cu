@@ -1100,7 +1100,8 @@ int wf_window_load(const float* windows, long long n_windows, const long long* i
 {
     if (int e = check_device()) return e;
     if (!windows || !x || B < 0 || C <= 0 || T <= 0 || n_windows <= 0) return fail(WF_E_ARG, "null pointer or bad window geometry");
-    if (((long long)C * T) % 4 != 0 || ((uintptr_t)windows & 15) || ((uintptr_t)x & 15)) return fail(WF_E_ARG, "windows must be 16-byte aligned with C*T a multiple of 4");
+    if (((uintptr_t)windows & 15) || ((uintptr_t)x & 15)) return fail(WF_E_ARG, "window buffers must be 16-byte aligned");
+    if (((long long)C * T) % 4 != 0 && (B > 1 || idx)) return fail(WF_E_ARG, "C*T must be a multiple of 4 (16-byte aligned windows) unless a single window is processed in place of the whole buffer");
     if (spans && (size_t)C * T * sizeof(float) > 200 * 1024) return fail(WF_E_UNSUPPORTED, "window larger than 200 KB of shared memory");
     if (B == 0) return 0;
     g_launches.fetch_add(1);

@@ -157,7 +157,7 @@ class PreprocessedCSIKeypointsDataset:
             x, y = self.batch([idx])
             x = x[0]
         else:
-            x = torch.from_numpy(np.ascontiguousarray(self.csi_windows[idx], dtype=np.float32)).to(self.device)
+            x = torch.from_numpy(np.array(self.csi_windows[idx], dtype=np.float32)).to(self.device)
             y = ops.keypoint_batch(self.frames, torch.tensor([self.frame_index[idx]], device=self.device), self._clean_per_batch)
         if self.transform:
             x = self.transform(x)

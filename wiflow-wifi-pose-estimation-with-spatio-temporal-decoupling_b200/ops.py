@@ -177,6 +177,8 @@ def window_load(windows: torch.Tensor, idx, out: torch.Tensor = None, spans: tor
         raise RuntimeError('spans must be an int32 [B, 2, 2] tensor of (start, length)')
     if stats is not None and (stats.dtype != torch.float64 or stats.numel() < 2):
         raise RuntimeError('stats must hold 2 doubles')
+    if B == 0:                                   # an empty batch is an empty tensor, not an error (nothing to launch)
+        return out
     with torch.cuda.device(windows.device):
         rc = _lib.lib().wf_window_load(_ptr(windows), N, _ptr(idx), _ptr(out), B, C, T, 1 if t_major else 0, _ptr(spans), _ptr(stats), _stream())
     _lib.check(rc, 'wf_window_load')

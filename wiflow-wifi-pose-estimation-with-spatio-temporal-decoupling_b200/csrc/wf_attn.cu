@@ -7,6 +7,7 @@
 // tile that is staged once per CTA with bn_qkv's affine applied on load.  BatchNorm on the logits needs batch
 // statistics, so forward and backward are each two passes: a statistics pass and a main pass that recomputes QK^T
 // (0.77 MMAC/sample, cheaper than spilling the 192 KB/sample logits to HBM).
+#include <cstdlib>
 #include "wf_common.cuh"
 #include "wf_elem.h"
 
@@ -15,7 +16,7 @@ namespace {
 enum { ATT_FWD_STATS = 0, ATT_FWD = 1, ATT_BWD_STATS = 2, ATT_BWD = 3 };
 
 template <int L, int LP, int RT, bool WIDTH, int MODE>
-__global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * L <= 320 ? 3 : 2) : (MODE == ATT_BWD ? 1 : 0)) attn_kernel(const AttnP p)
+__global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * L <= 320 ? 3 : 2) : (MODE == ATT_BWD ? (RT * 8 * L <= 160 ? 3 : 1) : 0)) attn_kernel(const AttnP p)
 {
     constexpr int NT = RT * 8 * L;
     constexpr int CS = RT * LP;                         // channel stride inside a tile
@@ -24,7 +25,7 @@ __global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * 
     extern __shared__ __align__(16) float smem[];
     float* T = smem;                                    // qkv tile (bn_qkv applied)
     float* G = smem + TILE;                             // backward: d sv tile (BN-backward applied)
-    float* MX = G + GTILE;                              // backward: [RT*8][L][LP] scratch matrix
+    float* MX = G + GTILE;                              // backward: two [RT*8][L][LP] scratch matrices (d logits, probabilities)
     auto tix = [](int c, int r, int s) { return c * CS + (c >> 3) * 4 + r * LP + s; };
 
     const int tid = threadIdx.x;
@@ -182,7 +183,17 @@ __global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * 
     }
 
     float gs[8];
-    if (MODE >= ATT_BWD_STATS) {
+    if (MODE == ATT_BWD) {
+        // Main backward pass.  Register pressure decides the occupancy here, so the logits and the probabilities of this thread's
+        // row are parked in two shared-memory matrices as soon as they exist (the dk / dv contractions need them transposed
+        // anyway): M holds the row's logits, later overwritten in place by d logits; MP holds the probabilities.
+        float* M = MX + (r * 8 + g) * (L * LP);
+        float* MP = MX + RT * 8 * L * LP + (r * 8 + g) * (L * LP);
+#pragma unroll
+        for (int j4 = 0; j4 < LP / 4; ++j4) {
+            st4(&M[i * LP + j4 * 4], make_float4(lg[j4 * 4], lg[j4 * 4 + 1], lg[j4 * 4 + 2], lg[j4 * 4 + 3]));
+            st4(&MP[i * LP + j4 * 4], make_float4(pr[j4 * 4], pr[j4 * 4 + 1], pr[j4 * 4 + 2], pr[j4 * 4 + 3]));
+        }
 #pragma unroll
         for (int c = 0; c < 8; ++c) gs[c] = G[tix(g * 8 + c, r, i)];
         // dp_j = sum_c gs[c] v[c][j];  dz_j = p_j (dp_j - sum_k dp_k p_k)
@@ -201,80 +212,87 @@ __global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * 
         float dot = 0.f;
 #pragma unroll
         for (int j = 0; j < L; ++j) dot = fmaf(dp[j], pr[j], dot);
+        // d logits through bn_similarity backward, written over the row's logits; dq accumulates on the way
+        const float al = p.sim_alpha[g], be = p.sim_beta[g], de = p.sim_delta[g], mu = p.sim_mean[g];
+        float dq[8];
 #pragma unroll
-        for (int j = 0; j < LP; ++j) dp[j] = (j < L) ? pr[j] * (dp[j] - dot) : 0.f;      // dp now holds dz
-
-        if (MODE == ATT_BWD_STATS) {
+        for (int c = 0; c < 8; ++c) dq[c] = 0.f;
 #pragma unroll
-            const float mu = p.sim_mean[g];
+        for (int j4 = 0; j4 < LP / 4; ++j4) {
+            const float4 l4 = ld4(&M[i * LP + j4 * 4]);
+            const float lgv[4] = {l4.x, l4.y, l4.z, l4.w};
+            float dl[4];
 #pragma unroll
-            for (int j = 0; j < L; ++j) { st0 += dp[j]; st1 = fmaf(dp[j], lg[j] - mu, st1); }
-        } else {
-            // d logits through bn_similarity backward
-            const float al = p.sim_alpha[g], be = p.sim_beta[g], de = p.sim_delta[g], mu = p.sim_mean[g];
-#pragma unroll
-            for (int j = 0; j < LP; ++j) dp[j] = (j < L) ? fmaf(al, dp[j], fmaf(be, lg[j] - mu, de)) : 0.f;   // dp now holds dl
-            float dq[8];
+            for (int e = 0; e < 4; ++e) {
+                const int j = j4 * 4 + e;
+                dl[e] = (j < L) ? fmaf(al, pr[j] * (dp[j] - dot), fmaf(be, lgv[e] - mu, de)) : 0.f;
+            }
+            st4(&M[i * LP + j4 * 4], make_float4(dl[0], dl[1], dl[2], dl[3]));
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                float a = 0.f;
-#pragma unroll
-                for (int j4 = 0; j4 < LP / 4; ++j4) {
-                    const float4 k4 = ld4(&T[tix(64 + g * 8 + c, r, j4 * 4)]);
-                    a = fmaf(dp[j4 * 4 + 0], k4.x, a); a = fmaf(dp[j4 * 4 + 1], k4.y, a);
-                    a = fmaf(dp[j4 * 4 + 2], k4.z, a); a = fmaf(dp[j4 * 4 + 3], k4.w, a);
-                }
-                dq[c] = a;
+                const float4 k4 = ld4(&T[tix(64 + g * 8 + c, r, j4 * 4)]);
+                dq[c] = fmaf(dl[0], k4.x, dq[c]); dq[c] = fmaf(dl[1], k4.y, dq[c]);
+                dq[c] = fmaf(dl[2], k4.z, dq[c]); dq[c] = fmaf(dl[3], k4.w, dq[c]);
             }
-            float* M = MX + (r * 8 + g) * (L * LP);
-#pragma unroll
-            for (int j4 = 0; j4 < LP / 4; ++j4)
-                st4(&M[i * LP + j4 * 4], make_float4(dp[j4 * 4], dp[j4 * 4 + 1], dp[j4 * 4 + 2], dp[j4 * 4 + 3]));
-            __syncthreads();
-            // dk[c][me] = sum_i' dl[i'][me] q[c][i']
-            float dk[8], dv[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
-            for (int ii = 0; ii < L; ++ii) {
-                const float m = M[ii * LP + i];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) dk[c] = fmaf(m, T[tix(g * 8 + c, r, ii)], dk[c]);
-            }
-            __syncthreads();
-#pragma unroll
-            for (int j4 = 0; j4 < LP / 4; ++j4)
-                st4(&M[i * LP + j4 * 4], make_float4(pr[j4 * 4], pr[j4 * 4 + 1], pr[j4 * 4 + 2], pr[j4 * 4 + 3]));
-            __syncthreads();
-            // dv[c][me] = sum_i' p[i'][me] gs[c][i']
-            for (int ii = 0; ii < L; ++ii) {
-                const float m = M[ii * LP + i];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) dv[c] = fmaf(m, G[tix(g * 8 + c, r, ii)], dv[c]);
-            }
-            __syncthreads();
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                T[tix(g * 8 + c, r, i)] = dq[c];
-                T[tix(64 + g * 8 + c, r, i)] = dk[c];
-                T[tix(128 + g * 8 + c, r, i)] = dv[c];
-            }
-            __syncthreads();
-            if (WIDTH) {
-                constexpr int Q = L / 4;
-                for (int idx = tid; idx < 192 * RT * Q; idx += NT) {
-                    const int qq = idx % Q, rr = (idx / Q) % RT, c = idx / (Q * RT);
-                    if (row0 + rr < nrows) st4(p.dqkv + c * cstride + row_base(rr) + qq * 4, ld4(&T[tix(c, rr, qq * 4)]));
-                }
-            } else {
-                for (int idx = tid; idx < 192 * L; idx += NT) {
-                    const int s = idx % L, c = idx / L;
-                    if (row0 < nrows)
-                        st4(p.dqkv + c * cstride + (long long)s * N + row0,
-                            make_float4(T[tix(c, 0, s)], T[tix(c, 1, s)], T[tix(c, 2, s)], T[tix(c, 3, s)]));
-                }
-            }
-            return;
         }
+        __syncthreads();
+        // dk[c][me] = sum_i' dl[i'][me] q[c][i'];  dv[c][me] = sum_i' p[i'][me] gs[c][i']
+        float dk[8], dv[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
+        for (int ii = 0; ii < L; ++ii) {
+            const float m = M[ii * LP + i], pp = MP[ii * LP + i];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                dk[c] = fmaf(m, T[tix(g * 8 + c, r, ii)], dk[c]);
+                dv[c] = fmaf(pp, G[tix(g * 8 + c, r, ii)], dv[c]);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            T[tix(g * 8 + c, r, i)] = dq[c];
+            T[tix(64 + g * 8 + c, r, i)] = dk[c];
+            T[tix(128 + g * 8 + c, r, i)] = dv[c];
+        }
+        __syncthreads();
+        if (WIDTH) {
+            constexpr int Q = L / 4;
+            for (int idx = tid; idx < 192 * RT * Q; idx += NT) {
+                const int qq = idx % Q, rr = (idx / Q) % RT, c = idx / (Q * RT);
+                if (row0 + rr < nrows) st4(p.dqkv + c * cstride + row_base(rr) + qq * 4, ld4(&T[tix(c, rr, qq * 4)]));
+            }
+        } else {
+            for (int idx = tid; idx < 192 * L; idx += NT) {
+                const int s = idx % L, c = idx / L;
+                if (row0 < nrows)
+                    st4(p.dqkv + c * cstride + (long long)s * N + row0,
+                        make_float4(T[tix(c, 0, s)], T[tix(c, 1, s)], T[tix(c, 2, s)], T[tix(c, 3, s)]));
+            }
+        }
+        return;
+    }
+    if (MODE == ATT_BWD_STATS) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) gs[c] = G[tix(g * 8 + c, r, i)];
+        float dp[LP];
+#pragma unroll
+        for (int j = 0; j < LP; ++j) dp[j] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+#pragma unroll
+            for (int j4 = 0; j4 < LP / 4; ++j4) {
+                const float4 v4 = ld4(&T[tix(128 + g * 8 + c, r, j4 * 4)]);
+                dp[j4 * 4 + 0] = fmaf(gs[c], v4.x, dp[j4 * 4 + 0]); dp[j4 * 4 + 1] = fmaf(gs[c], v4.y, dp[j4 * 4 + 1]);
+                dp[j4 * 4 + 2] = fmaf(gs[c], v4.z, dp[j4 * 4 + 2]); dp[j4 * 4 + 3] = fmaf(gs[c], v4.w, dp[j4 * 4 + 3]);
+            }
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < L; ++j) dot = fmaf(dp[j], pr[j], dot);
+        const float mu = p.sim_mean[g];
+#pragma unroll
+        for (int j = 0; j < L; ++j) { const float dz = pr[j] * (dp[j] - dot); st0 += dz; st1 = fmaf(dz, lg[j] - mu, st1); }
     }
 
     // ------------------------------- statistics reduction (per group) -------------------------------
@@ -303,7 +321,7 @@ cudaError_t launch_attn(const AttnP& p, cudaStream_t st)
     constexpr int CS = RT * LP;
     size_t smem = (192 * CS + 24 * 4) * sizeof(float);
     if (MODE >= ATT_BWD_STATS) smem += (64 * CS + 8 * 4) * sizeof(float);
-    if (MODE == ATT_BWD) smem += (size_t)RT * 8 * L * LP * sizeof(float);
+    if (MODE == ATT_BWD) smem += (size_t)2 * RT * 8 * L * LP * sizeof(float);
     auto kern = attn_kernel<L, LP, RT, WIDTH, MODE>;
     static bool configured = false;
     if (!configured) {
@@ -319,6 +337,10 @@ cudaError_t launch_attn(const AttnP& p, cudaStream_t st)
 template <int MODE>
 cudaError_t launch_attn_mode(const AttnP& p, cudaStream_t st)
 {
+    // backward main pass of the width axis: one row per CTA (160 threads, three CTAs per SM whose staging / compute / store phases
+    // interleave) instead of two rows in one 320-thread CTA per SM
+    static const bool rt1 = [] { const char* e = std::getenv("WF_ATTN_BWD_RT1"); return !(e && e[0] == '0'); }();
+    if (p.width && MODE == ATT_BWD && rt1) return launch_attn<20, 20, 1, true, MODE>(p, st);
     if (p.width) return launch_attn<20, 20, 2, true, MODE>(p, st);
     return launch_attn<15, 16, 4, false, MODE>(p, st);
 }

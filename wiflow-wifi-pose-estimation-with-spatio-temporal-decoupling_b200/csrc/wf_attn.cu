@@ -15,23 +15,33 @@ namespace {
 
 enum { ATT_FWD_STATS = 0, ATT_FWD = 1, ATT_BWD_STATS = 2, ATT_BWD = 3 };
 
-template <int L, int LP, int RT, bool WIDTH, int MODE>
-__global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * L <= 320 ? 3 : 2) : (MODE == ATT_BWD ? (RT * 8 * L <= 160 ? 3 : 1) : 0)) attn_kernel(const AttnP p)
+// A CTA owns RT rows x GH of the 8 groups (blockIdx.y selects which): the groups are independent (group g uses channels
+// g*8..g*8+7 of each of q, k, v and of d sv), so narrower CTAs cost no redundant traffic and more of them fit an SM.
+constexpr int attn_min_blocks(int nt, int mode)
 {
-    constexpr int NT = RT * 8 * L;
+    return mode == ATT_BWD ? (nt <= 160 ? 3 : nt <= 240 ? 2 : 1) : mode == ATT_BWD_STATS ? (nt <= 240 ? 4 : nt <= 320 ? 3 : 2) : 0;
+}
+
+template <int L, int LP, int RT, int GH, bool WIDTH, int MODE>
+__global__ void __launch_bounds__(RT * GH * L, attn_min_blocks(RT * GH * L, MODE)) attn_kernel(const AttnP p)
+{
+    constexpr int NT = RT * GH * L;
+    constexpr int GC = GH * 8;                          // channels per section (q, k, v, d sv) in this CTA
     constexpr int CS = RT * LP;                         // channel stride inside a tile
-    constexpr int TILE = 192 * CS + 24 * 4;             // + 4 floats of padding per group of 8 channels
-    constexpr int GTILE = 64 * CS + 8 * 4;
+    constexpr int TILE = 3 * GC * CS + 3 * GH * 4;      // + 4 floats of padding per group of 8 channels
+    constexpr int GTILE = GC * CS + GH * 4;
     extern __shared__ __align__(16) float smem[];
     float* T = smem;                                    // qkv tile (bn_qkv applied)
     float* G = smem + TILE;                             // backward: d sv tile (BN-backward applied)
-    float* MX = G + GTILE;                              // backward: two [RT*8][L][LP] scratch matrices (d logits, probabilities)
+    float* MX = G + GTILE;                              // backward: two [RT*GH][L][LP] scratch matrices (d logits, probabilities)
     auto tix = [](int c, int r, int s) { return c * CS + (c >> 3) * 4 + r * LP + s; };
 
     const int tid = threadIdx.x;
     const int N = p.N, B = p.B;
     const long long cstride = 15LL * N;                 // channel stride of [C][15][N] tensors
     const int row0 = blockIdx.x * RT;
+    const int g0 = blockIdx.y * GH;                     // first group of this CTA
+    auto qkv_chan = [&](int c) { return (c / GC) * 64 + g0 * 8 + (c % GC); };      // tile channel -> channel of the [192] qkv tensor
     const int nrows = WIDTH ? 15 * B : N;
 
     // global offset of element s of tile row r (excluding the channel term); rows are (h,b) or n
@@ -44,24 +54,24 @@ __global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * 
     // ------------------------------- stage tiles -------------------------------
     if (WIDTH) {
         constexpr int Q = L / 4;
-        for (int idx = tid; idx < 192 * RT * Q; idx += NT) {
-            const int q = idx % Q, r = (idx / Q) % RT, c = idx / (Q * RT);
+        for (int idx = tid; idx < 3 * GC * RT * Q; idx += NT) {
+            const int q = idx % Q, r = (idx / Q) % RT, c = idx / (Q * RT), cg = qkv_chan(c);
             float4 v = f4zero();
             if (row0 + r < nrows) {
-                v = ld4(p.qkv_raw + c * cstride + row_base(r) + q * 4);
-                const float a = p.qkv_scale[c], b = p.qkv_shift[c], mu = p.qkv_mean[c];
+                v = ld4(p.qkv_raw + cg * cstride + row_base(r) + q * 4);
+                const float a = p.qkv_scale[cg], b = p.qkv_shift[cg], mu = p.qkv_mean[cg];
                 v.x = fmaf(a, v.x - mu, b); v.y = fmaf(a, v.y - mu, b); v.z = fmaf(a, v.z - mu, b); v.w = fmaf(a, v.w - mu, b);
             }
             st4(&T[tix(c, r, q * 4)], v);
         }
         if (MODE >= ATT_BWD_STATS) {
-            for (int idx = tid; idx < 64 * RT * Q; idx += NT) {
-                const int q = idx % Q, r = (idx / Q) % RT, c = idx / (Q * RT);
+            for (int idx = tid; idx < GC * RT * Q; idx += NT) {
+                const int q = idx % Q, r = (idx / Q) % RT, c = idx / (Q * RT), cg = g0 * 8 + c;
                 float4 v = f4zero();
                 if (row0 + r < nrows) {
-                    const long long off = c * cstride + row_base(r) + q * 4;
+                    const long long off = cg * cstride + row_base(r) + q * 4;
                     const float4 d = ld4(p.dsv + off), w = ld4(p.sv_raw + off);
-                    const float a = p.sv_alpha[c], b = p.sv_beta[c], e = p.sv_delta[c], mu = p.sv_mean[c];
+                    const float a = p.sv_alpha[cg], b = p.sv_beta[cg], e = p.sv_delta[cg], mu = p.sv_mean[cg];
                     v.x = fmaf(a, d.x, fmaf(b, w.x - mu, e)); v.y = fmaf(a, d.y, fmaf(b, w.y - mu, e));
                     v.z = fmaf(a, d.z, fmaf(b, w.z - mu, e)); v.w = fmaf(a, d.w, fmaf(b, w.w - mu, e));
                 }
@@ -70,24 +80,24 @@ __global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * 
         }
     } else {
         static_assert(WIDTH || RT == 4, "height-axis tiles are 4 consecutive n wide");
-        for (int idx = tid; idx < 192 * LP; idx += NT) {
-            const int s = idx % LP, c = idx / LP;
+        for (int idx = tid; idx < 3 * GC * LP; idx += NT) {
+            const int s = idx % LP, c = idx / LP, cg = qkv_chan(c);
             float4 v = f4zero();
             if (s < L && row0 < nrows) {
-                v = ld4(p.qkv_raw + c * cstride + (long long)s * N + row0);
-                const float a = p.qkv_scale[c], b = p.qkv_shift[c], mu = p.qkv_mean[c];
+                v = ld4(p.qkv_raw + cg * cstride + (long long)s * N + row0);
+                const float a = p.qkv_scale[cg], b = p.qkv_shift[cg], mu = p.qkv_mean[cg];
                 v.x = fmaf(a, v.x - mu, b); v.y = fmaf(a, v.y - mu, b); v.z = fmaf(a, v.z - mu, b); v.w = fmaf(a, v.w - mu, b);
             }
             T[tix(c, 0, s)] = v.x; T[tix(c, 1, s)] = v.y; T[tix(c, 2, s)] = v.z; T[tix(c, 3, s)] = v.w;
         }
         if (MODE >= ATT_BWD_STATS) {
-            for (int idx = tid; idx < 64 * LP; idx += NT) {
-                const int s = idx % LP, c = idx / LP;
+            for (int idx = tid; idx < GC * LP; idx += NT) {
+                const int s = idx % LP, c = idx / LP, cg = g0 * 8 + c;
                 float4 v = f4zero();
                 if (s < L && row0 < nrows) {
-                    const long long off = c * cstride + (long long)s * N + row0;
+                    const long long off = cg * cstride + (long long)s * N + row0;
                     const float4 d = ld4(p.dsv + off), w = ld4(p.sv_raw + off);
-                    const float a = p.sv_alpha[c], b = p.sv_beta[c], e = p.sv_delta[c], mu = p.sv_mean[c];
+                    const float a = p.sv_alpha[cg], b = p.sv_beta[cg], e = p.sv_delta[cg], mu = p.sv_mean[cg];
                     v.x = fmaf(a, d.x, fmaf(b, w.x - mu, e)); v.y = fmaf(a, d.y, fmaf(b, w.y - mu, e));
                     v.z = fmaf(a, d.z, fmaf(b, w.z - mu, e)); v.w = fmaf(a, d.w, fmaf(b, w.w - mu, e));
                 }
@@ -98,7 +108,8 @@ __global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * 
     __syncthreads();
 
     // ------------------------------- per-thread attention row -------------------------------
-    const int i = tid % L, g = (tid / L) % 8, r = tid / (8 * L);
+    const int i = tid % L, g = (tid / L) % GH, r = tid / (GH * L);
+    const int gg0 = g0 + g;                             // group index into the per-group coefficient / statistics arrays
     const bool rvalid = (row0 + r) < nrows;
     float q[8];
 #pragma unroll
@@ -110,7 +121,7 @@ __global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * 
     for (int c = 0; c < 8; ++c) {
 #pragma unroll
         for (int j4 = 0; j4 < LP / 4; ++j4) {
-            const float4 k4 = ld4(&T[tix(64 + g * 8 + c, r, j4 * 4)]);
+            const float4 k4 = ld4(&T[tix(GC + g * 8 + c, r, j4 * 4)]);
             lg[j4 * 4 + 0] = fmaf(q[c], k4.x, lg[j4 * 4 + 0]);
             lg[j4 * 4 + 1] = fmaf(q[c], k4.y, lg[j4 * 4 + 1]);
             lg[j4 * 4 + 2] = fmaf(q[c], k4.z, lg[j4 * 4 + 2]);
@@ -125,7 +136,7 @@ __global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * 
 #pragma unroll
         for (int j = 0; j < L; ++j) { st0 += lg[j]; st1 = fmaf(lg[j], lg[j], st1); }
     } else {
-        const float ss = p.sim_scale[g], ts = p.sim_shift[g], ms = p.sim_mean[g];
+        const float ss = p.sim_scale[gg0], ts = p.sim_shift[gg0], ms = p.sim_mean[gg0];
         float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < L; ++j) { pr[j] = fmaf(ss, lg[j] - ms, ts); mx = fmaxf(mx, pr[j]); }
@@ -146,7 +157,7 @@ __global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * 
             float a = 0.f;
 #pragma unroll
             for (int j4 = 0; j4 < LP / 4; ++j4) {
-                const float4 v4 = ld4(&T[tix(128 + g * 8 + c, r, j4 * 4)]);
+                const float4 v4 = ld4(&T[tix(2 * GC + g * 8 + c, r, j4 * 4)]);
                 a = fmaf(pr[j4 * 4 + 0], v4.x, a); a = fmaf(pr[j4 * 4 + 1], v4.y, a);
                 a = fmaf(pr[j4 * 4 + 2], v4.z, a); a = fmaf(pr[j4 * 4 + 3], v4.w, a);
             }
@@ -158,26 +169,26 @@ __global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * 
         __syncthreads();
         if (WIDTH) {
             constexpr int Q = L / 4;
-            for (int idx = tid; idx < 64 * RT * Q; idx += NT) {
+            for (int idx = tid; idx < GC * RT * Q; idx += NT) {
                 const int qq = idx % Q, rr = (idx / Q) % RT, c = idx / (Q * RT);
-                if (row0 + rr < nrows) st4(p.sv_raw + c * cstride + row_base(rr) + qq * 4, ld4(&T[tix(c, rr, qq * 4)]));
+                if (row0 + rr < nrows) st4(p.sv_raw + (g0 * 8 + c) * cstride + row_base(rr) + qq * 4, ld4(&T[tix(c, rr, qq * 4)]));
             }
         } else {
-            for (int idx = tid; idx < 64 * L; idx += NT) {
+            for (int idx = tid; idx < GC * L; idx += NT) {
                 const int s = idx % L, c = idx / L;
                 if (row0 < nrows)
-                    st4(p.sv_raw + c * cstride + (long long)s * N + row0,
+                    st4(p.sv_raw + (g0 * 8 + c) * cstride + (long long)s * N + row0,
                         make_float4(T[tix(c, 0, s)], T[tix(c, 1, s)], T[tix(c, 2, s)], T[tix(c, 3, s)]));
             }
         }
-        if (p.sv_s0 && tid < 64) {
+        if (p.sv_s0 && tid < GC) {
             float a = 0.f, b = 0.f;
             for (int rr = 0; rr < RT; ++rr) {
                 if (row0 + rr >= nrows) break;
                 for (int s = 0; s < L; ++s) { const float v = T[tix(tid, rr, s)]; a += v; b = fmaf(v, v, b); }
             }
-            atomicAdd(p.sv_s0 + tid, (double)a);
-            atomicAdd(p.sv_s1 + tid, (double)b);
+            atomicAdd(p.sv_s0 + g0 * 8 + tid, (double)a);
+            atomicAdd(p.sv_s1 + g0 * 8 + tid, (double)b);
         }
         return;
     }
@@ -187,8 +198,8 @@ __global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * 
         // Main backward pass.  Register pressure decides the occupancy here, so the logits and the probabilities of this thread's
         // row are parked in two shared-memory matrices as soon as they exist (the dk / dv contractions need them transposed
         // anyway): M holds the row's logits, later overwritten in place by d logits; MP holds the probabilities.
-        float* M = MX + (r * 8 + g) * (L * LP);
-        float* MP = MX + RT * 8 * L * LP + (r * 8 + g) * (L * LP);
+        float* M = MX + (r * GH + g) * (L * LP);
+        float* MP = MX + RT * GH * L * LP + (r * GH + g) * (L * LP);
 #pragma unroll
         for (int j4 = 0; j4 < LP / 4; ++j4) {
             st4(&M[i * LP + j4 * 4], make_float4(lg[j4 * 4], lg[j4 * 4 + 1], lg[j4 * 4 + 2], lg[j4 * 4 + 3]));
@@ -204,7 +215,7 @@ __global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * 
         for (int c = 0; c < 8; ++c) {
 #pragma unroll
             for (int j4 = 0; j4 < LP / 4; ++j4) {
-                const float4 v4 = ld4(&T[tix(128 + g * 8 + c, r, j4 * 4)]);
+                const float4 v4 = ld4(&T[tix(2 * GC + g * 8 + c, r, j4 * 4)]);
                 dp[j4 * 4 + 0] = fmaf(gs[c], v4.x, dp[j4 * 4 + 0]); dp[j4 * 4 + 1] = fmaf(gs[c], v4.y, dp[j4 * 4 + 1]);
                 dp[j4 * 4 + 2] = fmaf(gs[c], v4.z, dp[j4 * 4 + 2]); dp[j4 * 4 + 3] = fmaf(gs[c], v4.w, dp[j4 * 4 + 3]);
             }
@@ -213,7 +224,7 @@ __global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * 
 #pragma unroll
         for (int j = 0; j < L; ++j) dot = fmaf(dp[j], pr[j], dot);
         // d logits through bn_similarity backward, written over the row's logits; dq accumulates on the way
-        const float al = p.sim_alpha[g], be = p.sim_beta[g], de = p.sim_delta[g], mu = p.sim_mean[g];
+        const float al = p.sim_alpha[gg0], be = p.sim_beta[gg0], de = p.sim_delta[gg0], mu = p.sim_mean[gg0];
         float dq[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) dq[c] = 0.f;
@@ -230,7 +241,7 @@ __global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * 
             st4(&M[i * LP + j4 * 4], make_float4(dl[0], dl[1], dl[2], dl[3]));
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                const float4 k4 = ld4(&T[tix(64 + g * 8 + c, r, j4 * 4)]);
+                const float4 k4 = ld4(&T[tix(GC + g * 8 + c, r, j4 * 4)]);
                 dq[c] = fmaf(dl[0], k4.x, dq[c]); dq[c] = fmaf(dl[1], k4.y, dq[c]);
                 dq[c] = fmaf(dl[2], k4.z, dq[c]); dq[c] = fmaf(dl[3], k4.w, dq[c]);
             }
@@ -252,21 +263,21 @@ __global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * 
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             T[tix(g * 8 + c, r, i)] = dq[c];
-            T[tix(64 + g * 8 + c, r, i)] = dk[c];
-            T[tix(128 + g * 8 + c, r, i)] = dv[c];
+            T[tix(GC + g * 8 + c, r, i)] = dk[c];
+            T[tix(2 * GC + g * 8 + c, r, i)] = dv[c];
         }
         __syncthreads();
         if (WIDTH) {
             constexpr int Q = L / 4;
-            for (int idx = tid; idx < 192 * RT * Q; idx += NT) {
+            for (int idx = tid; idx < 3 * GC * RT * Q; idx += NT) {
                 const int qq = idx % Q, rr = (idx / Q) % RT, c = idx / (Q * RT);
-                if (row0 + rr < nrows) st4(p.dqkv + c * cstride + row_base(rr) + qq * 4, ld4(&T[tix(c, rr, qq * 4)]));
+                if (row0 + rr < nrows) st4(p.dqkv + qkv_chan(c) * cstride + row_base(rr) + qq * 4, ld4(&T[tix(c, rr, qq * 4)]));
             }
         } else {
-            for (int idx = tid; idx < 192 * L; idx += NT) {
+            for (int idx = tid; idx < 3 * GC * L; idx += NT) {
                 const int s = idx % L, c = idx / L;
                 if (row0 < nrows)
-                    st4(p.dqkv + c * cstride + (long long)s * N + row0,
+                    st4(p.dqkv + qkv_chan(c) * cstride + (long long)s * N + row0,
                         make_float4(T[tix(c, 0, s)], T[tix(c, 1, s)], T[tix(c, 2, s)], T[tix(c, 3, s)]));
             }
         }
@@ -282,7 +293,7 @@ __global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * 
         for (int c = 0; c < 8; ++c) {
 #pragma unroll
             for (int j4 = 0; j4 < LP / 4; ++j4) {
-                const float4 v4 = ld4(&T[tix(128 + g * 8 + c, r, j4 * 4)]);
+                const float4 v4 = ld4(&T[tix(2 * GC + g * 8 + c, r, j4 * 4)]);
                 dp[j4 * 4 + 0] = fmaf(gs[c], v4.x, dp[j4 * 4 + 0]); dp[j4 * 4 + 1] = fmaf(gs[c], v4.y, dp[j4 * 4 + 1]);
                 dp[j4 * 4 + 2] = fmaf(gs[c], v4.z, dp[j4 * 4 + 2]); dp[j4 * 4 + 3] = fmaf(gs[c], v4.w, dp[j4 * 4 + 3]);
             }
@@ -290,7 +301,7 @@ __global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * 
         float dot = 0.f;
 #pragma unroll
         for (int j = 0; j < L; ++j) dot = fmaf(dp[j], pr[j], dot);
-        const float mu = p.sim_mean[g];
+        const float mu = p.sim_mean[gg0];
 #pragma unroll
         for (int j = 0; j < L; ++j) { const float dz = pr[j] * (dp[j] - dot); st0 += dz; st1 = fmaf(dz, lg[j] - mu, st1); }
     }
@@ -301,28 +312,29 @@ __global__ void __launch_bounds__(RT * 8 * L, MODE == ATT_BWD_STATS ? (RT * 8 * 
         float2* part = reinterpret_cast<float2*>(smem);  // reuse the tile
         part[tid] = rvalid ? make_float2(st0, st1) : make_float2(0.f, 0.f);
         __syncthreads();
-        if (tid < 16) {
+        if (tid < 2 * GH) {
             const int gg = tid >> 1, which = tid & 1;
             double a = 0;
             for (int rr = 0; rr < RT; ++rr)
                 for (int ii = 0; ii < L; ++ii) {
-                    const float2 v = part[(rr * 8 + gg) * L + ii];
+                    const float2 v = part[(rr * GH + gg) * L + ii];
                     a += which ? v.y : v.x;
                 }
             double* dst = (MODE == ATT_FWD_STATS) ? (which ? p.sim_s1 : p.sim_s0) : (which ? p.dsim_s1 : p.dsim_s0);
-            atomicAdd(dst + gg, a);
+            atomicAdd(dst + g0 + gg, a);
         }
     }
 }
 
-template <int L, int LP, int RT, bool WIDTH, int MODE>
+template <int L, int LP, int RT, int GH, bool WIDTH, int MODE>
 cudaError_t launch_attn(const AttnP& p, cudaStream_t st)
 {
-    constexpr int CS = RT * LP;
-    size_t smem = (192 * CS + 24 * 4) * sizeof(float);
-    if (MODE >= ATT_BWD_STATS) smem += (64 * CS + 8 * 4) * sizeof(float);
-    if (MODE == ATT_BWD) smem += (size_t)2 * RT * 8 * L * LP * sizeof(float);
-    auto kern = attn_kernel<L, LP, RT, WIDTH, MODE>;
+    constexpr int CS = RT * LP, GC = GH * 8;
+    size_t smem = (3 * GC * CS + 3 * GH * 4) * sizeof(float);
+    if (MODE >= ATT_BWD_STATS) smem += (GC * CS + GH * 4) * sizeof(float);
+    if (MODE == ATT_BWD) smem += (size_t)2 * RT * GH * L * LP * sizeof(float);
+    if (smem < (size_t)RT * GH * L * sizeof(float2)) smem = (size_t)RT * GH * L * sizeof(float2);      // statistics passes reuse the tile
+    auto kern = attn_kernel<L, LP, RT, GH, WIDTH, MODE>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -330,19 +342,27 @@ cudaError_t launch_attn(const AttnP& p, cudaStream_t st)
         configured = true;
     }
     const int nrows = WIDTH ? 15 * p.B : p.N;
-    kern<<<(nrows + RT - 1) / RT, RT * 8 * L, smem, st>>>(p);
+    kern<<<dim3((nrows + RT - 1) / RT, 8 / GH), RT * GH * L, smem, st>>>(p);
     return cudaGetLastError();
 }
 
+// CTA shapes (measured, B = 1024): the backward main pass needs ~128 registers per thread, so it runs as narrow CTAs of which two or
+// three fit an SM and whose load / compute / store phases interleave; WF_ATTN_CFG=<w><h> (digits) selects other shapes for A/B runs:
+// width 0 = 2 rows x 8 groups, 1 = 1 row x 8 groups, 2 = 1 row x 4 groups; height 0 = 8 groups, 1 = 4 groups, 2 = 2 groups.
 template <int MODE>
 cudaError_t launch_attn_mode(const AttnP& p, cudaStream_t st)
 {
-    // backward main pass of the width axis: one row per CTA (160 threads, three CTAs per SM whose staging / compute / store phases
-    // interleave) instead of two rows in one 320-thread CTA per SM
-    static const bool rt1 = [] { const char* e = std::getenv("WF_ATTN_BWD_RT1"); return !(e && e[0] == '0'); }();
-    if (p.width && MODE == ATT_BWD && rt1) return launch_attn<20, 20, 1, true, MODE>(p, st);
-    if (p.width) return launch_attn<20, 20, 2, true, MODE>(p, st);
-    return launch_attn<15, 16, 4, false, MODE>(p, st);
+    static const int cfg = [] { const char* e = std::getenv("WF_ATTN_CFG"); return e ? std::atoi(e) : -1; }();
+    const int wdef = MODE == ATT_BWD ? 1 : 0, hdef = MODE == ATT_BWD ? 1 : 0;
+    const int w = cfg >= 0 ? cfg / 10 : wdef, h = cfg >= 0 ? cfg % 10 : hdef;
+    if (p.width) {
+        if (w == 2) return launch_attn<20, 20, 1, 4, true, MODE>(p, st);
+        if (w == 1) return launch_attn<20, 20, 1, 8, true, MODE>(p, st);
+        return launch_attn<20, 20, 2, 8, true, MODE>(p, st);
+    }
+    if (h == 2) return launch_attn<15, 16, 4, 2, false, MODE>(p, st);
+    if (h == 1) return launch_attn<15, 16, 4, 4, false, MODE>(p, st);
+    return launch_attn<15, 16, 4, 8, false, MODE>(p, st);
 }
 
 }  // namespace

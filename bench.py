@@ -169,8 +169,19 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     pg = None
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-        pg = dist.group.WORLD
+        # NCCL prints its version banner on fd 1 when the first communicator comes up: keep stdout to the one JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            pg = dist.group.WORLD
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     B = args.batch
     torch.manual_seed(0)
     model = wf.WiFlowPoseModel(dropout=0.5).to(dev)

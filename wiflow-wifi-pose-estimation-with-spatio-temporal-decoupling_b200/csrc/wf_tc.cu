@@ -364,22 +364,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const WgradP p
             const float* gp2 = p.g2 + col;
             const float* xp = p.in + pos * p.in_sp + b * p.in_sb + t;
             const float* mp = p.mask + b * p.m_sb + (long long)t * m_st;
-            float4 v[MAXG];
+            // Unit j of a warp is row group (warp>>1) + 8j: j < GUNITS are G' rows, the rest X' rows -- a compile-time split.  All loads
+            // of the chunk are issued first, as bare predicated loads with no arithmetic inside the guards, so that ptxas keeps up to
+            // 2*MAXG 128-bit requests per thread in flight; the prologues run afterwards.  (With the math inside the guards every unit
+            // waited for its own loads in turn: long-scoreboard stalls were 11.6 per issued instruction and the tensor pipe 9 % busy.)
+            constexpr int GUNITS = (BM / 8) / (NPW / 2);
+            static_assert((BM / 8) % (NPW / 2) == 0, "G' row groups must fill whole units");
+            float4 v[MAXG], w[MAXG];
 #pragma unroll
             for (int j = 0; j < MAXG; ++j) {
-                const int grp = (warp >> 1) + j * (NPW / 2);
-                v[j] = f4zero();
-                if (colv && ((valid >> j) & 1u)) {
-                    if (grp < BM / 8) {
-                        v[j] = ld4(gp + rowoff[j]);
-                        if (GPRO == PRO_BNBWD) v[j] = pro4<PRO_BNBWD, false>(v[j], ld4(gp2 + rowoff[j]), ca[j], cb[j], cc[j], cd[j]);
-                    } else {
-                        v[j] = ld4(xp + rowoff[j]);
-                        float4 mk = f4zero();
-                        if (MASK) { if (m_st == 1) mk = ld4(mp + moff[j]); else { const float mm = mp[moff[j]]; mk = make_float4(mm, mm, mm, mm); } }
-                        v[j] = pro4<XPRO, MASK>(v[j], mk, ca[j], cb[j], 0.f, cd[j]);
+                const bool ok = colv && ((valid >> j) & 1u);
+                v[j] = f4zero(); w[j] = f4zero();
+                if (j < GUNITS) {
+                    if (ok) v[j] = ld4(gp + rowoff[j]);
+                    if (GPRO == PRO_BNBWD) { if (ok) w[j] = ld4(gp2 + rowoff[j]); }
+                } else {
+                    if (ok) v[j] = ld4(xp + rowoff[j]);
+                    if (MASK) {
+                        if (m_st == 1) { if (ok) w[j] = ld4(mp + moff[j]); }
+                        else { float mm = 0.f; if (ok) mm = mp[moff[j]]; w[j] = make_float4(mm, mm, mm, mm); }
                     }
                 }
+            }
+#pragma unroll
+            for (int j = 0; j < MAXG; ++j) {
+                const bool ok = colv && ((valid >> j) & 1u);
+                float4 r;
+                if (j < GUNITS) r = (GPRO == PRO_BNBWD) ? pro4<PRO_BNBWD, false>(v[j], w[j], ca[j], cb[j], cc[j], cd[j]) : v[j];
+                else r = pro4<XPRO, MASK>(v[j], w[j], ca[j], cb[j], 0.f, cd[j]);
+                v[j] = sel4(ok, r, f4zero());
             }
             mbar_wait(empty(s), ph ^ 1u);
             uint8_t* ah = smem + s * WG_STAGE_BYTES;

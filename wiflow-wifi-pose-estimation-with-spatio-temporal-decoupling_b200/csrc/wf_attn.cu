@@ -52,57 +52,66 @@ __global__ void __launch_bounds__(RT * GH * L, attn_min_blocks(RT * GH * L, MODE
     };
 
     // ------------------------------- stage tiles -------------------------------
-    if (WIDTH) {
-        constexpr int Q = L / 4;
-        for (int idx = tid; idx < 3 * GC * RT * Q; idx += NT) {
-            const int q = idx % Q, r = (idx / Q) % RT, c = idx / (Q * RT), cg = qkv_chan(c);
-            float4 v = f4zero();
-            if (row0 + r < nrows) {
-                v = ld4(p.qkv_raw + cg * cstride + row_base(r) + q * 4);
+    // Every global load of the tile is issued before the first transform (the loops are fully unrolled and the guards hold nothing but
+    // the load), so a thread has up to NIT + 2*GIT 128-bit requests in flight instead of one load -> use -> store chain per item.
+    constexpr int Q = L / 4;                                        // width axis: column quads per row
+    constexpr int ITEMS = WIDTH ? 3 * GC * RT * Q : 3 * GC * LP;
+    constexpr int GITEMS = WIDTH ? GC * RT * Q : GC * LP;
+    constexpr int NIT = (ITEMS + NT - 1) / NT, GIT = MODE >= ATT_BWD_STATS ? (GITEMS + NT - 1) / NT : 0;
+    static_assert(WIDTH || RT == 4, "height-axis tiles are 4 consecutive n wide");
+    float4 tv[NIT], gd[GIT > 0 ? GIT : 1], gw[GIT > 0 ? GIT : 1];
+    // item -> (tile channel, row / slot, quad) and its global offset without the channel term; valid = inside the tensor
+    auto t_item = [&](int idx, int& c, int& r, int& s, long long& off) -> bool {
+        if (WIDTH) { const int q = idx % Q; r = (idx / Q) % RT; c = idx / (Q * RT); s = q * 4; off = row_base(r) + s; return row0 + r < nrows; }
+        s = idx % LP; c = idx / LP; r = 0; off = (long long)s * N + row0; return s < L && row0 < nrows;
+    };
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int idx = tid + it * NT;
+        int c, r, s; long long off;
+        tv[it] = f4zero();
+        if (idx < ITEMS && t_item(idx, c, r, s, off)) tv[it] = ld4(p.qkv_raw + qkv_chan(c) * cstride + off);
+    }
+#pragma unroll
+    for (int it = 0; it < GIT; ++it) {
+        const int idx = tid + it * NT;
+        int c, r, s; long long off;
+        gd[it] = f4zero(); gw[it] = f4zero();
+        if (idx < GITEMS && t_item(idx, c, r, s, off)) {
+            gd[it] = ld4(p.dsv + (g0 * 8 + c) * cstride + off);
+            gw[it] = ld4(p.sv_raw + (g0 * 8 + c) * cstride + off);
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int idx = tid + it * NT;
+        if (idx < ITEMS) {
+            int c, r, s; long long off;
+            float4 v = tv[it];
+            if (t_item(idx, c, r, s, off)) {
+                const int cg = qkv_chan(c);
                 const float a = p.qkv_scale[cg], b = p.qkv_shift[cg], mu = p.qkv_mean[cg];
                 v.x = fmaf(a, v.x - mu, b); v.y = fmaf(a, v.y - mu, b); v.z = fmaf(a, v.z - mu, b); v.w = fmaf(a, v.w - mu, b);
             }
-            st4(&T[tix(c, r, q * 4)], v);
+            if (WIDTH) st4(&T[tix(c, r, s)], v);
+            else { T[tix(c, 0, s)] = v.x; T[tix(c, 1, s)] = v.y; T[tix(c, 2, s)] = v.z; T[tix(c, 3, s)] = v.w; }
         }
-        if (MODE >= ATT_BWD_STATS) {
-            for (int idx = tid; idx < GC * RT * Q; idx += NT) {
-                const int q = idx % Q, r = (idx / Q) % RT, c = idx / (Q * RT), cg = g0 * 8 + c;
-                float4 v = f4zero();
-                if (row0 + r < nrows) {
-                    const long long off = cg * cstride + row_base(r) + q * 4;
-                    const float4 d = ld4(p.dsv + off), w = ld4(p.sv_raw + off);
-                    const float a = p.sv_alpha[cg], b = p.sv_beta[cg], e = p.sv_delta[cg], mu = p.sv_mean[cg];
-                    v.x = fmaf(a, d.x, fmaf(b, w.x - mu, e)); v.y = fmaf(a, d.y, fmaf(b, w.y - mu, e));
-                    v.z = fmaf(a, d.z, fmaf(b, w.z - mu, e)); v.w = fmaf(a, d.w, fmaf(b, w.w - mu, e));
-                }
-                st4(&G[tix(c, r, q * 4)], v);
-            }
-        }
-    } else {
-        static_assert(WIDTH || RT == 4, "height-axis tiles are 4 consecutive n wide");
-        for (int idx = tid; idx < 3 * GC * LP; idx += NT) {
-            const int s = idx % LP, c = idx / LP, cg = qkv_chan(c);
+    }
+#pragma unroll
+    for (int it = 0; it < GIT; ++it) {
+        const int idx = tid + it * NT;
+        if (idx < GITEMS) {
+            int c, r, s; long long off;
             float4 v = f4zero();
-            if (s < L && row0 < nrows) {
-                v = ld4(p.qkv_raw + cg * cstride + (long long)s * N + row0);
-                const float a = p.qkv_scale[cg], b = p.qkv_shift[cg], mu = p.qkv_mean[cg];
-                v.x = fmaf(a, v.x - mu, b); v.y = fmaf(a, v.y - mu, b); v.z = fmaf(a, v.z - mu, b); v.w = fmaf(a, v.w - mu, b);
+            if (t_item(idx, c, r, s, off)) {
+                const int cg = g0 * 8 + c;
+                const float4 d = gd[it], w = gw[it];
+                const float a = p.sv_alpha[cg], b = p.sv_beta[cg], e = p.sv_delta[cg], mu = p.sv_mean[cg];
+                v.x = fmaf(a, d.x, fmaf(b, w.x - mu, e)); v.y = fmaf(a, d.y, fmaf(b, w.y - mu, e));
+                v.z = fmaf(a, d.z, fmaf(b, w.z - mu, e)); v.w = fmaf(a, d.w, fmaf(b, w.w - mu, e));
             }
-            T[tix(c, 0, s)] = v.x; T[tix(c, 1, s)] = v.y; T[tix(c, 2, s)] = v.z; T[tix(c, 3, s)] = v.w;
-        }
-        if (MODE >= ATT_BWD_STATS) {
-            for (int idx = tid; idx < GC * LP; idx += NT) {
-                const int s = idx % LP, c = idx / LP, cg = g0 * 8 + c;
-                float4 v = f4zero();
-                if (s < L && row0 < nrows) {
-                    const long long off = cg * cstride + (long long)s * N + row0;
-                    const float4 d = ld4(p.dsv + off), w = ld4(p.sv_raw + off);
-                    const float a = p.sv_alpha[cg], b = p.sv_beta[cg], e = p.sv_delta[cg], mu = p.sv_mean[cg];
-                    v.x = fmaf(a, d.x, fmaf(b, w.x - mu, e)); v.y = fmaf(a, d.y, fmaf(b, w.y - mu, e));
-                    v.z = fmaf(a, d.z, fmaf(b, w.z - mu, e)); v.w = fmaf(a, d.w, fmaf(b, w.w - mu, e));
-                }
-                G[tix(c, 0, s)] = v.x; G[tix(c, 1, s)] = v.y; G[tix(c, 2, s)] = v.z; G[tix(c, 3, s)] = v.w;
-            }
+            if (WIDTH) st4(&G[tix(c, r, s)], v);
+            else { G[tix(c, 0, s)] = v.x; G[tix(c, 1, s)] = v.y; G[tix(c, 2, s)] = v.z; G[tix(c, 3, s)] = v.w; }
         }
     }
     __syncthreads();

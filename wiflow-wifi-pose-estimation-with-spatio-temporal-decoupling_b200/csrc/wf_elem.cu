@@ -77,41 +77,74 @@ __global__ void bn_eval_coefs_kernel(BnEvalTable tab, const float* params, const
 // Residual joins.  TCN: silu(mask*silu(bn(pw2)) + res) (models/tcn.py:74), conv blocks: silu(bn(c3) + bn(ds))
 // (models/convnet.py:36-37,72-73).  One channel per blockIdx.y, float4 over the [P][N] plane.
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void join_eval(const JoinP& p, int c, long long i, int N, float4& a4, float4& r4,
-                                          float ya[4], float av[4], float mk[4], float z[4])
+// Per-channel state of a join CTA: the coefficients are read once, element offsets are 32-bit (a plane is at most 240 x 20 480
+// elements), and the loads of an iteration are separated from its arithmetic so that two float4 groups are in flight per thread.
+struct JoinCh {
+    const float *a, *r, *mask;
+    float as, at, am, rs, rt, rm;
+    unsigned N, r_sp, r_sb, m_sb, m_st;
+    bool silu, masked;
+};
+__device__ __forceinline__ JoinCh join_channel(const JoinP& p, int c)
 {
-    const int n = (int)(i % N);
-    const int pos = (int)(i / N);
-    const int b = n / WF_T, t = n % WF_T;
-    a4 = ld4(p.a + (long long)c * p.plane + i);
-    r4 = ld4(p.r + (long long)c * p.r_sc + (long long)pos * p.r_sp + (long long)b * p.r_sb + t);
-    const float as = p.a_scale[c], at = p.a_shift[c], am = p.a_mean[c];
-    const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-    const float r[4] = {r4.x, r4.y, r4.z, r4.w};
-    mk[0] = mk[1] = mk[2] = mk[3] = 1.f;
-    if (p.a_mode == PRO_BNSILU && p.mask) {
-        const float* mp = p.mask + (long long)b * p.m_sb + (long long)c * p.m_sc + (long long)t * p.m_st;
-        if (p.m_st == 1) { float4 m4 = ld4(mp); mk[0] = m4.x; mk[1] = m4.y; mk[2] = m4.z; mk[3] = m4.w; }
-        else { mk[0] = mk[1] = mk[2] = mk[3] = *mp; }
+    JoinCh k;
+    k.a = p.a + (long long)c * p.plane;
+    k.r = p.r + (long long)c * p.r_sc;
+    k.silu = p.a_mode == PRO_BNSILU;
+    k.masked = k.silu && p.mask != nullptr;
+    k.mask = k.masked ? p.mask + (long long)c * p.m_sc : nullptr;
+    k.as = p.a_scale[c]; k.at = p.a_shift[c]; k.am = p.a_mean[c];
+    k.rs = 1.f; k.rt = 0.f; k.rm = 0.f;
+    if (p.r_mode == PRO_AFFINE) { k.rs = p.r_scale[c]; k.rt = p.r_shift[c]; k.rm = p.r_mean[c]; }
+    k.N = (unsigned)p.N; k.r_sp = (unsigned)p.r_sp; k.r_sb = (unsigned)p.r_sb; k.m_sb = (unsigned)p.m_sb; k.m_st = (unsigned)p.m_st;
+    return k;
+}
+struct JoinLd { float4 a4, r4, m4; };
+__device__ __forceinline__ void join_load(const JoinCh& k, unsigned i, JoinLd& l)
+{
+    const unsigned pos = i / k.N, n = i - pos * k.N;
+    const unsigned b = n / WF_T, t = n - b * WF_T;
+    l.a4 = ld4(k.a + i);
+    l.r4 = ld4(k.r + (pos * k.r_sp + b * k.r_sb + t));
+    l.m4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (k.masked) {
+        const float* mp = k.mask + (b * k.m_sb + t * k.m_st);
+        if (k.m_st == 1) l.m4 = ld4(mp); else { const float m = *mp; l.m4 = make_float4(m, m, m, m); }
     }
-    float rs = 1.f, rt = 0.f, rm = 0.f;
-    if (p.r_mode == PRO_AFFINE) { rs = p.r_scale[c]; rt = p.r_shift[c]; rm = p.r_mean[c]; }
+}
+__device__ __forceinline__ void join_math(const JoinCh& k, const JoinLd& l, float ya[4], float mk[4], float z[4])
+{
+    const float a[4] = {l.a4.x, l.a4.y, l.a4.z, l.a4.w};
+    const float r[4] = {l.r4.x, l.r4.y, l.r4.z, l.r4.w};
+    mk[0] = l.m4.x; mk[1] = l.m4.y; mk[2] = l.m4.z; mk[3] = l.m4.w;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        ya[j] = fmaf(as, a[j] - am, at);
-        av[j] = (p.a_mode == PRO_BNSILU) ? mk[j] * wf_silu(ya[j]) : ya[j];
-        z[j] = av[j] + fmaf(rs, r[j] - rm, rt);
+        ya[j] = fmaf(k.as, a[j] - k.am, k.at);
+        const float av = k.silu ? mk[j] * wf_silu(ya[j]) : ya[j];
+        z[j] = av + fmaf(k.rs, r[j] - k.rm, k.rt);
     }
 }
 
-__global__ void join_fwd_kernel(JoinP p)
+constexpr int JOIN_UNR = 2;
+
+__global__ void __launch_bounds__(256) join_fwd_kernel(JoinP p)
 {
     const int c = blockIdx.y;
-    const long long total4 = p.plane / 4;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += (long long)gridDim.x * blockDim.x) {
-        float4 a4, r4; float ya[4], av[4], mk[4], z[4];
-        join_eval(p, c, q * 4, p.N, a4, r4, ya, av, mk, z);
-        st4(p.out + (long long)c * p.plane + q * 4, make_float4(wf_silu(z[0]), wf_silu(z[1]), wf_silu(z[2]), wf_silu(z[3])));
+    const JoinCh k = join_channel(p, c);
+    const unsigned total4 = (unsigned)(p.plane / 4), stride = gridDim.x * blockDim.x;
+    float* out = p.out + (long long)c * p.plane;
+    for (unsigned q0 = blockIdx.x * blockDim.x + threadIdx.x; q0 < total4; q0 += JOIN_UNR * stride) {
+        JoinLd l[JOIN_UNR];
+#pragma unroll
+        for (int u = 0; u < JOIN_UNR; ++u) if (q0 + u * stride < total4) join_load(k, (q0 + u * stride) * 4, l[u]);
+#pragma unroll
+        for (int u = 0; u < JOIN_UNR; ++u) {
+            if (q0 + u * stride < total4) {
+                float ya[4], mk[4], z[4];
+                join_math(k, l[u], ya, mk, z);
+                st4(out + (q0 + u * stride) * 4, make_float4(wf_silu(z[0]), wf_silu(z[1]), wf_silu(z[2]), wf_silu(z[3])));
+            }
+        }
     }
 }
 
@@ -121,26 +154,39 @@ template <int NT>
 __global__ void __launch_bounds__(NT) join_bwd_kernel(JoinP p)
 {
     const int c = blockIdx.y;
-    const long long total4 = p.plane / 4;
+    const JoinCh k = join_channel(p, c);
+    const unsigned total4 = (unsigned)(p.plane / 4), stride = gridDim.x * NT;
     float sa0 = 0.f, sa1 = 0.f, sr0 = 0.f, sr1 = 0.f;
-    const float am = p.a_mean[c], rm = p.r_mean ? p.r_mean[c] : 0.f;
-    for (long long q = (long long)blockIdx.x * NT + threadIdx.x; q < total4; q += (long long)gridDim.x * NT) {
-        float4 a4, r4; float ya[4], av[4], mk[4], z[4];
-        join_eval(p, c, q * 4, p.N, a4, r4, ya, av, mk, z);
-        const float4 g4 = ld4(p.dout + (long long)c * p.plane + q * 4);
-        const float g[4] = {g4.x, g4.y, g4.z, g4.w};
-        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-        const float r[4] = {r4.x, r4.y, r4.z, r4.w};
-        float dz[4], da[4];
+    const float rmean = p.r_mean ? p.r_mean[c] : 0.f;       // centre of the shortcut's BatchNorm-backward sum (also when r enters unscaled)
+    const float* dout = p.dout + (long long)c * p.plane;
+    float* dzp = p.dz + (long long)c * p.plane;
+    float* dap = p.da ? p.da + (long long)c * p.plane : nullptr;
+    for (unsigned q0 = blockIdx.x * NT + threadIdx.x; q0 < total4; q0 += JOIN_UNR * stride) {
+        JoinLd l[JOIN_UNR];
+        float4 g4[JOIN_UNR];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            dz[j] = g[j] * wf_dsilu(z[j]);
-            da[j] = (p.a_mode == PRO_BNSILU) ? dz[j] * mk[j] * wf_dsilu(ya[j]) : dz[j];
-            sa0 += da[j]; sa1 = fmaf(da[j], a[j] - am, sa1);
-            sr0 += dz[j]; sr1 = fmaf(dz[j], r[j] - rm, sr1);
+        for (int u = 0; u < JOIN_UNR; ++u)
+            if (q0 + u * stride < total4) { join_load(k, (q0 + u * stride) * 4, l[u]); g4[u] = ld4(dout + (q0 + u * stride) * 4); }
+#pragma unroll
+        for (int u = 0; u < JOIN_UNR; ++u) {
+            if (q0 + u * stride < total4) {
+                float ya[4], mk[4], z[4];
+                join_math(k, l[u], ya, mk, z);
+                const float g[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
+                const float a[4] = {l[u].a4.x, l[u].a4.y, l[u].a4.z, l[u].a4.w};
+                const float r[4] = {l[u].r4.x, l[u].r4.y, l[u].r4.z, l[u].r4.w};
+                float dz[4], da[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    dz[j] = g[j] * wf_dsilu(z[j]);
+                    da[j] = k.silu ? dz[j] * mk[j] * wf_dsilu(ya[j]) : dz[j];
+                    sa0 += da[j]; sa1 = fmaf(da[j], a[j] - k.am, sa1);
+                    sr0 += dz[j]; sr1 = fmaf(dz[j], r[j] - rmean, sr1);
+                }
+                st4(dzp + (q0 + u * stride) * 4, make_float4(dz[0], dz[1], dz[2], dz[3]));
+                if (dap) st4(dap + (q0 + u * stride) * 4, make_float4(da[0], da[1], da[2], da[3]));
+            }
         }
-        st4(p.dz + (long long)c * p.plane + q * 4, make_float4(dz[0], dz[1], dz[2], dz[3]));
-        if (p.da) st4(p.da + (long long)c * p.plane + q * 4, make_float4(da[0], da[1], da[2], da[3]));
     }
     block_accum2<NT>(sa0, sa1, p.a_stat0 + c, p.a_stat1 + c);
     if (p.r_stat0) block_accum2<NT>(sr0, sr1, p.r_stat0 + c, p.r_stat1 + c);

@@ -124,39 +124,61 @@ struct TileSrc {
     const float* mask; long long m_sb, m_sc; int m_st;
     int C, P;
 };
-template <int NT>
+template <int NT, int U = 1>                                // U = items in flight per thread: their loads are issued before any transform
 __device__ __forceinline__ void wf_stage_tile(const TileSrc& s, float* sm, int crows, int pos_lo, int npos, int n0, int N, int tid, int nthreads)
 {
     constexpr int Q = NT / 4;
     const int items = crows * npos * Q;
-    for (int idx = tid; idx < items; idx += nthreads) {
-        const int q = idx % Q, r = (idx / Q) % npos, c = idx / (Q * npos);
-        const int pos = pos_lo + r, n = n0 + q * 4;
-        float4 v = f4zero();
-        if (c < s.C && pos >= 0 && pos < s.P && n < N) {
-            const int b = n / WF_T, t = n % WF_T;
-            const long long off = (long long)c * s.sc + (long long)pos * s.sp + (long long)b * s.sb + t;
-            v = ld4(s.p + off);
-            if (s.mode == PRO_BNSILU) {
-                const float ca = s.a[c], cb = s.b[c], cm = s.d[c];
-                float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (s.mask) {
-                    const float* mp = s.mask + (long long)b * s.m_sb + (long long)c * s.m_sc + (long long)t * s.m_st;
-                    if (s.m_st == 1) m = ld4(mp); else { float mm = *mp; m = make_float4(mm, mm, mm, mm); }
+    for (int base = tid; base < items; base += U * nthreads) {
+        float4 v[U], w[U];
+        long long moff[U];
+        int cc[U], dst[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int idx = base + u * nthreads;
+            v[u] = f4zero(); w[u] = f4zero(); ok[u] = false; cc[u] = 0; dst[u] = -1; moff[u] = -1;
+            if (idx < items) {
+                const int q = idx % Q, r = (idx / Q) % npos, c = idx / (Q * npos);
+                const int pos = pos_lo + r, n = n0 + q * 4;
+                cc[u] = c;
+                dst[u] = (c * npos + r) * NT + q * 4;
+                if (c < s.C && pos >= 0 && pos < s.P && n < N) {
+                    ok[u] = true;
+                    const int b = n / WF_T, t = n % WF_T;
+                    const long long off = (long long)c * s.sc + (long long)pos * s.sp + (long long)b * s.sb + t;
+                    v[u] = ld4(s.p + off);
+                    if (s.mode == PRO_BNBWD) w[u] = ld4(s.p2 + off);
+                    else if (s.mode == PRO_BNSILU && s.mask) {
+                        const float* mp = s.mask + (long long)b * s.m_sb + (long long)c * s.m_sc + (long long)t * s.m_st;
+                        if (s.m_st == 1) w[u] = ld4(mp); else { const float mm = *mp; w[u] = make_float4(mm, mm, mm, mm); }
+                    } else w[u] = make_float4(1.f, 1.f, 1.f, 1.f);
                 }
-                v.x = wf_silu(fmaf(ca, v.x - cm, cb)) * m.x; v.y = wf_silu(fmaf(ca, v.y - cm, cb)) * m.y;
-                v.z = wf_silu(fmaf(ca, v.z - cm, cb)) * m.z; v.w = wf_silu(fmaf(ca, v.w - cm, cb)) * m.w;
-            } else if (s.mode == PRO_AFFINE) {
-                const float ca = s.a[c], cb = s.b[c], cm = s.d[c];
-                v.x = fmaf(ca, v.x - cm, cb); v.y = fmaf(ca, v.y - cm, cb); v.z = fmaf(ca, v.z - cm, cb); v.w = fmaf(ca, v.w - cm, cb);
-            } else if (s.mode == PRO_BNBWD) {
-                const float4 w = ld4(s.p2 + off);
-                const float ca = s.a[c], cb = s.b[c], cc = s.c[c], cd = s.d[c];
-                v.x = fmaf(ca, v.x, fmaf(cb, w.x - cd, cc)); v.y = fmaf(ca, v.y, fmaf(cb, w.y - cd, cc));
-                v.z = fmaf(ca, v.z, fmaf(cb, w.z - cd, cc)); v.w = fmaf(ca, v.w, fmaf(cb, w.w - cd, cc));
             }
         }
-        st4(sm + ((long long)(c * npos + r) * NT + q * 4), v);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (dst[u] < 0) continue;
+            float4 x = v[u];
+            if (ok[u]) {
+                const int c = cc[u];
+                if (s.mode == PRO_BNSILU) {
+                    const float ca = s.a[c], cb = s.b[c], cm = s.d[c];
+                    const float4 m = w[u];
+                    x.x = wf_silu(fmaf(ca, x.x - cm, cb)) * m.x; x.y = wf_silu(fmaf(ca, x.y - cm, cb)) * m.y;
+                    x.z = wf_silu(fmaf(ca, x.z - cm, cb)) * m.z; x.w = wf_silu(fmaf(ca, x.w - cm, cb)) * m.w;
+                } else if (s.mode == PRO_AFFINE) {
+                    const float ca = s.a[c], cb = s.b[c], cm = s.d[c];
+                    x.x = fmaf(ca, x.x - cm, cb); x.y = fmaf(ca, x.y - cm, cb); x.z = fmaf(ca, x.z - cm, cb); x.w = fmaf(ca, x.w - cm, cb);
+                } else if (s.mode == PRO_BNBWD) {
+                    const float4 r = w[u];
+                    const float ca = s.a[c], cb = s.b[c], ccf = s.c[c], cd = s.d[c];
+                    x.x = fmaf(ca, x.x, fmaf(cb, r.x - cd, ccf)); x.y = fmaf(ca, x.y, fmaf(cb, r.y - cd, ccf));
+                    x.z = fmaf(ca, x.z, fmaf(cb, r.z - cd, ccf)); x.w = fmaf(ca, x.w, fmaf(cb, r.w - cd, ccf));
+                }
+            }
+            st4(sm + dst[u], x);
+        }
     }
 }
 

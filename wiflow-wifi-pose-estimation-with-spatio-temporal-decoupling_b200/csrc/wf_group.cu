@@ -8,6 +8,7 @@
 // on the warp-level tensor-core path (mma.sync m16n8k8 tf32, fp32 accumulate, 3xTF32 split: a_lo*b_hi + a_hi*b_lo in a
 // correction accumulator, a_hi*b_hi in the main one).  No barrier inside the K loop.  The epilogue pairs lanes so every
 // thread owns 4 consecutive columns of one output row and reuses wf_epilogue_quad (BatchNorm sums, SiLU', dropout mask).
+#include <cstdlib>
 #include "wf_common.cuh"
 #include "wf_elem.h"
 
@@ -407,25 +408,23 @@ __global__ void __launch_bounds__(G_NT, 1) group_wgrad_kernel(const WgradP p, lo
         t0 = t0 + (GW_KCH % WF_T) >= WF_T ? t0 + (GW_KCH % WF_T) - WF_T : t0 + (GW_KCH % WF_T);
     }
 
-    // reduce the 8 warps' partial sums through shared memory (stage buffers are free now), then one atomic per weight
+    // the 8 warps' partial sums meet in shared memory (stage buffers are free now) through shared-memory reductions -- all warps at
+    // once instead of eight barrier-separated turns --, then one global reduction per weight per CTA
     float* red = smem;                                               // [3][32][32]
-    for (int w = 0; w < 8; ++w) {
-        if (warp == w) {
+    for (int idx = tid; idx < 3 * 32 * 32; idx += G_NT) red[idx] = 0.f;
+    __syncthreads();
 #pragma unroll
-            for (int tap = 0; tap < 3; ++tap)
+    for (int tap = 0; tap < 3; ++tap)
 #pragma unroll
-                for (int mi = 0; mi < 2; ++mi)
+        for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                    for (int ni = 0; ni < 4; ++ni)
+            for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int co = mi * 16 + fr + (e >= 2 ? 8 : 0), ci = ni * 8 + fc * 2 + (e & 1);
-                            float* dst = red + (tap * 32 + co) * 32 + ci;
-                            *dst = (w == 0 ? 0.f : *dst) + acc[tap][mi][ni][e];
-                        }
-        }
-        __syncthreads();
-    }
+                for (int e = 0; e < 4; ++e) {
+                    const int co = mi * 16 + fr + (e >= 2 ? 8 : 0), ci = ni * 8 + fc * 2 + (e & 1);
+                    if (co < p.Cout && ci < p.Cin) atomicAdd(red + (tap * 32 + co) * 32 + ci, acc[tap][mi][ni][e]);
+                }
+    __syncthreads();
     // the group's weights are one contiguous block of dW ([co][ci][tap]): consecutive threads reduce into consecutive addresses
     {
         const int per_co = p.Cin * p.ntaps, total = p.Cout * per_co;
@@ -457,7 +456,8 @@ cudaError_t wf_launch_group_wgrad(const WgradP& p, int num_sms, cudaStream_t st)
         if (e != cudaSuccess) return e;
         cfg = true;
     }
-    long long splits = (2LL * num_sms) / p.groups;                       // two rounds of one-CTA-per-SM
+    static const int rounds = [] { const char* e = std::getenv("WF_GROUP_WGRAD_ROUNDS"); const int v = e ? std::atoi(e) : 0; return v > 0 ? v : 1; }();
+    long long splits = ((long long)rounds * num_sms) / p.groups;         // one round of one-CTA-per-SM (measured: every extra round costs 14 us per launch in prime + reduction)
     const long long max_splits = (p.N + 8LL * GW_KCH - 1) / (8LL * GW_KCH);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;

@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(384, 2) thin_wgrad_kernel(const WgradP p, int 
         const int p0 = (reg / ntile_n) * PC;
         const int xlo = p0 * p.pmul + dmin;
         __syncthreads();                                 // previous region fully consumed
-        wf_stage_tile<NT>(gs, gt, coutp, p0, PC, n0, p.N, tid, nthreads);
+        wf_stage_tile<NT, 4>(gs, gt, coutp, p0, PC, n0, p.N, tid, nthreads);     // 2-3 items per thread: one round trip instead of three
         wf_stage_tile<NT>(xs, xt, CINP, xlo, xpos_max, n0, p.N, tid, nthreads);
         __syncthreads();
         for (int pl = ps; pl < PC; pl += PS) {

@@ -356,22 +356,27 @@ def run_ours(args, rank, world, local_rank):
             nwin = 8192
             resident = torch.randn(nwin, 540, 20, device=dev)
             gidx = [torch.randint(0, nwin, (B,), device=dev) for _ in range(8)]
-            noise = torch.randn(B, 540, 20, device=dev)
-            gout = torch.empty(B, 540, 20, device=dev)
+            # every buffer rotates over 4 copies (177 MB each of noise and output on top of the 354 MB source), so that no launch
+            # finds its operands in the 126 MB L2
+            noises = [torch.randn(B, 540, 20, device=dev) for _ in range(4)]
+            gouts = [torch.empty(B, 540, 20, device=dev) for _ in range(4)]
+            for gbuf in gouts:
+                gbuf.normal_()
             stats = torch.zeros(2, device=dev, dtype=torch.float64)
             spans_h = A.draw_time_masks(B, 540, 0.3)
             spans_d = A._spans_to_device(spans_h, dev)
             wbytes = B * 43200
             inp = {}
             for name, fn, nbytes in (
-                    ('gather', lambda i: ops.window_load(resident, gidx[i % 8], gout), 2 * wbytes),
-                    ('gather_mask_stats', lambda i: ops.window_load(resident, gidx[i % 8], gout, spans_d, stats), 2 * wbytes),
-                    ('noise_scale', lambda i: ops.noise_scale(gout, noise, 0.02, 1.05, stats, gout), 3 * wbytes)):
+                    ('gather', lambda i: ops.window_load(resident, gidx[i % 8], gouts[i % 4]), 2 * wbytes),
+                    ('gather_mask_stats', lambda i: ops.window_load(resident, gidx[i % 8], gouts[i % 4], spans_d, stats), 2 * wbytes),
+                    ('noise_scale', lambda i: ops.noise_scale(gouts[i % 4], noises[(i + 1) % 4], 0.02, 1.0001, stats, gouts[i % 4]), 3 * wbytes)):
                 for i in range(3):
                     fn(i)
-                msk = timed_loop(fn, 50, dev) / 50
+                msk = timed_loop(fn, 48, dev) / 48
                 inp[name] = {'ms': msk, 'windows_per_s': B / (msk / 1e3), 'algorithmic_bytes': nbytes,
                              'achieved_gbs': nbytes / (msk / 1e3) / 1e9, 'frac_of_hbm_peak': nbytes / (msk / 1e3) / 1e9 / pk['hbm_gbs']}
+            noise = noises[0]
             xc = resident[:64].cpu()
             nc = noise[:64].cpu()
             torch.manual_seed(0)
@@ -385,7 +390,7 @@ def run_ours(args, rank, world, local_rank):
                            '(30 % of the windows) + sum/sumsq for add_noise; noise_scale = add_noise + random_scaling in place; '
                            'cpu port = oracle augment_step (the reference\'s Python loops) on 64 windows')
             also['input_side'] = inp
-            del resident, noise, gout
+            del resident, noise, noises, gouts
             line['also'] = also
             rate, n, dt, cores = cpu_train_step_rate(64, args.cpu_seconds, 2)
             line['cpu_baseline'] = {'value': rate, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',

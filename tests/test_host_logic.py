@@ -52,3 +52,21 @@ def test_scheduler_settings_match_reference():
         got.append(tr.lr)
     assert got[4] == lr and got[5] == lr / 2          # 4th bad epoch after the best one triggers the first halving
     assert min(got) == pytest.approx(lr / 1000)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the reference's CPU path on the host cores) needs no GPU: one JSON line with the contract's keys"""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline', 'dtype',
+                'data', 'config', 'impl', 'cpu_baseline', 'e2e'):
+        assert key in d, key
+    assert d['impl'] == 'reference' and d['value'] > 0 and d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e']['h2d_bytes_per_step'] == 0 and 'workload' in d['config']

@@ -71,6 +71,7 @@ class TrainStep:
         self.pred = None
         self.use_graph = use_cuda_graph
         self._graph_a = self._graph_b = None
+        self._copy_stream = None                             # host-input path (_upload): created on first use
         self.kernel_launches = 0
         self.micro = 0                                       # micro-batches accumulated since the last optimizer step
         self.acc = torch.zeros(n, device=dev) if self.k > 1 else None
@@ -173,6 +174,34 @@ class TrainStep:
         if self.micro > 0:
             self._apply()
 
+    def _upload(self, x, y):
+        """Host batch -> the step's input buffers through one of two device staging slots on a copy stream: the upload of batch i+1
+        is enqueued while step i still runs (the copy engine works next to the SMs), and the compute stream only pays a device-to-
+        device copy of 44 MB.  Pinned host tensors make the upload asynchronous; pageable ones work but serialise on the host."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+            self._xs = [torch.empty_like(self.x) for _ in range(2)]
+            self._ys = [torch.empty_like(self.y) for _ in range(2)]
+            self._slot_free = [None, None]
+            self._slot = 0
+        k = self._slot
+        self._slot ^= 1
+        cur = torch.cuda.current_stream(self.dev)
+        cs = self._copy_stream
+        if self._slot_free[k] is not None:
+            cs.wait_event(self._slot_free[k])            # the step that consumed this slot two calls ago has read it
+        with torch.cuda.stream(cs):
+            self._xs[k].copy_(x, non_blocking=True)
+            self._ys[k].copy_(y, non_blocking=True)
+            up = torch.cuda.Event()
+            up.record(cs)
+        cur.wait_event(up)
+        self.x.copy_(self._xs[k], non_blocking=True)
+        self.y.copy_(self._ys[k], non_blocking=True)
+        free = torch.cuda.Event()
+        free.record(cur)
+        self._slot_free[k] = free
+
     # -- public -----------------------------------------------------------------------------------------
     def step(self, x, y):
         """one micro-batch; every `accumulation_steps`-th call also runs the exchange + optimizer step"""
@@ -182,8 +211,11 @@ class TrainStep:
                 raise RuntimeError(f'batch of {B} windows exceeds the workspace sized for {self.B}')
             self._fwd_bwd_on(x.to(self.dev, non_blocking=True).contiguous(), y.to(self.dev, non_blocking=True).contiguous())
         else:
-            self.x.copy_(x, non_blocking=True)
-            self.y.copy_(y, non_blocking=True)
+            if x.is_cuda:
+                self.x.copy_(x, non_blocking=True)
+                self.y.copy_(y, non_blocking=True)
+            else:
+                self._upload(x, y)
             if self.use_graph:
                 if self._graph_a is None:
                     # the warm-up iterations inside _capture must not disturb the weights: they only run fwd/bwd

@@ -56,14 +56,28 @@ window_load_kernel(const float* src, const long long* __restrict__ idx, long lon
     if (spans) { m[0] = spans[b * 4]; m[1] = spans[b * 4 + 1]; m[2] = spans[b * 4 + 2]; m[3] = spans[b * 4 + 3]; }
     double s0 = 0, s1 = 0;
     if (m[1] <= 0 && m[3] <= 0) {
-        // plain gather: registers only
-        for (int q = tid; q < Q; q += DATA_THREADS) {
-            const float4 v = have ? sp[q] : f4zero();
-            if (static_cast<const float4*>(dp + q) != sp + q) dp[q] = v;     // in place and unmasked: nothing to write
-            if (stats) {
-                float a = (v.x + v.y) + (v.z + v.w);
-                float c2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
-                s0 += a; s1 += c2;
+        // plain gather: registers only, four 128-bit requests per thread in flight
+        constexpr int U = 4;
+        const bool inplace = static_cast<const float4*>(dp) == sp;           // in place and unmasked: nothing to write
+        for (int q0 = tid; q0 < Q; q0 += U * DATA_THREADS) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = q0 + u * DATA_THREADS;
+                v[u] = f4zero();
+                if (have && q < Q) v[u] = sp[q];
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = q0 + u * DATA_THREADS;
+                if (q < Q) {
+                    if (!inplace) dp[q] = v[u];
+                    if (stats) {
+                        float a = (v[u].x + v[u].y) + (v[u].z + v[u].w);
+                        float c2 = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, fmaf(v[u].z, v[u].z, v[u].w * v[u].w)));
+                        s0 += a; s1 += c2;
+                    }
+                }
             }
         }
         if (4 * Q + tid < W) {           // scalar tail (W not a multiple of 4: single-window calls only)
@@ -74,7 +88,13 @@ window_load_kernel(const float* src, const long long* __restrict__ idx, long lon
             if (stats) { s0 += v; s1 += v * v; }
         }
     } else {
-        for (int q = tid; q < Q; q += DATA_THREADS) win4[q] = have ? sp[q] : f4zero();
+        for (int q0 = tid; q0 < Q; q0 += 4 * DATA_THREADS) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int q = q0 + u * DATA_THREADS; v[u] = f4zero(); if (have && q < Q) v[u] = sp[q]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int q = q0 + u * DATA_THREADS; if (q < Q) win4[q] = v[u]; }
+        }
         if (4 * Q + tid < W) win[4 * Q + tid] = have ? reinterpret_cast<const float*>(sp)[4 * Q + tid] : 0.f;
         __syncthreads();
         const int warp = tid >> 5, lane = tid & 31;

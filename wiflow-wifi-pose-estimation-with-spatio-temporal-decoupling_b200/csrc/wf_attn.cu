@@ -25,6 +25,7 @@ constexpr int attn_min_blocks(int nt, int mode)
 template <int L, int LP, int RT, int GH, bool WIDTH, int MODE>
 __global__ void __launch_bounds__(RT * GH * L, attn_min_blocks(RT * GH * L, MODE)) attn_kernel(const AttnP p)
 {
+    wf_pdl_enter();
     constexpr int NT = RT * GH * L;
     constexpr int GC = GH * 8;                          // channels per section (q, k, v, d sv) in this CTA
     constexpr int CS = RT * LP;                         // channel stride inside a tile
@@ -351,7 +352,7 @@ cudaError_t launch_attn(const AttnP& p, cudaStream_t st)
         configured = true;
     }
     const int nrows = WIDTH ? 15 * p.B : p.N;
-    kern<<<dim3((nrows + RT - 1) / RT, 8 / GH), RT * GH * L, smem, st>>>(p);
+    wf_launch_pdl(kern, dim3(dim3((nrows + RT - 1) / RT, 8 / GH)), dim3(RT * GH * L), smem, st, p);
     return cudaGetLastError();
 }
 

@@ -79,6 +79,16 @@ __device__ __forceinline__ float wf_sigmoid(float x)
 __device__ __forceinline__ float wf_silu(float x) { return x * wf_sigmoid(x); }
 __device__ __forceinline__ float wf_dsilu(float x) { float s = wf_sigmoid(x); return s * (1.f + x * (1.f - s)); }
 
+// Programmatic dependent launch: every kernel of the model path starts with wf_pdl_enter() -- it lets the next kernel of the stream
+// begin launching (its CTAs take SM slots as ours retire and park at their own griddepcontrol.wait) and then waits until everything
+// the previous kernels wrote is visible.  Nothing may touch global memory before it.  Launched through wf_launch_pdl() below;
+// with the attribute off (WF_PDL=0) both instructions are no-ops.
+__device__ __forceinline__ void wf_pdl_enter()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
@@ -209,4 +219,23 @@ __device__ __forceinline__ void block_accum2(float a, float b, double* d0, doubl
         atomicAdd(d1, s1);
     }
     __syncthreads();
+}
+
+// ---- host side: launch with the programmatic-stream-serialisation attribute (CUDA-graph capturable) ----
+#include <cstdlib>
+inline bool wf_pdl_enabled()
+{
+    static const bool on = [] { const char* e = std::getenv("WF_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t wf_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = wf_pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }

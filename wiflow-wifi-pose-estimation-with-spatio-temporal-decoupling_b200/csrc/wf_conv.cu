@@ -25,6 +25,7 @@ template <int BM, int BN, int BK, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 conv_gemm_kernel(const ConvP p)
 {
+    wf_pdl_enter();
     constexpr int NTX = BN / TN, NTY = BM / TM, NT = NTX * NTY;
     constexpr int QPR = BN / 4;                        // column quads per B-tile row
     static_assert(NT % QPR == 0, "thread count must be a multiple of the quads per row");
@@ -266,6 +267,7 @@ template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 conv_wgrad_kernel(const WgradP p)
 {
+    wf_pdl_enter();
     constexpr int BK = 8;
     constexpr int NTX = BN / TN, NTY = BM / TM, NT = NTX * NTY;
     constexpr int A_ITEMS = BM * 2, B_ITEMS = BN * 2;           // float4 items per stage (2 quads per row)
@@ -458,7 +460,7 @@ template <int BM, int BN, int BK, int TM, int TN>
 static cudaError_t launch_conv_t(const ConvP& p, cudaStream_t st)
 {
     dim3 grid((p.N + BN - 1) / BN, p.Pout * (p.Mpad / BM), p.groups);
-    conv_gemm_kernel<BM, BN, BK, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, st>>>(p);
+    wf_launch_pdl(conv_gemm_kernel<BM, BN, BK, TM, TN>, dim3(grid), dim3((BM / TM) * (BN / TN)), 0, st, p);
     return cudaGetLastError();
 }
 
@@ -487,7 +489,7 @@ static cudaError_t launch_wgrad_t(WgradP p, int target_ctas, cudaStream_t st)
     if (kc < 1) kc = 1;
     p.kchunks = (int)kc;
     dim3 grid((unsigned)kc, tiles, z);
-    conv_wgrad_kernel<BM, BN, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, st>>>(p);
+    wf_launch_pdl(conv_wgrad_kernel<BM, BN, TM, TN>, dim3(grid), dim3((BM / TM) * (BN / TN)), 0, st, p);
     return cudaGetLastError();
 }
 

@@ -15,6 +15,7 @@ namespace {
 // ---------------------------------------------------------------------------------------------------------
 __global__ void bn_finalize_fwd_kernel(BnFwdFin a, BnFwdFin b, int n)
 {
+    wf_pdl_enter();
     const BnFwdFin& d = (blockIdx.y == 0) ? a : b;
     if ((int)blockIdx.y >= n) return;
     int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -40,6 +41,7 @@ __global__ void bn_finalize_fwd_kernel(BnFwdFin a, BnFwdFin b, int n)
 
 __global__ void bn_finalize_bwd_kernel(BnBwdFin a, BnBwdFin b, int n)
 {
+    wf_pdl_enter();
     const BnBwdFin& d = (blockIdx.y == 0) ? a : b;
     if ((int)blockIdx.y >= n) return;
     int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,6 +62,7 @@ __global__ void bn_finalize_bwd_kernel(BnBwdFin a, BnBwdFin b, int n)
 // eval mode: (scale, shift) of all BatchNorms from the running statistics, one launch
 __global__ void bn_eval_coefs_kernel(BnEvalTable tab, const float* params, const float* running, float* coefs)
 {
+    wf_pdl_enter();
     const BnEvalEntry e = tab.e[blockIdx.y];
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if ((int)blockIdx.y >= tab.n || c >= e.C) return;
@@ -129,6 +132,7 @@ constexpr int JOIN_UNR = 2;
 
 __global__ void __launch_bounds__(256) join_fwd_kernel(JoinP p)
 {
+    wf_pdl_enter();
     const int c = blockIdx.y;
     const JoinCh k = join_channel(p, c);
     const unsigned total4 = (unsigned)(p.plane / 4), stride = gridDim.x * blockDim.x;
@@ -153,6 +157,7 @@ __global__ void __launch_bounds__(256) join_fwd_kernel(JoinP p)
 template <int NT>
 __global__ void __launch_bounds__(NT) join_bwd_kernel(JoinP p)
 {
+    wf_pdl_enter();
     const int c = blockIdx.y;
     const JoinCh k = join_channel(p, c);
     const unsigned total4 = (unsigned)(p.plane / 4), stride = gridDim.x * NT;
@@ -196,6 +201,7 @@ __global__ void __launch_bounds__(NT) join_bwd_kernel(JoinP p)
 template <int NT>
 __global__ void __launch_bounds__(NT) bn_bwd_stats_kernel(const float* dy, const float* raw, const float* mean, long long plane, double* s0, double* s1)
 {
+    wf_pdl_enter();
     const int c = blockIdx.y;
     const float mu = mean[c];
     float a = 0.f, b = 0.f;
@@ -213,6 +219,7 @@ __global__ void __launch_bounds__(NT) bn_bwd_stats_kernel(const float* dy, const
 // ---------------------------------------------------------------------------------------------------------
 __global__ void pool_fwd_kernel(const float* raw, const float* scale, const float* shift, const float* mean, float* pred, int B)
 {
+    wf_pdl_enter();
     int i = blockIdx.x * blockDim.x + threadIdx.x;       // (o, j, b)
     if (i >= 2 * 15 * B) return;
     const int b = i % B, j = (i / B) % 15, o = i / (15 * B);
@@ -231,6 +238,7 @@ template <int NT>
 __global__ void __launch_bounds__(NT) pool_bwd_kernel(const float* raw, const float* scale, const float* shift, const float* mean, const float* dpred,
                                                       float* dy, int B, double* s0, double* s1)
 {
+    wf_pdl_enter();
     const int o = blockIdx.y;
     const float s = scale[o], t = shift[o], mu = mean[o];
     float a0 = 0.f, a1 = 0.f;
@@ -275,6 +283,7 @@ template <int NT>
 __global__ void __launch_bounds__(NT) pose_loss_kernel(const float* pred, const float* target, int B, int type, float pw, float bw,
                                                        const float* gscale, float* dpred, double* acc)
 {
+    wf_pdl_enter();
     float ps = 0.f, bs = 0.f;
     const int b = blockIdx.x * NT + threadIdx.x;
     if (b < B) {
@@ -312,6 +321,7 @@ __global__ void __launch_bounds__(NT) pose_loss_kernel(const float* pred, const 
 
 __global__ void pose_loss_finish_kernel(double* acc, int B, float pw, float bw, float* out3)
 {
+    wf_pdl_enter();
     const float pos = (float)(acc[0] / (30.0 * B)), bone = (float)(acc[1] / (14.0 * B));
     out3[0] = pw * pos + bw * bone;
     out3[1] = pos;
@@ -326,6 +336,7 @@ template <int NT>
 __global__ void __launch_bounds__(NT) metrics_kernel(const float* pred, const float* target, int B, MetricThr thr, int ia, int ib,
                                                      unsigned long long* counts, double* dsum)
 {
+    wf_pdl_enter();
     __shared__ unsigned int scnt[WF_MAX_THR];
     if (threadIdx.x < WF_MAX_THR) scnt[threadIdx.x] = 0;
     __syncthreads();
@@ -359,6 +370,7 @@ __global__ void __launch_bounds__(NT) metrics_kernel(const float* pred, const fl
 
 __global__ void metrics_finish_kernel(unsigned long long* counts, double* dsum, int B, int nthr, float* out)
 {
+    wf_pdl_enter();
     const int k = threadIdx.x;
     if (k < nthr) { out[k] = (float)counts[k] / (float)(15 * B); counts[k] = 0; }
     if (k == 0) { out[nthr] = (float)(*dsum / (15.0 * B)); *dsum = 0; }
@@ -370,6 +382,7 @@ __global__ void metrics_finish_kernel(unsigned long long* counts, double* dsum, 
 // ---------------------------------------------------------------------------------------------------------
 __global__ void pack_weights_kernel(PackTable tab, const float* params, float* packed)
 {
+    wf_pdl_enter();
     const PackEntry e = tab.e[blockIdx.y];
     const int cout_g = e.cout / e.groups;
     const int total = e.cout * e.cin * e.ntaps;
@@ -389,6 +402,7 @@ __global__ void pack_weights_kernel(PackTable tab, const float* params, float* p
 template <int NT>
 __global__ void __launch_bounds__(NT) sumsq_kernel(const float* g, long long n, double* acc)
 {
+    wf_pdl_enter();
     float a = 0.f, b = 0.f;
     const long long n4 = n / 4;
     for (long long q = (long long)blockIdx.x * NT + threadIdx.x; q < n4; q += (long long)gridDim.x * NT) {
@@ -411,6 +425,7 @@ __global__ void __launch_bounds__(NT) sumsq_kernel(const float* g, long long n, 
 
 __global__ void adamw_prep_kernel(AdamState* st, float lr, float b1, float b2, float max_norm, float grad_scale)
 {
+    wf_pdl_enter();
     st->step += 1;
     const double gn = sqrt(st->sumsq) * grad_scale;
     st->grad_norm = (float)gn;
@@ -426,6 +441,7 @@ __global__ void adamw_prep_kernel(AdamState* st, float lr, float b1, float b2, f
 __global__ void adamw_kernel(float* p, const float* g, float* m, float* v, long long n, const AdamState* st,
                              float lr, float b1, float b2, float eps, float wd)
 {
+    wf_pdl_enter();
     const float coef = st->clip_coef, step_size = st->step_size, ibc2 = st->inv_bc2_sqrt;
     const float decay = 1.f - lr * wd;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -446,6 +462,7 @@ __global__ void adamw_kernel(float* p, const float* g, float* m, float* v, long 
 __global__ void permute_kernel(const float* src, float* dst, int C, int P, int B, long long r_sb, long long r_sc, long long r_sp,
                                long long r_st, int to_internal, const float* scale, const float* shift, const float* mean)
 {
+    wf_pdl_enter();
     const long long total = (long long)C * P * B * WF_T;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int t = (int)(i % WF_T);
@@ -468,7 +485,7 @@ cudaError_t wf_launch_bn_fwd_fin(const BnFwdFin* d, int n, cudaStream_t st)
     int cmax = d[0].C;
     if (n > 1 && d[1].C > cmax) cmax = d[1].C;
     dim3 grid(cdiv(cmax, 128), n);
-    bn_finalize_fwd_kernel<<<grid, 128, 0, st>>>(d[0], n > 1 ? d[1] : d[0], n);
+    wf_launch_pdl(bn_finalize_fwd_kernel, dim3(grid), dim3(128), 0, st, d[0], n > 1 ? d[1] : d[0], n);
     return cudaGetLastError();
 }
 cudaError_t wf_launch_bn_bwd_fin(const BnBwdFin* d, int n, cudaStream_t st)
@@ -476,13 +493,13 @@ cudaError_t wf_launch_bn_bwd_fin(const BnBwdFin* d, int n, cudaStream_t st)
     int cmax = d[0].C;
     if (n > 1 && d[1].C > cmax) cmax = d[1].C;
     dim3 grid(cdiv(cmax, 128), n);
-    bn_finalize_bwd_kernel<<<grid, 128, 0, st>>>(d[0], n > 1 ? d[1] : d[0], n);
+    wf_launch_pdl(bn_finalize_bwd_kernel, dim3(grid), dim3(128), 0, st, d[0], n > 1 ? d[1] : d[0], n);
     return cudaGetLastError();
 }
 cudaError_t wf_launch_bn_eval_coefs(const BnEvalTable& tab, const float* params, const float* running, float* coefs, cudaStream_t st)
 {
     dim3 grid(cdiv(540, 128), tab.n);
-    bn_eval_coefs_kernel<<<grid, 128, 0, st>>>(tab, params, running, coefs);
+    wf_launch_pdl(bn_eval_coefs_kernel, dim3(grid), dim3(128), 0, st, tab, params, running, coefs);
     return cudaGetLastError();
 }
 static int ew_blocks(long long total4, int C, int num_sms)
@@ -496,70 +513,70 @@ static int ew_blocks(long long total4, int C, int num_sms)
 cudaError_t wf_launch_join_fwd(const JoinP& p, int num_sms, cudaStream_t st)
 {
     dim3 grid(ew_blocks(p.plane / 4, p.C, num_sms), p.C);
-    join_fwd_kernel<<<grid, 256, 0, st>>>(p);
+    wf_launch_pdl(join_fwd_kernel, dim3(grid), dim3(256), 0, st, p);
     return cudaGetLastError();
 }
 cudaError_t wf_launch_join_bwd(const JoinP& p, int num_sms, cudaStream_t st)
 {
     dim3 grid(ew_blocks(p.plane / 4, p.C, num_sms), p.C);
-    join_bwd_kernel<256><<<grid, 256, 0, st>>>(p);
+    wf_launch_pdl(join_bwd_kernel<256>, dim3(grid), dim3(256), 0, st, p);
     return cudaGetLastError();
 }
 cudaError_t wf_launch_bn_bwd_stats(const float* dy, const float* raw, const float* mean, int C, long long plane, double* s0, double* s1, int num_sms, cudaStream_t st)
 {
     dim3 grid(ew_blocks(plane / 4, C, num_sms), C);
-    bn_bwd_stats_kernel<256><<<grid, 256, 0, st>>>(dy, raw, mean, plane, s0, s1);
+    wf_launch_pdl(bn_bwd_stats_kernel<256>, dim3(grid), dim3(256), 0, st, dy, raw, mean, plane, s0, s1);
     return cudaGetLastError();
 }
 cudaError_t wf_launch_pool_fwd(const float* raw, const float* scale, const float* shift, const float* mean, float* pred, int B, cudaStream_t st)
 {
-    pool_fwd_kernel<<<cdiv(30LL * B, 128), 128, 0, st>>>(raw, scale, shift, mean, pred, B);
+    wf_launch_pdl(pool_fwd_kernel, dim3(cdiv(30LL * B, 128)), dim3(128), 0, st, raw, scale, shift, mean, pred, B);
     return cudaGetLastError();
 }
 cudaError_t wf_launch_pool_bwd(const float* raw, const float* scale, const float* shift, const float* mean, const float* dpred, float* dy, int B,
                                double* s0, double* s1, cudaStream_t st)
 {
     dim3 grid(cdiv(15LL * B, 256) > 64 ? 64 : cdiv(15LL * B, 256), 2);
-    pool_bwd_kernel<256><<<grid, 256, 0, st>>>(raw, scale, shift, mean, dpred, dy, B, s0, s1);
+    wf_launch_pdl(pool_bwd_kernel<256>, dim3(grid), dim3(256), 0, st, raw, scale, shift, mean, dpred, dy, B, s0, s1);
     return cudaGetLastError();
 }
 cudaError_t wf_launch_pose_loss(const float* pred, const float* target, int B, int type, float pw, float bw, const float* gscale,
                                 float* dpred, double* acc2, float* out3, cudaStream_t st)
 {
-    pose_loss_kernel<128><<<cdiv(B, 128), 128, 0, st>>>(pred, target, B, type, pw, bw, gscale, dpred, acc2);
-    pose_loss_finish_kernel<<<1, 1, 0, st>>>(acc2, B, pw, bw, out3);
+    wf_launch_pdl(pose_loss_kernel<128>, dim3(cdiv(B, 128)), dim3(128), 0, st, pred, target, B, type, pw, bw, gscale, dpred, acc2);
+    wf_launch_pdl(pose_loss_finish_kernel, dim3(1), dim3(1), 0, st, acc2, B, pw, bw, out3);
     return cudaGetLastError();
 }
 cudaError_t wf_launch_metrics(const float* pred, const float* target, int B, const MetricThr& thr, int torso, unsigned long long* counts,
                               double* dsum, float* out, cudaStream_t st)
 {
-    metrics_kernel<128><<<cdiv(B, 128), 128, 0, st>>>(pred, target, B, thr, 2, torso ? 12 : 5, counts, dsum);
-    metrics_finish_kernel<<<1, 32, 0, st>>>(counts, dsum, B, thr.n, out);
+    wf_launch_pdl(metrics_kernel<128>, dim3(cdiv(B, 128)), dim3(128), 0, st, pred, target, B, thr, 2, torso ? 12 : 5, counts, dsum);
+    wf_launch_pdl(metrics_finish_kernel, dim3(1), dim3(32), 0, st, counts, dsum, B, thr.n, out);
     return cudaGetLastError();
 }
 cudaError_t wf_launch_pack(const PackTable& tab, const float* params, float* packed, cudaStream_t st)
 {
     dim3 grid(64, tab.n);
-    pack_weights_kernel<<<grid, 256, 0, st>>>(tab, params, packed);
+    wf_launch_pdl(pack_weights_kernel, dim3(grid), dim3(256), 0, st, tab, params, packed);
     return cudaGetLastError();
 }
 cudaError_t wf_launch_adamw(float* p, const float* g, float* m, float* v, long long n, AdamState* state, float lr, float b1, float b2,
                             float eps, float wd, float max_norm, float grad_scale, int num_sms, cudaStream_t st)
 {
-    sumsq_kernel<256><<<num_sms * 2, 256, 0, st>>>(g, n, &state->sumsq);
-    adamw_prep_kernel<<<1, 1, 0, st>>>(state, lr, b1, b2, max_norm, grad_scale);
-    adamw_kernel<<<num_sms * 4, 256, 0, st>>>(p, g, m, v, n, state, lr, b1, b2, eps, wd);
+    wf_launch_pdl(sumsq_kernel<256>, dim3(num_sms * 2), dim3(256), 0, st, g, n, &state->sumsq);
+    wf_launch_pdl(adamw_prep_kernel, dim3(1), dim3(1), 0, st, state, lr, b1, b2, max_norm, grad_scale);
+    wf_launch_pdl(adamw_kernel, dim3(num_sms * 4), dim3(256), 0, st, p, g, m, v, n, state, lr, b1, b2, eps, wd);
     return cudaGetLastError();
 }
 cudaError_t wf_launch_permute(const float* src, float* dst, int C, int P, int B, long long r_sb, long long r_sc, long long r_sp,
                               long long r_st, int to_internal, int num_sms, cudaStream_t st)
 {
-    permute_kernel<<<num_sms * 8, 256, 0, st>>>(src, dst, C, P, B, r_sb, r_sc, r_sp, r_st, to_internal, nullptr, nullptr, nullptr);
+    wf_launch_pdl(permute_kernel, dim3(num_sms * 8), dim3(256), 0, st, src, dst, C, P, B, r_sb, r_sc, r_sp, r_st, to_internal, nullptr, nullptr, nullptr);
     return cudaGetLastError();
 }
 cudaError_t wf_launch_permute_affine(const float* src, float* dst, int C, int P, int B, long long r_sb, long long r_sc, long long r_sp,
                                      long long r_st, const float* scale, const float* shift, const float* mean, int num_sms, cudaStream_t st)
 {
-    permute_kernel<<<num_sms * 8, 256, 0, st>>>(src, dst, C, P, B, r_sb, r_sc, r_sp, r_st, 0, scale, shift, mean);
+    wf_launch_pdl(permute_kernel, dim3(num_sms * 8), dim3(256), 0, st, src, dst, C, P, B, r_sb, r_sc, r_sp, r_st, 0, scale, shift, mean);
     return cudaGetLastError();
 }

@@ -36,6 +36,7 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 template <int BM>       // 16 or 32 output channels (the whole group)
 __global__ void __launch_bounds__(G_NT, 2) group_conv_kernel(const ConvP p)
 {
+    wf_pdl_enter();
     constexpr int MI = BM / 16, WS = BM + 8;
     extern __shared__ __align__(16) float smem[];
     float* Xs = smem;                                         // [hi|lo][G_KMAX][G_XS]
@@ -228,7 +229,7 @@ cudaError_t launch_group(const ConvP& p, cudaStream_t st)
         cfg = true;
     }
     dim3 grid((p.N + G_BN - 1) / G_BN, 1, p.groups);
-    group_conv_kernel<BM><<<grid, G_NT, smem, st>>>(p);
+    wf_launch_pdl(group_conv_kernel<BM>, dim3(grid), dim3(G_NT), smem, st, p);
     return cudaGetLastError();
 }
 
@@ -267,6 +268,7 @@ constexpr int GW_STAGE = 2 * 32 * GW_GS + 2 * 32 * GW_XS;      // words per stag
 
 __global__ void __launch_bounds__(G_NT, 1) group_wgrad_kernel(const WgradP p, long long cols_per_split)
 {
+    wf_pdl_enter();
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = blockIdx.z;
@@ -465,6 +467,6 @@ cudaError_t wf_launch_group_wgrad(const WgradP& p, int num_sms, cudaStream_t st)
     per = (per + GW_KCH - 1) / GW_KCH * GW_KCH;
     splits = (p.N + per - 1) / per;
     dim3 grid((unsigned)splits, 1, p.groups);
-    group_wgrad_kernel<<<grid, G_NT, smem, st>>>(p, per);
+    wf_launch_pdl(group_wgrad_kernel, dim3(grid), dim3(G_NT), smem, st, p, per);
     return cudaGetLastError();
 }

@@ -94,6 +94,7 @@ __device__ __forceinline__ int desc_chan(int d) { return (d >> 20) & 255; }
 template <int MI, int NI, int MW, int NW, int LD, int MINB, int PRO, bool HASDN>
 __global__ void __launch_bounds__(32 * MW * NW, MINB) slide_conv_kernel(const ConvP p, const SlideGeo g)
 {
+    wf_pdl_enter();
     constexpr int NT = 32 * MW * NW, BM = 16 * MI * MW, BN = 8 * NI * NW, XS = BN + 2 * SL_H, Q = XS / 4, WS = BM + 8;
     extern __shared__ __align__(16) float smem[];
     __shared__ double red[2][BM];
@@ -371,6 +372,7 @@ __global__ void __launch_bounds__(32 * MW * NW, MINB) slide_conv_kernel(const Co
 template <int MI, int NTAPS, int K8S, int LD, int MINB, int PRO>
 __global__ void __launch_bounds__(256, MINB) slide_thin_kernel(const ConvP p, const SlideGeo g)
 {
+    wf_pdl_enter();
     constexpr int NT = 256, NW = 8, BN = 16 * MI * NW, XS = BN + 2 * SL_H, Q = XS / 4, K8 = 8 * K8S;
     extern __shared__ __align__(16) float smem[];
     __shared__ double red[2][8];
@@ -629,6 +631,7 @@ constexpr int SW_NT = 256;
 template <int MTW, int NTW, int NTAPS, int LDG, int LDX, int MINB, int PRO>
 __global__ void __launch_bounds__(SW_NT, MINB) slide_wgrad_kernel(const WgradP p, const SlideGeo g)
 {
+    wf_pdl_enter();
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fr = lane >> 2, fc = lane & 3;
@@ -993,7 +996,7 @@ cudaError_t launch_slide_conv(const ConvP& p, int num_sms, cudaStream_t st, bool
     const double c_fix = (double)p.ntaps * K8 * BM / 128.0 * 2.0 + 600.0;
     g.PC = pick_pc(p.Pout, g.PS, coltiles, num_sms * occ, span, c_slab, c_pos, c_fix);
     dim3 grid(coltiles, (p.Pout + g.PC - 1) / g.PC, 1);
-    slide_conv_kernel<MI, NI, MW, NW, LD, MINB, PRO, HASDN><<<grid, NT, smem, st>>>(p, g);
+    wf_launch_pdl(slide_conv_kernel<MI, NI, MW, NW, LD, MINB, PRO, HASDN>, dim3(grid), dim3(NT), smem, st, p, g);
     return cudaGetLastError();
 }
 
@@ -1050,7 +1053,7 @@ cudaError_t launch_slide_thin(const ConvP& p, int num_sms, cudaStream_t st, bool
     const double c_pos = (double)(BN / 16) * K8S * p.ntaps * 3 * 2.0 * 1.5 + (double)BN * 8 / 128.0 * 8.0 + 100.0;
     g.PC = pick_pc(p.Pout, g.PS, coltiles, num_sms * occ, span, c_slab, c_pos, 400.0);
     dim3 grid(coltiles, (p.Pout + g.PC - 1) / g.PC, 1);
-    slide_thin_kernel<MI, NTAPS, K8S, LD, MINB, PRO><<<grid, NT, smem, st>>>(p, g);
+    wf_launch_pdl(slide_thin_kernel<MI, NTAPS, K8S, LD, MINB, PRO>, dim3(grid), dim3(NT), smem, st, p, g);
     return cudaGetLastError();
 }
 
@@ -1146,7 +1149,7 @@ cudaError_t launch_slide_wgrad(const WgradP& p, const WgCfg& c, int num_sms, cud
     g.PC = pick_pc(p.Pout, g.PS, g.ncol, slots, span, c_slab, c_pos, 300.0);
     g.nitems = g.ncol * ((p.Pout + g.PC - 1) / g.PC);
     const int grid = g.nitems < slots ? g.nitems : slots;
-    slide_wgrad_kernel<MTW, NTW, NTAPS, LDG, LDX, MINB, PRO><<<grid, SW_NT, smem, st>>>(p, g);
+    wf_launch_pdl(slide_wgrad_kernel<MTW, NTW, NTAPS, LDG, LDX, MINB, PRO>, dim3(grid), dim3(SW_NT), smem, st, p, g);
     return cudaGetLastError();
 }
 

@@ -76,6 +76,7 @@ struct TcGeom { int bn, bnp, nst, tmem_cols; };
 template <int PRO, bool MASK>
 __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const TcGeom g)
 {
+    wf_pdl_enter();
     const int BN = g.bn, STAGES = g.nst;
     const int B_HALF = KC * BN * 4;                       // one of hi/lo of the BN x KC K-major activation tile
     const int STAGE_BYTES = 2 * A_HALF + 2 * B_HALF;
@@ -286,6 +287,7 @@ constexpr int WG_STAGE_BYTES = 2 * A_HALF + 2 * WG_BN_MAX * KC * 4;
 template <int GPRO, int XPRO, bool MASK>
 __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const WgradP p, int bn, int ntile_n, long long cols_per_split)
 {
+    wf_pdl_enter();
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int B_HALF = WG_BN_MAX * KC * 4;
     constexpr int TCOLS = 2 * WG_BN_MAX;
@@ -482,6 +484,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const WgradP p
 // =========================================================================================================
 __global__ void tc_pack_kernel(TcPackTable tab, const float* params, float* packed)
 {
+    wf_pdl_enter();
     const TcPackEntry e = tab.e[blockIdx.y];
     const int f_mt = (e.cout + BM - 1) / BM, f_kt = (e.cin + KC - 1) / KC;
     const int b_mt = (e.cin + BM - 1) / BM, b_kt = (e.cout + KC - 1) / KC;
@@ -518,7 +521,7 @@ cudaError_t launch_conv_t(const ConvP& p, const TcGeom& g, dim3 grid, int smem, 
         if (e != cudaSuccess) return e;
         cfg = true;
     }
-    pw_tc_kernel<PRO, MASK><<<grid, NTHREADS, smem, st>>>(p, g);
+    wf_launch_pdl(pw_tc_kernel<PRO, MASK>, dim3(grid), dim3(NTHREADS), smem, st, p, g);
     return cudaGetLastError();
 }
 
@@ -532,7 +535,7 @@ cudaError_t launch_wgrad_t(const WgradP& p, int bn, int nt, long long per, dim3 
         if (e != cudaSuccess) return e;
         cfg = true;
     }
-    pw_wgrad_tc_kernel<GPRO, XPRO, MASK><<<grid, NTHREADS, smem, st>>>(p, bn, nt, per);
+    wf_launch_pdl(pw_wgrad_tc_kernel<GPRO, XPRO, MASK>, dim3(grid), dim3(NTHREADS), smem, st, p, bn, nt, per);
     return cudaGetLastError();
 }
 
@@ -544,7 +547,7 @@ cudaError_t wf_launch_tc_pack(const TcPackTable& tab, const float* params, float
 {
     if (tab.n == 0) return cudaSuccess;
     dim3 grid(64, tab.n);
-    tc_pack_kernel<<<grid, 256, 0, st>>>(tab, params, packed);
+    wf_launch_pdl(tc_pack_kernel, dim3(grid), dim3(256), 0, st, tab, params, packed);
     return cudaGetLastError();
 }
 

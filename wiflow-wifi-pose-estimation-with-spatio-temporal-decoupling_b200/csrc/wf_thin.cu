@@ -19,6 +19,7 @@ __device__ __forceinline__ int floor_div(int a, int b) { return (a >= 0) ? a / b
 template <int COUTP>
 __global__ void __launch_bounds__(256, COUTP == 8 ? 4 : 3) thin_conv_kernel(const ConvP p, int PC)
 {
+    wf_pdl_enter();
     constexpr int NT = THIN_NT, Q = NT / 4;
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -114,6 +115,7 @@ constexpr int TW_PC = 4;             // output positions per region
 template <int CINP>
 __global__ void __launch_bounds__(384, 2) thin_wgrad_kernel(const WgradP p, int coutp, int PS, int nregions)
 {
+    wf_pdl_enter();
     constexpr int NT = TW_NT, PC = TW_PC;
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -197,11 +199,11 @@ cudaError_t wf_launch_thin_conv(const ConvP& p, cudaStream_t st)
     if (coutp == 8) {
         static bool cfg = false;
         if (!cfg) { e = cudaFuncSetAttribute(thin_conv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); if (e) return e; cfg = true; }
-        thin_conv_kernel<8><<<grid, threads, smem, st>>>(p, PC);
+        wf_launch_pdl(thin_conv_kernel<8>, dim3(grid), dim3(threads), smem, st, p, PC);
     } else {
         static bool cfg = false;
         if (!cfg) { e = cudaFuncSetAttribute(thin_conv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); if (e) return e; cfg = true; }
-        thin_conv_kernel<16><<<grid, threads, smem, st>>>(p, PC);
+        wf_launch_pdl(thin_conv_kernel<16>, dim3(grid), dim3(threads), smem, st, p, PC);
     }
     return cudaGetLastError();
 }
@@ -234,7 +236,7 @@ static cudaError_t launch_thin_wgrad_t(const WgradP& p, int num_sms, cudaStream_
         if (e) return e;
         cfg = true;
     }
-    thin_wgrad_kernel<CINP><<<grid, warps * 32, smem, st>>>(p, coutp, PS, nregions);
+    wf_launch_pdl(thin_wgrad_kernel<CINP>, dim3(grid), dim3(warps * 32), smem, st, p, coutp, PS, nregions);
     return cudaGetLastError();
 }
 

@@ -556,6 +556,7 @@ cudaError_t wf_launch_metrics(const float* pred, const float* target, int B, con
 }
 cudaError_t wf_launch_pack(const PackTable& tab, const float* params, float* packed, cudaStream_t st)
 {
+    if (tab.n == 0) return cudaSuccess;
     dim3 grid(64, tab.n);
     wf_launch_pdl(pack_weights_kernel, dim3(grid), dim3(256), 0, st, tab, params, packed);
     return cudaGetLastError();

@@ -754,10 +754,10 @@ void prepare_weights(Ctx& c)
     Scope sc(c, "pack_weights");
     c.ck(cudaMemsetAsync(n.packed, 0, n.packed_floats * sizeof(float), c.st));
     PackTable tab{};
-    tab.n = (int)n.conv.size();
-    for (int i = 0; i < tab.n; ++i) {
+    for (size_t i = 0; i < n.conv.size(); ++i) {
         const ConvUnit& u = n.conv[i];
-        PackEntry& e = tab.e[i];
+        if (u.tc) continue;                         // tcgen05 layers read their own split images (tc_pack below): 86 % of all weights
+        PackEntry& e = tab.e[tab.n++];
         e.param_off = (int)u.w_off; e.cout = u.cout_g * u.groups; e.cin = u.cin_g; e.groups = u.groups; e.ntaps = u.ntaps;
         e.f_kpad = u.f_kpad; e.f_mpad = u.f_mpad; e.b_kpad = u.b_kpad; e.b_mpad = u.b_mpad;
         e.fwd_off = u.fpack; e.bwd_off = u.bpack;

@@ -168,3 +168,33 @@ def test_fit_bookkeeping(wf):
     st = _oracle_state(model)
     tot = sum(O.mpjpe(O.forward(st, x, train=False), y) * x.shape[0] for x, y in val) / sum(x.shape[0] for x, _ in val)
     assert abs(again['mpjpe'] - tot) < 5e-5
+
+
+def test_host_batches_take_the_staged_upload_path_and_match_device_batches():
+    """TrainStep.step with pinned HOST tensors (upload through two staging slots on a copy stream, engine.py::_upload) gives the same
+    steps as with device tensors; the staging slots are reused safely over more calls than there are slots"""
+    import wiflow_b200 as wf
+    from oracle import wiflow_oracle as O
+    dev = torch.device('cuda', 0)
+    B = 16
+    batches = [O.synthetic_batch(B, 40 + i) for i in range(5)]
+    outs = []
+    for host in (False, True):
+        torch.manual_seed(3)
+        model = wf.WiFlowPoseModel(dropout=0.0).to(dev)
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.Dropout2d):
+                mod.p = 0.0
+        ts = wf.TrainStep(model, B, dropout=False)
+        res = []
+        for x, y in batches:
+            if host:
+                out = ts.step(x.pin_memory(), y.pin_memory())
+            else:
+                out = ts.step(x.to(dev), y.to(dev))
+            res.append(out.clone())
+        torch.cuda.synchronize(dev)
+        assert (ts._copy_stream is not None) == host
+        outs.append((torch.stack(res).cpu(), ts.params.detach().cpu().clone()))
+    assert torch.allclose(outs[0][0], outs[1][0], rtol=2e-4, atol=1e-6), (outs[0][0], outs[1][0])
+    assert (outs[0][1] - outs[1][1]).abs().max().item() <= 1e-5

@@ -45,6 +45,8 @@ __global__ void __launch_bounds__(G_NT, 2) group_conv_kernel(const ConvP p)
     const int g = blockIdx.z;
     const int n0 = blockIdx.x * G_BN;
     const int K8 = (p.Cin + 7) / 8 * 8;                       // channels rounded up to the mma K step (rows >= Cin are zero)
+    __shared__ double red[2][32];                             // BatchNorm sums of the CTA's rows: the 8 warps meet here first
+    if (tid < 64) red[tid >> 5][tid & 31] = 0.0;
 
     // ---- stage the weights of this group: [tap][k][m]; all loads of a thread are in flight before the first is used ----
     {
@@ -211,9 +213,17 @@ __global__ void __launch_bounds__(G_NT, 2) group_conv_kernel(const ConvP p)
             s0 += __shfl_xor_sync(0xffffffffu, s0, 2);               // lanes fc and fc^2 share the row
             s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
             if (fc < 2 && mv) {
-                atomicAdd(p.stat0 + co, (double)s0);
-                atomicAdd(p.stat1 + co, (double)s1);
+                atomicAdd(&red[0][m], (double)s0);
+                atomicAdd(&red[1][m], (double)s1);
             }
+        }
+    }
+    // one global reduction pair per row per CTA (was one per warp: 8x the traffic onto the same 2 x Cout addresses of the group)
+    if (want_stats) {
+        __syncthreads();
+        if (tid < p.Cout) {
+            atomicAdd(p.stat0 + g * p.Cout + tid, red[0][tid]);
+            atomicAdd(p.stat1 + g * p.Cout + tid, red[1][tid]);
         }
     }
 }

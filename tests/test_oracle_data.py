@@ -109,6 +109,26 @@ def test_product_epoch_order_and_split(g):
     assert np.array_equal(tr, g['split_train']) and np.array_equal(va, g['split_val']) and np.array_equal(te, g['split_test'])
 
 
+def test_sharded_epoch_covers_the_single_process_batches():
+    """SURVEY 8e x 8f-3: world processes that seed identically see, together, exactly the batches of one process"""
+    from wiflow_b200 import data as P
+    idx = np.arange(100, 100 + 53)
+    for world in (2, 4):
+        torch.manual_seed(9)
+        single = P.shard_epoch(idx, 4 * world, True)
+        shards = []
+        for rank in range(world):
+            torch.manual_seed(9)
+            shards.append(P.shard_epoch(idx, 4, True, False, rank, world))
+        assert all(len(s) == len(single) for s in shards)
+        for b, glob in enumerate(single):
+            parts = [s[b] for s in shards]
+            assert np.array_equal(np.concatenate(parts), glob)
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    torch.manual_seed(9)
+    assert sum(len(b) for b in P.shard_epoch(idx, 4, True, True, 1, 2)) == (53 // 8) * 4       # drop_last drops the ragged global batch
+
+
 def test_product_data_path_has_no_host_fallback(tmp_path):
     from wiflow_b200 import data as P
     from wiflow_b200.utils import augmentation as A

@@ -57,6 +57,22 @@ def split_files(n_files, window_ranges, random_seed=42):
     return out, parts
 
 
+def shard_epoch(indices, batch_size, shuffle, drop_last=False, rank=0, world=1):
+    """This rank's batches of one epoch: the DataLoader order over `indices` cut into global batches of batch_size * world windows,
+    of which rank keeps its contiguous shard (at most one window more or less than the other ranks in a ragged last batch)."""
+    from .engine import shard_bounds
+    indices = np.asarray(indices, dtype=np.int64)
+    order = indices[sampler_order(len(indices), shuffle)]
+    g = batch_size * max(1, world)
+    nb = len(order) // g if drop_last else (len(order) + g - 1) // g
+    out = []
+    for i in range(nb):
+        glob = order[i * g:(i + 1) * g]
+        lo, hi = shard_bounds(len(glob), rank, world)
+        out.append(glob[lo:hi])
+    return out
+
+
 class PreprocessedCSIKeypointsDataset:
     """Same constructor arguments, files and indexing behaviour as dataset.py:16; tensors come back on `device`."""
 
@@ -175,7 +191,11 @@ class DeviceBatchLoader:
     """Iterates (x, y) CUDA batches over `indices` of a dataset in DataLoader order (batch_size, shuffle, drop_last as torch's).
     Yielded tensors stay valid until the second following batch is requested (two device slots)."""
 
-    def __init__(self, dataset, indices=None, batch_size=64, shuffle=False, drop_last=False, augment=False):
+    def __init__(self, dataset, indices=None, batch_size=64, shuffle=False, drop_last=False, augment=False, rank=0, world=1):
+        """rank / world: data-parallel training with one process per GPU.  Every rank walks the SAME epoch order (seed
+        the default torch generator identically on all ranks) in global batches of batch_size * world windows and keeps its
+        contiguous shard of each (engine.shard_bounds), so world processes together see exactly the batches one process would."""
+        self.rank, self.world = int(rank), max(1, int(world))
         self.dataset = dataset
         self.indices = np.arange(len(dataset), dtype=np.int64) if indices is None else np.asarray(indices, dtype=np.int64)
         self.batch_size = int(batch_size)
@@ -192,12 +212,11 @@ class DeviceBatchLoader:
             self._copied = [None, None]
 
     def __len__(self):
-        n = len(self.indices)
-        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+        n, g = len(self.indices), self.batch_size * self.world
+        return n // g if self.drop_last else (n + g - 1) // g
 
     def epoch_batches(self):
-        order = self.indices[sampler_order(len(self.indices), self.shuffle)]
-        return [order[i * self.batch_size:(i + 1) * self.batch_size] for i in range(len(self))]
+        return shard_epoch(self.indices, self.batch_size, self.shuffle, self.drop_last, self.rank, self.world)
 
     # streaming mode: worker thread fills pinned slot k (gather out of the memory map), then the copy stream moves it
     def _fill(self, slot, idx):

@@ -627,6 +627,7 @@ __global__ void __launch_bounds__(256, MINB) slide_thin_kernel(const ConvP p, co
 // =========================================================================================================
 constexpr int SW_BN = 64, SW_GS = SW_BN + 4, SW_XS = SW_BN + 2 * SL_H + 4, SW_GQ = SW_BN / 4, SW_XQ = (SW_BN + 2 * SL_H) / 4;
 constexpr int SW_NT = 256;
+constexpr int SW_UNROLL = 2;          // k8 steps of one position unrolled together in slide_wgrad_kernel
 
 template <int MTW, int NTW, int NTAPS, int LDG, int LDX, int MINB, int PRO>
 __global__ void __launch_bounds__(SW_NT, MINB) slide_wgrad_kernel(const WgradP p, const SlideGeo g)
@@ -793,13 +794,12 @@ __global__ void __launch_bounds__(SW_NT, MINB) slide_wgrad_kernel(const WgradP p
             // being skipped, which keeps the MMA sequence free of divergence bookkeeping
             const int nunits = (oe - op) * (SW_BN / 8);
             const int upw = (nunits + KWs - 1) / KWs;
-            int cur_pos = -1;
             int xb[NTAPS];
             const float* gs = nullptr;
-            for (int unit = wk * upw; unit < min((wk + 1) * upw, nunits); ++unit) {
-                const int pi = unit >> 3, kc = (unit & 7) * 8;
-                if (pi != cur_pos) {
-                    cur_pos = pi;
+            const int u0 = wk * upw, u1 = min((wk + 1) * upw, nunits);
+            for (int pi = u0 >> 3; u0 < u1 && pi <= ((u1 - 1) >> 3); ++pi) {
+                const int k_lo = pi == (u0 >> 3) ? (u0 & 7) : 0, k_hi = pi == ((u1 - 1) >> 3) ? ((u1 - 1) & 7) + 1 : 8;
+                {
                     const int opos = op + pi;
                     gs = Gs + (cur * PS + pi) * gslab + (wm * MTW * 16 + fr) * SW_GS + fc;
 #pragma unroll
@@ -809,6 +809,11 @@ __global__ void __launch_bounds__(SW_NT, MINB) slide_wgrad_kernel(const WgradP p
                         xb[tap] = slot * xslab + (wn * NTW * 8 + fr) * SW_XS + SL_H + fc + (HASDN ? p.dn[tap] : 0);
                     }
                 }
+                // the k8 steps of one position share all addressing: a plain counted loop the compiler can software-pipeline
+                // (fragment loads of step k+1 under the MMAs of step k)
+#pragma unroll(SW_UNROLL)
+                for (int k8i = k_lo; k8i < k_hi; ++k8i) {
+                const int kc = k8i * 8;
                 uint32_t ah[MTW][4], al[MTW][4];
 #pragma unroll
                 for (int mi = 0; mi < MTW; ++mi) {
@@ -850,6 +855,7 @@ __global__ void __launch_bounds__(SW_NT, MINB) slide_wgrad_kernel(const WgradP p
                                     else if (pass == 1) mma_tf32(acc[tg + tt][mi][ni], ah[mi], bl[tt][ni]);
                                     else mma_tf32(acc[tg + tt][mi][ni], ah[mi], bh[tt][ni]);
                                 }
+                }
                 }
             }
 

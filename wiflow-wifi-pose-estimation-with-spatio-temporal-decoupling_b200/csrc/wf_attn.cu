@@ -261,7 +261,23 @@ __global__ void __launch_bounds__(RT * GH * L, attn_min_blocks(RT * GH * L, MODE
         float dk[8], dv[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
-        for (int ii = 0; ii < L; ++ii) {
+        // four source rows per step: q and d sv arrive as 128-bit broadcasts (one LDS per 4 products instead of one per product;
+        // the pass is shared-memory bound), same summation order as the scalar loop
+        constexpr int L4 = L / 4 * 4;
+#pragma unroll
+        for (int i0 = 0; i0 < L4; i0 += 4) {
+            float m[4], pp[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { m[e] = M[(i0 + e) * LP + i]; pp[e] = MP[(i0 + e) * LP + i]; }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 q4 = ld4(&T[tix(g * 8 + c, r, i0)]), g4 = ld4(&G[tix(g * 8 + c, r, i0)]);
+                dk[c] = fmaf(m[0], q4.x, dk[c]); dk[c] = fmaf(m[1], q4.y, dk[c]); dk[c] = fmaf(m[2], q4.z, dk[c]); dk[c] = fmaf(m[3], q4.w, dk[c]);
+                dv[c] = fmaf(pp[0], g4.x, dv[c]); dv[c] = fmaf(pp[1], g4.y, dv[c]); dv[c] = fmaf(pp[2], g4.z, dv[c]); dv[c] = fmaf(pp[3], g4.w, dv[c]);
+            }
+        }
+#pragma unroll
+        for (int ii = L4; ii < L; ++ii) {
             const float m = M[ii * LP + i], pp = MP[ii * LP + i];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {

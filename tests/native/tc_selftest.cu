@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include "../../wiflow-wifi-pose-estimation-with-spatio-temporal-decoupling_b200/csrc/wf_elem.h"
 
+thread_local int wf_pdl_mode = 0;      // launch switch of wf_common.cuh (defined by wf_model.cu in the library)
+
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 2; } } while (0)
 
 static float frand() { return (float)rand() / RAND_MAX * 2.f - 1.f; }

@@ -223,10 +223,15 @@ __device__ __forceinline__ void block_accum2(float a, float b, double* d0, doubl
 
 // ---- host side: launch with the programmatic-stream-serialisation attribute (CUDA-graph capturable) ----
 #include <cstdlib>
+// Set per call by the forward / backward schedules (wf_model.cu): on for small batches, where the step is a chain of short launches
+// (B = 64: 2.64 -> 2.53 ms), off for large ones, where early-resident dependents only take slots from the running kernel
+// (measured: eval forward at 4096 windows per pass 232.9 k samples/s without, 220.6 k with; B = 1024 training: no difference).
+// WF_PDL=0 forces it off, WF_PDL=1 on.
+extern thread_local int wf_pdl_mode;
 inline bool wf_pdl_enabled()
 {
-    static const bool on = [] { const char* e = std::getenv("WF_PDL"); return !(e && e[0] == '0'); }();
-    return on;
+    static const int env = [] { const char* e = std::getenv("WF_PDL"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+    return env >= 0 ? env != 0 : wf_pdl_mode != 0;
 }
 template <typename... KArgs, typename... Args>
 inline cudaError_t wf_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)

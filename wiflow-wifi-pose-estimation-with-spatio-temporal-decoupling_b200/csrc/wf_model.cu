@@ -15,6 +15,9 @@
 #include "../../include/wiflow_b200.h"
 #include "wf_elem.h"
 
+thread_local int wf_pdl_mode = 1;          // see wf_common.cuh: programmatic dependent launch for the launches of this thread
+constexpr int WF_PDL_MAX_B = 512;          // windows per call up to which the launch chain, not the kernels, bounds the step
+
 namespace {
 
 thread_local std::string g_err;
@@ -828,6 +831,7 @@ int run_forward(const wf_block_desc* d, const float* x, const float* params, flo
                 float* y, void* ws, size_t ws_bytes, int B, int flags, cudaStream_t st)
 {
     if (int e = check_device()) return e;
+    wf_pdl_mode = B <= WF_PDL_MAX_B ? 1 : 0;
     if (!d || !x || !params || !y || !ws || B <= 0) return fail(WF_E_ARG, "null pointer or non-positive batch");
     const bool train = (flags & WF_FLAG_TRAIN) != 0;
     if (!train && !running) return fail(WF_E_ARG, "eval mode needs the running statistics");
@@ -893,6 +897,7 @@ int run_backward(const wf_block_desc* d, const float* x, const float* params, co
                  float* dx, void* ws, size_t ws_bytes, int B, int flags, cudaStream_t st)
 {
     if (int e = check_device()) return e;
+    wf_pdl_mode = B <= WF_PDL_MAX_B ? 1 : 0;
     if (!d || !x || !params || !dy || !grads || !ws || B <= 0) return fail(WF_E_ARG, "null pointer or non-positive batch");
     if ((flags & (WF_FLAG_TRAIN | WF_FLAG_SAVE_FOR_BACKWARD)) != (WF_FLAG_TRAIN | WF_FLAG_SAVE_FOR_BACKWARD))
         return fail(WF_E_UNSUPPORTED, "backward needs a forward run with WF_FLAG_TRAIN|WF_FLAG_SAVE_FOR_BACKWARD");

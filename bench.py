@@ -141,6 +141,13 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def synthetic_batch(B, seed=0):
+    """x ~ N(0,1) [B,540,20] (amplitude-normalised CSI stand-in), y ~ U(0,1) [B,15,2] (key points / 1000)"""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, 540, 20, generator=g), torch.rand(B, 15, 2, generator=g)
+
+
 def workload_name(args):
     return (f'C4 WiFlow data-parallel training step, {args.batch} windows of 540x20 per GPU (fwd+PoseLoss+bwd+clip(1.0)+AdamW, '
             'dropout on: TCN p=0.5 / conv p=0.3, fp32, random-init weights)')
@@ -163,7 +170,6 @@ def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     import wiflow_b200 as wf
     from wiflow_b200 import _lib, ops
-    from oracle import wiflow_oracle as O          # synthetic inputs + cpu_baseline only
 
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
@@ -189,7 +195,7 @@ def run_ours(args, rank, world, local_rank):
     nbatch = 4
     xs, ys = [], []
     for i in range(nbatch):
-        x, y = O.synthetic_batch(B, seed=1000 * rank + i)
+        x, y = synthetic_batch(B, seed=1000 * rank + i)
         xs.append(x.to(dev)); ys.append(y.to(dev))
 
     def barrier():
@@ -345,7 +351,7 @@ def run_ours(args, rank, world, local_rank):
             torch.manual_seed(0)
             m2 = wf.WiFlowPoseModel(dropout=0.5).to(dev)
             t2 = wf.TrainStep(m2, 64)
-            x2, y2 = O.synthetic_batch(64, 5)
+            x2, y2 = synthetic_batch(64, 5)
             x2, y2 = x2.to(dev), y2.to(dev)
             for i in range(5):
                 t2.step(x2, y2)
@@ -354,7 +360,7 @@ def run_ours(args, rank, world, local_rank):
                                     'frac_of_fp32_roofline': 64 * 50 / (ms2 / 1e3) * TRAIN_FLOPS / 1e12 / pk['fp32_tflops']}
             # C3: inference B=8192
             inf = wf.InferStep(model, 8192)
-            x3, _ = O.synthetic_batch(8192, 6)
+            x3, _ = synthetic_batch(8192, 6)
             x3 = x3.to(dev)
             for i in range(3):
                 inf.step(x3)
@@ -363,7 +369,7 @@ def run_ours(args, rank, world, local_rank):
                                       'frac_of_fp32_roofline': 8192 * 5 / (ms3 / 1e3) * FWD_FLOPS / 1e12 / pk['fp32_tflops']}
             # input side: resident-window gather and the train.py:187-193 augmentation, HBM-bound
             from wiflow_b200.utils import augmentation as A
-            from oracle import data_oracle as DO
+            from oracle import data_oracle as DO          # cpu_baseline leg of the input side: the only use of oracle/ in this arm
             nwin = 8192
             resident = torch.randn(nwin, 540, 20, device=dev)
             gidx = [torch.randint(0, nwin, (B,), device=dev) for _ in range(8)]

@@ -197,4 +197,7 @@ def test_host_batches_take_the_staged_upload_path_and_match_device_batches():
         assert (ts._copy_stream is not None) == host
         outs.append((torch.stack(res).cpu(), ts.params.detach().cpu().clone()))
     assert torch.allclose(outs[0][0], outs[1][0], rtol=2e-4, atol=1e-6), (outs[0][0], outs[1][0])
-    assert (outs[0][1] - outs[1][1]).abs().max().item() <= 1e-5
+    # weights after 5 AdamW steps: the two runs differ by the summation order of the atomics in the weight-gradient kernels, and Adam
+    # turns a rounding-level difference of a near-zero gradient into up to lr = 1e-4 per step for that one weight
+    diff = (outs[0][1] - outs[1][1]).abs()
+    assert diff.mean().item() <= 1e-6 and diff.max().item() <= 5e-4, (diff.mean().item(), diff.max().item())

@@ -90,8 +90,10 @@ WF_API int wf_pose_metrics(const float* pred, const float* target, int B, const 
                     float* out, void* scratch, wf_stream_t stream);
 
 /* ---- train.py:105-110,235-236 clip_grad_norm_(max_norm) + torch.optim.AdamW.step over flat buffers ----
- * grads are multiplied by grad_scale first (1/world_size after a sum-allreduce).  state: 64 bytes, zero before the
- * first step (holds the step counter); after the call state[+16] (float) is the pre-clip gradient norm. */
+ * grads are multiplied by grad_scale first (1/world_size after a sum-allreduce).  state: WF_ADAM_STATE_BYTES bytes, zero before
+ * the first step (holds the step counter and the per-block partial sums of the deterministic gradient-norm reduction: ranks that
+ * hold the same all-reduced gradient compute bit-identical updates); after the call state[+16] (float) is the pre-clip norm. */
+#define WF_ADAM_STATE_BYTES (64 + 8 * 256)
 WF_API int wf_clip_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, void* state,
                   float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm, float grad_scale,
                   wf_stream_t stream);

@@ -1,0 +1,182 @@
+// Standalone self-test of the TMA + tcgen05 slab kernels (wf_slabtc.cu) against a CPU loop that restates the ConvP contract:
+//   out[co][opos][n] = epi( bias[co] + sum_tap sum_ci W[tap][co][ci] * pro(in)[ci][ipos(opos,tap)][n] ),
+//   ipos = (opos*pmul + dp[tap]) / pdiv, valid iff divisible and inside [0, Pin).
+// First a structured case (identity weights, position-coded activations) that exposes operand-layout / descriptor mistakes,
+// then random data over the layer shapes of the conv stack (stride 1 / 2 forward, their backward-data forms, every prologue and
+// epilogue mode, ragged column tails).  Built by build.py, run by tests/test_gpu_native.py.
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../wiflow-wifi-pose-estimation-with-spatio-temporal-decoupling_b200/csrc/wf_elem.h"
+
+thread_local int wf_pdl_mode = 0;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 2; } } while (0)
+
+static float frand() { return (float)rand() / RAND_MAX * 2.f - 1.f; }
+static double silu(double x) { return x / (1.0 + exp(-x)); }
+static double dsilu(double x) { double s = 1.0 / (1.0 + exp(-x)); return s * (1.0 + x * (1.0 - s)); }
+
+struct Case {
+    const char* name;
+    int cin, cout, ntaps, pin, pout, pmul, pdiv, B;
+    int dp[3];
+    int pro, epi, mask, bias, accumulate, bwd_image, structured;
+};
+
+template <class T> static T* dev(const std::vector<T>& h)
+{
+    T* d = nullptr;
+    if (cudaMalloc(&d, h.size() * sizeof(T) + 16) != cudaSuccess) return nullptr;
+    cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return d;
+}
+
+static int run_case(const Case& c, int verbose)
+{
+    const int N = c.B * WF_T;
+    // layer weights in the reference layout [cout_l][cin_l][ntaps]; a backward-data case contracts over cout_l
+    const int cout_l = c.bwd_image ? c.cin : c.cout, cin_l = c.bwd_image ? c.cout : c.cin;
+    std::vector<float> WL((size_t)cout_l * cin_l * c.ntaps);
+    for (auto& v : WL) v = frand() * 0.3f;
+    auto Wat = [&](int tap, int co, int ci) -> float {      // weight of (tap, output channel co, input channel ci) of THIS conv
+        return c.bwd_image ? WL[((size_t)ci * cin_l + co) * c.ntaps + tap] : WL[((size_t)co * cin_l + ci) * c.ntaps + tap];
+    };
+    if (c.structured) {
+        for (auto& v : WL) v = 0.f;
+        for (int i = 0; i < c.cin && i < c.cout; ++i) WL[((size_t)i * cin_l + i) * c.ntaps + 0] = 1.f;
+    }
+    std::vector<float> X((size_t)c.cin * c.pin * N), X2(X.size());
+    for (size_t i = 0; i < X.size(); ++i) { X[i] = frand(); X2[i] = frand(); }
+    if (c.structured) for (int ci = 0; ci < c.cin; ++ci) for (int q = 0; q < c.pin; ++q) for (int n = 0; n < N; ++n)
+        X[((size_t)ci * c.pin + q) * N + n] = (float)(ci * 4096 + q * 512 + (n % 512));
+    std::vector<float> pa(c.cin), pb(c.cin), pc(c.cin), pd(c.cin), bias(c.cout), es(c.cout), et(c.cout), em(c.cout);
+    for (int i = 0; i < c.cin; ++i) { pa[i] = 0.5f + 0.5f * fabsf(frand()); pb[i] = frand() * 0.2f; pc[i] = frand() * 0.1f; pd[i] = frand() * 0.3f; }
+    for (int i = 0; i < c.cout; ++i) { bias[i] = c.bias ? frand() : 0.f; es[i] = 0.5f + fabsf(frand()); et[i] = frand() * 0.2f; em[i] = frand() * 0.3f; }
+    std::vector<float> mask((size_t)c.B * c.cin), emask((size_t)c.B * c.cout);
+    for (auto& v : mask) v = (rand() % 10 < 3) ? 0.f : 1.f / 0.7f;
+    for (auto& v : emask) v = (rand() % 10 < 3) ? 0.f : 1.f / 0.7f;
+    std::vector<float> eraw((size_t)c.cout * c.pout * N), out0(eraw.size());
+    for (size_t i = 0; i < eraw.size(); ++i) { eraw[i] = frand(); out0[i] = c.accumulate ? frand() : NAN; }
+
+    // ---- CPU reference ----
+    std::vector<double> Xp(X.size());
+    for (int ci = 0; ci < c.cin; ++ci) for (int q = 0; q < c.pin; ++q) for (int n = 0; n < N; ++n) {
+        const size_t i = ((size_t)ci * c.pin + q) * N + n;
+        double x = X[i];
+        if (c.pro == PRO_BNSILU) { x = silu((double)pa[ci] * ((double)X[i] - pd[ci]) + pb[ci]); if (c.mask) x *= mask[(size_t)(n / WF_T) * c.cin + ci]; }
+        else if (c.pro == PRO_AFFINE) x = (double)pa[ci] * ((double)X[i] - pd[ci]) + pb[ci];
+        else if (c.pro == PRO_BNBWD) x = (double)pa[ci] * X[i] + (double)pb[ci] * ((double)X2[i] - pd[ci]) + pc[ci];
+        Xp[i] = x;
+    }
+    std::vector<double> R(eraw.size()), S0(c.cout, 0.0), S1(c.cout, 0.0);
+    for (int co = 0; co < c.cout; ++co) for (int op = 0; op < c.pout; ++op) for (int n = 0; n < N; ++n) {
+        double a = bias[co];
+        for (int t = 0; t < c.ntaps; ++t) {
+            const int num = op * c.pmul + c.dp[t];
+            if (num < 0 || num % c.pdiv) continue;
+            const int q = num / c.pdiv;
+            if (q >= c.pin) continue;
+            for (int ci = 0; ci < c.cin; ++ci) a += (double)Wat(t, co, ci) * Xp[((size_t)ci * c.pin + q) * N + n];
+        }
+        const size_t o = ((size_t)co * c.pout + op) * N + n;
+        if (c.accumulate) a += out0[o];
+        if (c.epi == EPI_STATS) { S0[co] += a; S1[co] += a * a; }
+        else if (c.epi == EPI_DSILU || c.epi == EPI_DAFF) {
+            const double rw = eraw[o];
+            if (c.epi == EPI_DSILU) a = a * (c.mask ? emask[(size_t)(n / WF_T) * c.cout + co] : 1.0) * dsilu((double)es[co] * (rw - em[co]) + et[co]);
+            S0[co] += a; S1[co] += a * (rw - em[co]);
+        }
+        R[o] = a;
+    }
+
+    // ---- device ----
+    float *dWL = dev(WL), *dX = dev(X), *dX2 = dev(X2), *dpa = dev(pa), *dpb = dev(pb), *dpc = dev(pc), *dpd = dev(pd), *dbias = dev(bias);
+    float *des = dev(es), *det = dev(et), *dem = dev(em), *dmask = dev(mask), *demask = dev(emask), *deraw = dev(eraw), *dout = dev(out0);
+    const long long pf = wf_slabtc_pack_floats(cout_l, cin_l, c.ntaps, false), pbk = wf_slabtc_pack_floats(cout_l, cin_l, c.ntaps, true);
+    float* dP; double* dS;
+    CK(cudaMalloc(&dP, (pf + pbk) * 4)); CK(cudaMalloc(&dS, 2 * c.cout * sizeof(double))); CK(cudaMemset(dS, 0, 2 * c.cout * sizeof(double)));
+    SlabPackTable tab{}; tab.n = 1; tab.e[0] = SlabPackEntry{0, cout_l, cin_l, c.ntaps, 0, pf};
+    CK(wf_launch_slabtc_pack(tab, dWL, dP, 0));
+    ConvP p{};
+    p.in = dX; p.in2 = dX2; p.in_sc = (long long)c.pin * N; p.in_sp = N; p.in_sb = WF_T;
+    p.pro_mode = c.pro; p.pro_a = dpa; p.pro_b = dpb; p.pro_c = dpc; p.pro_d = dpd;
+    if (c.pro == PRO_BNSILU && c.mask) { p.mask = dmask; p.m_sb = c.cin; p.m_sc = 1; p.m_st = 0; }
+    p.wtc = dP + (c.bwd_image ? pf : 0);
+    p.Cin = c.cin; p.Cout = c.cout; p.groups = 1; p.Pin = c.pin; p.Pout = c.pout; p.N = N; p.ntaps = c.ntaps; p.pmul = c.pmul; p.pdiv = c.pdiv;
+    for (int t = 0; t < c.ntaps; ++t) { p.dp[t] = c.dp[t]; p.dn[t] = 0; }
+    p.out = dout; p.out_sc = (long long)c.pout * N; p.out_sp = N; p.out_sb = WF_T;
+    p.bias = c.bias ? dbias : nullptr; p.epi_mode = c.epi; p.accumulate = c.accumulate;
+    p.eraw = deraw; p.e_scale = des; p.e_shift = det; p.e_mean = dem;
+    if (c.epi == EPI_DSILU && c.mask) { p.emask = demask; p.em_sb = c.cout; p.em_sc = 1; p.em_st = 0; }
+    p.stat0 = dS; p.stat1 = dS + c.cout;
+    if (!wf_slabtc_conv_ok(p)) { printf("%-28s: shape declined by wf_slabtc_conv_ok -> FAIL\n", c.name); return 1; }
+    CK(wf_launch_slabtc_conv(p, 0));
+    CK(cudaDeviceSynchronize());
+    std::vector<float> D(R.size()); std::vector<double> S(2 * c.cout);
+    CK(cudaMemcpy(D.data(), dout, D.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(S.data(), dS, S.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    double maxe = 0, maxr = 0; int bad = 0;
+    for (size_t i = 0; i < D.size(); ++i) maxr = fmax(maxr, fabs(R[i]));
+    for (size_t i = 0; i < D.size(); ++i) {
+        double e = fabs((double)D[i] - R[i]); if (!(e <= 1e30)) e = 1e30;
+        maxe = fmax(maxe, e);
+        if (e > 2e-5 * maxr + 1e-30 && bad < verbose) {
+            const int n = (int)(i % N), op = (int)((i / N) % c.pout), co = (int)(i / ((size_t)N * c.pout));
+            printf("   mismatch out[%d][%d][%d] = %g expected %g", co, op, n, D[i], R[i]);
+            if (c.structured) { const int v = (int)lrintf(D[i]); printf("  (= X[c %d][q %d][n %d])", v / 4096, (v / 512) % 8, v % 512); }
+            printf("\n"); ++bad;
+        }
+    }
+    double se = 0;
+    if (c.epi != EPI_STORE) for (int co = 0; co < c.cout; ++co) {
+        double sa0 = 0, sa1 = 0;
+        for (int op = 0; op < c.pout; ++op) for (int n = 0; n < N; ++n) { const size_t o = ((size_t)co * c.pout + op) * N + n; sa0 += fabs(R[o]); sa1 += c.epi == EPI_STATS ? R[o] * R[o] : fabs(R[o] * (eraw[o] - em[co])); }
+        se = fmax(se, fabs(S[co] - S0[co]) / (1e-30 + sa0));
+        se = fmax(se, fabs(S[c.cout + co] - S1[co]) / (1e-30 + sa1));
+    }
+    const bool ok = maxe <= 2e-5 * maxr && se < 1e-5;
+    printf("%-28s: max abs err %.3g (max |ref| %.3g, rel %.3g)  stats rel err %.3g -> %s\n", c.name, maxe, maxr, maxe / (maxr + 1e-30), se, ok ? "ok" : "FAIL");
+    cudaFree(dWL); cudaFree(dX); cudaFree(dX2); cudaFree(dpa); cudaFree(dpb); cudaFree(dpc); cudaFree(dpd); cudaFree(dbias); cudaFree(des); cudaFree(det);
+    cudaFree(dem); cudaFree(dmask); cudaFree(demask); cudaFree(deraw); cudaFree(dout); cudaFree(dP); cudaFree(dS);
+    return ok ? 0 : 1;
+}
+
+int main(int argc, char** argv)
+{
+    const int verbose = argc > 1 ? atoi(argv[1]) : 6;
+    const int only = argc > 2 ? atoi(argv[2]) : -1;
+    srand(1234);
+    const Case cases[] = {
+        // name                         cin cout taps pin pout pmul pdiv  B   dp          pro          epi        mask bias acc bwd structured
+        {"structured 8->8 1 tap",         8,  8, 1,  1,  1, 1, 1,   7, {0, 0, 0},   PRO_NONE,   EPI_STORE, 0, 0, 0, 0, 1},
+        {"structured 64->64 1 tap",      64, 64, 1,  2,  2, 1, 1,   7, {0, 0, 0},   PRO_NONE,   EPI_STORE, 0, 0, 0, 0, 1},
+        {"8->8 s1 P=12",                  8,  8, 3, 12, 12, 1, 1,  13, {-1, 0, 1},  PRO_NONE,   EPI_STATS, 0, 1, 0, 0, 0},
+        {"8->8 s1 P=240 bnsilu mask",     8,  8, 3, 240, 240, 1, 1, 16, {-1, 0, 1}, PRO_BNSILU, EPI_STATS, 1, 1, 0, 0, 0},
+        {"8->16 s2 P=120->60",            8, 16, 3, 120, 60, 2, 1, 11, {-1, 0, 1},  PRO_NONE,   EPI_STATS, 0, 1, 0, 0, 0},
+        {"8->16 s2 shortcut 1 tap",       8, 16, 1, 120, 60, 2, 1, 11, {0, 0, 0},   PRO_NONE,   EPI_STATS, 0, 0, 0, 0, 0},
+        {"16->16 s1 P=60 bnsilu",        16, 16, 3, 60, 60, 1, 1,  9, {-1, 0, 1},   PRO_BNSILU, EPI_STATS, 1, 1, 0, 0, 0},
+        {"32->64 s2 P=30->15",           32, 64, 3, 30, 15, 2, 1, 40, {-1, 0, 1},   PRO_NONE,   EPI_STATS, 0, 1, 0, 0, 0},
+        {"64->64 s1 P=15 bnsilu mask",   64, 64, 3, 15, 15, 1, 1, 64, {-1, 0, 1},   PRO_BNSILU, EPI_STATS, 1, 1, 0, 0, 0},
+        {"64->64 s1 P=15 eval store",    64, 64, 3, 15, 15, 1, 1,  5, {-1, 0, 1},   PRO_BNSILU, EPI_STORE, 0, 1, 0, 0, 0},
+        {"dgrad 64->64 s1 dsilu mask",   64, 64, 3, 15, 15, 1, 1, 33, {1, 0, -1},   PRO_BNBWD,  EPI_DSILU, 1, 0, 0, 1, 0},
+        {"dgrad 64->32 s2 15->30 store", 64, 32, 3, 15, 30, 1, 2, 21, {1, 0, -1},   PRO_BNBWD,  EPI_STORE, 0, 0, 1, 1, 0},
+        {"dgrad 16->8 s2 1 tap store",   16,  8, 1, 60, 120, 1, 2, 10, {0, 0, 0},   PRO_BNBWD,  EPI_STORE, 0, 0, 0, 1, 0},
+        {"dgrad 8->8 s1 P=240 dsilu",     8,  8, 3, 240, 240, 1, 1, 12, {1, 0, -1}, PRO_BNBWD,  EPI_DSILU, 1, 0, 0, 1, 0},
+        {"dgrad 32->32 s1 daff",         32, 32, 3, 30, 30, 1, 1, 17, {1, 0, -1},   PRO_BNBWD,  EPI_DAFF,  0, 0, 0, 1, 0},
+        {"affine 64->32 1 tap",          64, 32, 1, 15, 15, 1, 1, 19, {0, 0, 0},    PRO_AFFINE, EPI_STATS, 0, 1, 0, 0, 0},
+        {"8->8 s1 P=240 B=256",           8,  8, 3, 240, 240, 1, 1, 256, {-1, 0, 1}, PRO_BNSILU, EPI_STATS, 1, 1, 0, 0, 0},
+        {"64->64 s1 P=15 B=512",         64, 64, 3, 15, 15, 1, 1, 512, {-1, 0, 1},  PRO_BNSILU, EPI_STATS, 1, 1, 0, 0, 0},
+    };
+    int fails = 0, idx = 0;
+    for (const Case& c : cases) {
+        if (only >= 0 && idx++ != only) continue;
+        const int r = run_case(c, verbose);
+        if (r == 2) { printf("SELFTEST ABORTED (CUDA error)\n"); return 2; }
+        fails += r;
+    }
+    printf(fails ? "SLAB SELFTEST FAILED (%d cases)\n" : "SLAB SELFTEST PASSED\n", fails);
+    return fails ? 1 : 0;
+}

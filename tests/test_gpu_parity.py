@@ -180,7 +180,7 @@ def test_train_step_matches_reference_fixture(wf, golden, tag, use_masks):
     from wiflow_b200 import ops
     flat, _, _ = model._wf_state()
     m, v = torch.zeros_like(flat), torch.zeros_like(flat)
-    state = torch.zeros(8, device='cuda', dtype=torch.float64)
+    state = ops.adam_state('cuda')
     ops.clip_adamw(flat, grads, m, v, state, 1e-4, 0.9, 0.999, 1e-8, 5e-5, 1.0, 1.0)
     torch.cuda.synchronize()
     gn = state.view(torch.float32)[4].item()

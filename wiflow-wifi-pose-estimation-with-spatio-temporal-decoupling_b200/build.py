@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-SOURCES = ['wf_conv.cu', 'wf_group.cu', 'wf_slide.cu', 'wf_tc.cu', 'wf_thin.cu', 'wf_elem.cu', 'wf_attn.cu', 'wf_data.cu', 'wf_model.cu']
+SOURCES = ['wf_conv.cu', 'wf_group.cu', 'wf_slide.cu', 'wf_slabtc.cu', 'wf_tc.cu', 'wf_thin.cu', 'wf_elem.cu', 'wf_attn.cu', 'wf_data.cu', 'wf_model.cu']
 LIB = os.path.join(HERE, 'libwiflow_b200.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']
@@ -50,6 +50,12 @@ def build(force=False, verbose=False):
     if os.path.exists(st_src) and (force or procs or any(_newer(d, st_exe) for d in [st_src, tc_obj])):
         subprocess.check_call([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O2', '-std=c++17', '-Wno-deprecated-gpu-targets',
                                '-o', st_exe, st_src, tc_obj, '-lcudart'])
+    sl_src = os.path.join(HERE, '..', 'tests', 'native', 'slab_selftest.cu')
+    sl_exe = os.path.join(HERE, '..', 'tests', 'native', 'slab_selftest')
+    sl_obj = os.path.join(CSRC, 'wf_slabtc.o')
+    if os.path.exists(sl_src) and (force or procs or any(_newer(d, sl_exe) for d in [sl_src, sl_obj])):
+        subprocess.check_call([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O2', '-std=c++17', '-Wno-deprecated-gpu-targets',
+                               '-o', sl_exe, sl_src, sl_obj, '-lcudart'])
     return LIB
 
 

@@ -466,6 +466,7 @@ static cudaError_t launch_conv_t(const ConvP& p, cudaStream_t st)
 
 cudaError_t wf_launch_conv(const ConvP& p, cudaStream_t st)
 {
+    if (wf_slabtc_conv_ok(p)) return wf_launch_slabtc_conv(p, st);
     if (wf_slide_conv_ok(p)) return wf_launch_slide_conv(p, st);
     if (wf_thin_conv_ok(p)) return wf_launch_thin_conv(p, st);
     if (wf_group_conv_ok(p)) return wf_launch_group_conv(p, st);

@@ -399,8 +399,11 @@ __global__ void pack_weights_kernel(PackTable tab, const float* params, float* p
 // ---------------------------------------------------------------------------------------------------------
 // clip_grad_norm_(max_norm) + AdamW over the flat parameter buffer (train.py:105-110,235-236)
 // ---------------------------------------------------------------------------------------------------------
+// Deterministic: a fixed grid (WF_SUMSQ_BLOCKS, independent of the SM count), a fixed element -> thread assignment, a fixed
+// reduction tree per block and one partial per block; adamw_prep_kernel adds the partials in index order.  No atomics, so every
+// rank of a data-parallel job computes bit-identical clip coefficients from the all-reduced gradient (replicas stay in lock step).
 template <int NT>
-__global__ void __launch_bounds__(NT) sumsq_kernel(const float* g, long long n, double* acc)
+__global__ void __launch_bounds__(NT) sumsq_kernel(const float* g, long long n, double* partial)
 {
     wf_pdl_enter();
     float a = 0.f, b = 0.f;
@@ -419,7 +422,7 @@ __global__ void __launch_bounds__(NT) sumsq_kernel(const float* g, long long n, 
     if (threadIdx.x == 0) {
         double s = 0;
         for (int i = 0; i < NT / 32; ++i) s += red[i];
-        atomicAdd(acc, s);
+        partial[blockIdx.x] = s;
     }
 }
 
@@ -427,6 +430,9 @@ __global__ void adamw_prep_kernel(AdamState* st, float lr, float b1, float b2, f
 {
     wf_pdl_enter();
     st->step += 1;
+    double ss = 0;
+    for (int i = 0; i < WF_SUMSQ_BLOCKS; ++i) ss += st->partial[i];
+    st->sumsq = ss;
     const double gn = sqrt(st->sumsq) * grad_scale;
     st->grad_norm = (float)gn;
     float coef = 1.f;
@@ -435,7 +441,6 @@ __global__ void adamw_prep_kernel(AdamState* st, float lr, float b1, float b2, f
     const double bc1 = 1.0 - pow((double)b1, (double)st->step), bc2 = 1.0 - pow((double)b2, (double)st->step);
     st->step_size = (float)(lr / bc1);
     st->inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
-    st->sumsq = 0;
 }
 
 __global__ void adamw_kernel(float* p, const float* g, float* m, float* v, long long n, const AdamState* st,
@@ -564,7 +569,7 @@ cudaError_t wf_launch_pack(const PackTable& tab, const float* params, float* pac
 cudaError_t wf_launch_adamw(float* p, const float* g, float* m, float* v, long long n, AdamState* state, float lr, float b1, float b2,
                             float eps, float wd, float max_norm, float grad_scale, int num_sms, cudaStream_t st)
 {
-    wf_launch_pdl(sumsq_kernel<256>, dim3(num_sms * 2), dim3(256), 0, st, g, n, &state->sumsq);
+    wf_launch_pdl(sumsq_kernel<256>, dim3(WF_SUMSQ_BLOCKS), dim3(256), 0, st, g, n, &state->partial[0]);
     wf_launch_pdl(adamw_prep_kernel, dim3(1), dim3(1), 0, st, state, lr, b1, b2, max_norm, grad_scale);
     wf_launch_pdl(adamw_kernel, dim3(num_sms * 4), dim3(256), 0, st, p, g, m, v, n, state, lr, b1, b2, eps, wd);
     return cudaGetLastError();

@@ -46,7 +46,12 @@ struct PackTable { int n; PackEntry e[WF_MAX_CONV]; };
 struct TcPackEntry { int param_off, cout, cin; long long fwd_off, bwd_off; };
 struct TcPackTable { int n; TcPackEntry e[WF_MAX_CONV]; };
 
-struct AdamState { double sumsq; long long step; float grad_norm, clip_coef, step_size, inv_bc2_sqrt; };
+struct SlabPackEntry { int param_off, cout, cin, ntaps; long long fwd_off, bwd_off; };
+struct SlabPackTable { int n; SlabPackEntry e[WF_MAX_CONV]; };
+
+#define WF_SUMSQ_BLOCKS 256
+// first 64 bytes: scalars (step counter persists between calls); then one partial sum of squares per block of sumsq_kernel
+struct AdamState { double sumsq; long long step; float grad_norm, clip_coef, step_size, inv_bc2_sqrt; double pad_[4]; double partial[WF_SUMSQ_BLOCKS]; };
 
 // attention (wf_attn.cu)
 struct AttnP {
@@ -81,6 +86,12 @@ cudaError_t wf_launch_slide_conv(const ConvP& p, cudaStream_t st);
 bool wf_slide_conv_is_thin(const ConvP& p);
 bool wf_slide_wgrad_ok(const WgradP& p);
 cudaError_t wf_launch_slide_wgrad(const WgradP& p, int num_sms, cudaStream_t st);
+// TMA + tcgen05 path for position-tap convs (wf_slabtc.cu)
+bool wf_slabtc_shape_ok(int cin, int cout, int groups, int ntaps, const int* dn);
+long long wf_slabtc_pack_floats(int cout, int cin, int ntaps, bool bwd);
+cudaError_t wf_launch_slabtc_pack(const SlabPackTable& tab, const float* params, float* packed, cudaStream_t st);
+bool wf_slabtc_conv_ok(const ConvP& p);
+cudaError_t wf_launch_slabtc_conv(const ConvP& p, cudaStream_t st);
 // tcgen05 pointwise-conv path (wf_tc.cu)
 long long wf_tc_pack_floats(int m, int k);
 cudaError_t wf_launch_tc_pack(const TcPackTable& tab, const float* params, float* packed, cudaStream_t st);

@@ -66,6 +66,8 @@ struct ConvUnit {
     long long fpack, bpack;   // float offsets into the packed-weight region
     bool tc;                  // pointwise conv wide enough for the tcgen05 kernels (wf_tc.cu)
     long long tc_fpack, tc_bpack;
+    bool sl;                  // position-tap conv of the conv stack on the TMA + tcgen05 slab kernels (wf_slabtc.cu)
+    long long sl_fpack, sl_bpack;
     float *raw, *dy;          // [groups*cout_g][pout][N]
     long long numel_per_n() const { return (long long)groups * cout_g * pout; }
 };
@@ -96,6 +98,7 @@ struct Net {
     // workspace regions
     float* packed = nullptr; long long packed_floats = 0;
     float* tcpacked = nullptr; long long tcpacked_floats = 0;
+    float* slpacked = nullptr; long long slpacked_floats = 0;
     char* fstats = nullptr; size_t fstats_bytes = 0;
     char* bstats = nullptr; size_t bstats_bytes = 0;
     float* dpred_buf = nullptr;
@@ -138,6 +141,7 @@ int add_conv(Net& n, const std::string& name, int cout_total, int cin_g, int gro
     c.b_kpad = round_up(c.cout_g, wf_conv_bk_for(cin_g));
     c.b_mpad = round_up(cin_g, wf_conv_bm_for(cin_g));
     c.tc = g_use_tc && groups == 1 && ntaps == 1 && stride == 1 && pin == pout && cin_g >= 64 && cout_total >= 64;
+    c.sl = !c.tc && pin > 1 && wf_slabtc_shape_ok(cin_g, cout_total, groups, ntaps, c.dnf);
     n.conv.push_back(c);
     return (int)n.conv.size() - 1;
 }
@@ -303,6 +307,14 @@ size_t layout(Net& n, int B, int flags, char* base)
     }
     n.tcpacked_floats = tf;
     n.tcpacked = bp.take<float>(tf);
+    long long sf = 0;
+    for (auto& c : n.conv) {
+        if (!c.sl) continue;
+        c.sl_fpack = sf; sf += wf_slabtc_pack_floats(c.cout_g, c.cin_g, c.ntaps, false);
+        c.sl_bpack = sf; sf += wf_slabtc_pack_floats(c.cout_g, c.cin_g, c.ntaps, true);
+    }
+    n.slpacked_floats = sf;
+    n.slpacked = bp.take<float>(sf);
     // BN statistics (fp64) and coefficients
     size_t s0 = (bp.off + 255) & ~(size_t)255;
     for (auto& b : n.bn) { b.f0 = bp.take<double>(b.C); b.f1 = bp.take<double>(b.C); }
@@ -444,7 +456,8 @@ void fwd_conv(Ctx& c, int ui, Act in, Pro pro)
     p.bias = u.b_off >= 0 ? c.params + u.b_off : nullptr;
     p.epi_mode = c.train ? EPI_STATS : EPI_STORE;
     p.stat0 = bo.f0; p.stat1 = bo.f1;
-    Scope sc(c, std::string(u.tc ? "tc_fwd " : wf_slide_conv_ok(p) ? (wf_slide_conv_is_thin(p) ? "slidethin_fwd " : "slide_fwd ") : wf_thin_conv_ok(p) ? "thin_fwd " : wf_group_conv_ok(p) ? "group_fwd " : "conv_fwd ") + u.name, conv_flops(u, c.N));
+    if (u.sl) p.wtc = c.n.slpacked + u.sl_fpack;
+    Scope sc(c, std::string(u.tc ? "tc_fwd " : wf_slabtc_conv_ok(p) ? "slab_fwd " : wf_slide_conv_ok(p) ? (wf_slide_conv_is_thin(p) ? "slidethin_fwd " : "slide_fwd ") : wf_thin_conv_ok(p) ? "thin_fwd " : wf_group_conv_ok(p) ? "group_fwd " : "conv_fwd ") + u.name, conv_flops(u, c.N));
     if (u.tc) { p.wtc = c.n.tcpacked + u.tc_fpack; p.tc_kt = (u.cin_g + TC_KC - 1) / TC_KC; c.ck(wf_launch_tc_conv(p, c.sms, c.st)); }
     else c.ck(wf_launch_conv(p, c.st));
 }
@@ -513,7 +526,8 @@ void dgrad_conv(Ctx& c, int ui, float* out, int epi, int src_bn, const float* sr
         p.emask = emask.p; p.em_sb = emask.sb; p.em_sc = emask.sc; p.em_st = emask.st;
         p.stat0 = bs.b0; p.stat1 = bs.b1;
     }
-    Scope sc(c, std::string(u.tc ? "tc_dgrad " : wf_slide_conv_ok(p) ? (wf_slide_conv_is_thin(p) ? "slidethin_dgrad " : "slide_dgrad ") : wf_thin_conv_ok(p) ? "thin_dgrad " : wf_group_conv_ok(p) ? "group_dgrad " : "conv_dgrad ") + u.name, conv_flops(u, c.N));
+    if (u.sl) p.wtc = c.n.slpacked + u.sl_bpack;
+    Scope sc(c, std::string(u.tc ? "tc_dgrad " : wf_slabtc_conv_ok(p) ? "slab_dgrad " : wf_slide_conv_ok(p) ? (wf_slide_conv_is_thin(p) ? "slidethin_dgrad " : "slide_dgrad ") : wf_thin_conv_ok(p) ? "thin_dgrad " : wf_group_conv_ok(p) ? "group_dgrad " : "conv_dgrad ") + u.name, conv_flops(u, c.N));
     if (u.tc) { p.wtc = c.n.tcpacked + u.tc_bpack; p.tc_kt = (u.cout_g + TC_KC - 1) / TC_KC; c.ck(wf_launch_tc_conv(p, c.sms, c.st)); }
     else c.ck(wf_launch_conv(p, c.st));
 }
@@ -770,6 +784,10 @@ void prepare_weights(Ctx& c)
     for (const ConvUnit& u : n.conv)
         if (u.tc) tt.e[tt.n++] = TcPackEntry{(int)u.w_off, u.cout_g, u.cin_g, u.tc_fpack, u.tc_bpack};
     c.ck(wf_launch_tc_pack(tt, c.params, n.tcpacked, c.st));
+    SlabPackTable sp{};
+    for (const ConvUnit& u : n.conv)
+        if (u.sl) sp.e[sp.n++] = SlabPackEntry{(int)u.w_off, u.cout_g, u.cin_g, u.ntaps, u.sl_fpack, u.sl_bpack};
+    c.ck(wf_launch_slabtc_pack(sp, c.params, n.slpacked, c.st));
 }
 
 void eval_coefs(Ctx& c)

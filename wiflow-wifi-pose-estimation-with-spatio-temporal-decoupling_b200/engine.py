@@ -61,7 +61,7 @@ class TrainStep:
         self.grads = torch.zeros(n, device=dev)
         self.exp_avg = torch.zeros(n, device=dev)
         self.exp_avg_sq = torch.zeros(n, device=dev)
-        self.adam_state = torch.zeros(8, device=dev, dtype=torch.float64)
+        self.adam_state = ops.adam_state(dev)
         self.flags = _lib.FLAG_TRAIN | _lib.FLAG_SAVE
         self.ws = torch.empty(ops.workspace_bytes(MODEL_DESC, self.B, self.flags), device=dev, dtype=torch.uint8)
         self.x = torch.zeros(self.B, 540, 20, device=dev)

@@ -146,10 +146,20 @@ def _(pred, target, thresholds, use_torso_norm, scratch):
     return pred.new_empty(len(thresholds) + 1)
 
 
+ADAM_STATE_BYTES = 64 + 8 * 256          # WF_ADAM_STATE_BYTES of include/wiflow_b200.h
+
+
+def adam_state(device) -> torch.Tensor:
+    """zeroed optimizer-state block of wf_clip_adamw: step counter, clip results, per-block partial sums of the gradient norm"""
+    return torch.zeros(ADAM_STATE_BYTES // 8, device=device, dtype=torch.float64)
+
+
 @torch.library.custom_op('wiflow_b200::clip_adamw', mutates_args=('params', 'exp_avg', 'exp_avg_sq', 'state'))
 def clip_adamw(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, state: torch.Tensor,
                lr: float, beta1: float, beta2: float, eps: float, weight_decay: float, max_norm: float, grad_scale: float) -> None:
     _need_cuda(params, grads, exp_avg, exp_avg_sq, state)
+    if state.numel() * state.element_size() < ADAM_STATE_BYTES:
+        raise RuntimeError(f'clip_adamw: state must hold {ADAM_STATE_BYTES} bytes (adam_state(device) allocates it)')
     with torch.cuda.device(params.device):
         rc = _lib.lib().wf_clip_adamw(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(), _ptr(state),
                                       lr, beta1, beta2, eps, weight_decay, max_norm, grad_scale, _stream())

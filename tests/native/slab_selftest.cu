@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
+#include <cstring>
 #include <vector>
 #include <cuda_runtime.h>
 #include "../../wiflow-wifi-pose-estimation-with-spatio-temporal-decoupling_b200/csrc/wf_elem.h"
@@ -33,6 +34,8 @@ template <class T> static T* dev(const std::vector<T>& h)
     cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
     return d;
 }
+
+static int g_bench = 0;          // bench mode: time the launch, skip the CPU reference
 
 static int run_case(const Case& c, int verbose)
 {
@@ -62,7 +65,8 @@ static int run_case(const Case& c, int verbose)
     for (size_t i = 0; i < eraw.size(); ++i) { eraw[i] = frand(); out0[i] = c.accumulate ? frand() : NAN; }
 
     // ---- CPU reference ----
-    std::vector<double> Xp(X.size());
+    std::vector<double> Xp(g_bench ? 0 : X.size());
+    if (!g_bench)
     for (int ci = 0; ci < c.cin; ++ci) for (int q = 0; q < c.pin; ++q) for (int n = 0; n < N; ++n) {
         const size_t i = ((size_t)ci * c.pin + q) * N + n;
         double x = X[i];
@@ -72,6 +76,7 @@ static int run_case(const Case& c, int verbose)
         Xp[i] = x;
     }
     std::vector<double> R(eraw.size()), S0(c.cout, 0.0), S1(c.cout, 0.0);
+    if (!g_bench)
     for (int co = 0; co < c.cout; ++co) for (int op = 0; op < c.pout; ++op) for (int n = 0; n < N; ++n) {
         double a = bias[co];
         for (int t = 0; t < c.ntaps; ++t) {
@@ -115,6 +120,24 @@ static int run_case(const Case& c, int verbose)
     if (!wf_slabtc_conv_ok(p)) { printf("%-28s: shape declined by wf_slabtc_conv_ok -> FAIL\n", c.name); return 1; }
     CK(wf_launch_slabtc_conv(p, 0));
     CK(cudaDeviceSynchronize());
+    if (g_bench) {
+        static const int dbgs[] = {0, 55, 2, 6, 4, 1};
+        printf("%-30s", c.name);
+        for (int d : dbgs) {
+            char buf[16]; snprintf(buf, sizeof buf, "%d", d); setenv("WF_SLABTC_DBG", buf, 1);
+            cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+            CK(wf_launch_slabtc_conv(p, 0));
+            cudaEventRecord(e0);
+            for (int it = 0; it < 20; ++it) CK(wf_launch_slabtc_conv(p, 0));
+            cudaEventRecord(e1);
+            CK(cudaDeviceSynchronize());
+            float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+            printf(" dbg%d %7.1fus", d, ms * 50.f);
+        }
+        printf("\n");
+        unsetenv("WF_SLABTC_DBG");
+        return 0;
+    }
     std::vector<float> D(R.size()); std::vector<double> S(2 * c.cout);
     CK(cudaMemcpy(D.data(), dout, D.size() * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(S.data(), dS, S.size() * sizeof(double), cudaMemcpyDeviceToHost));
@@ -170,6 +193,24 @@ int main(int argc, char** argv)
         {"8->8 s1 P=240 B=256",           8,  8, 3, 240, 240, 1, 1, 256, {-1, 0, 1}, PRO_BNSILU, EPI_STATS, 1, 1, 0, 0, 0},
         {"64->64 s1 P=15 B=512",         64, 64, 3, 15, 15, 1, 1, 512, {-1, 0, 1},  PRO_BNSILU, EPI_STATS, 1, 1, 0, 0, 0},
     };
+    if (argc > 1 && !strcmp(argv[1], "bench")) {
+        g_bench = 1;
+        printf("per-launch time; dbg bits: 1 no transform, 2 no MMA, 4 no epilogue memory traffic, 8 hi*hi MMA only\n");
+        const Case bc[] = {
+            {"64->64 s1 P=15 B=128 fwd",     64, 64, 3, 15, 15, 1, 1, 128, {-1, 0, 1},   PRO_BNSILU, EPI_STATS, 1, 1, 0, 0, 0},
+            {"64->64 s1 P=15 B=256 fwd",     64, 64, 3, 15, 15, 1, 1, 256, {-1, 0, 1},   PRO_BNSILU, EPI_STATS, 1, 1, 0, 0, 0},
+            {"64->64 s1 P=15 B=512 fwd",     64, 64, 3, 15, 15, 1, 1, 512, {-1, 0, 1},   PRO_BNSILU, EPI_STATS, 1, 1, 0, 0, 0},
+            {"64->64 s1 P=15 B=2048 fwd",    64, 64, 3, 15, 15, 1, 1, 2048, {-1, 0, 1},  PRO_BNSILU, EPI_STATS, 1, 1, 0, 0, 0},
+            {"8->8 s1 P=240 B=256 fwd",       8,  8, 3, 240, 240, 1, 1, 256, {-1, 0, 1}, PRO_BNSILU, EPI_STATS, 1, 1, 0, 0, 0},
+            {"8->8 s1 P=240 B=1024 fwd",      8,  8, 3, 240, 240, 1, 1, 1024, {-1, 0, 1}, PRO_BNSILU, EPI_STATS, 1, 1, 0, 0, 0},
+            {"16->16 s1 P=60 B=1024 fwd",    16, 16, 3, 60, 60, 1, 1, 1024, {-1, 0, 1},   PRO_BNSILU, EPI_STATS, 1, 1, 0, 0, 0},
+            {"64->64 s1 P=15 B=1024 fwd",    64, 64, 3, 15, 15, 1, 1, 1024, {-1, 0, 1},   PRO_BNSILU, EPI_STATS, 1, 1, 0, 0, 0},
+            {"64->64 s1 P=15 B=1024 dgrad",  64, 64, 3, 15, 15, 1, 1, 1024, {1, 0, -1},   PRO_BNBWD,  EPI_DSILU, 1, 0, 0, 1, 0},
+            {"8->8 s1 P=240 B=1024 dgrad",    8,  8, 3, 240, 240, 1, 1, 1024, {1, 0, -1}, PRO_BNBWD,  EPI_DSILU, 1, 0, 0, 1, 0},
+        };
+        for (const Case& c : bc) if (run_case(c, 0) == 2) return 2;
+        return 0;
+    }
     int fails = 0, idx = 0;
     for (const Case& c : cases) {
         if (only >= 0 && idx++ != only) continue;

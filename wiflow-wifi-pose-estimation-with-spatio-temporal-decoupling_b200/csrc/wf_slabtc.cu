@@ -18,7 +18,7 @@
 // flight (2-3 stages), not the tap window, which is what lets 64-channel layers keep 128-column tiles plus all tap weights
 // (hi and lo, 96 KB) in the 227 KB of shared memory.
 //
-// Warp roles (320 threads): warp 8 lane 0 issues the TMA loads, warp 9 lane 0 issues tcgen05.mma, warps 0-7 are workers:
+// Warp roles (672 threads): warp 16 lane 0 issues the TMA loads, lane 0 of warps 17-20 issue tcgen05.mma, warps 0-15 are workers:
 //   * transform: the raw slab (TMA) is rewritten IN PLACE as the activated operand -- BatchNorm+SiLU+Dropout2d, BatchNorm only,
 //     or BatchNorm-backward of (dy, raw) -- split into tf32 hi / lo images (3xTF32, fp32 parity: a*b ~ a_lo*b_hi + a_hi*b_lo +
 //     a_hi*b_hi).  Addresses are linear (the swizzle permutes 32-byte chunks inside a row, a row is one channel), so the
@@ -28,6 +28,7 @@
 //     are reduced across lanes once, at the end.
 // Work is the flattened list of (column tile, output position) units cut into one contiguous run per CTA (persistent, 1 CTA/SM).
 #include <cuda.h>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include "wf_tc.cuh"
@@ -39,21 +40,26 @@ namespace {
 using namespace tc;
 
 constexpr int TILE = 128;                 // columns per tile = UMMA M
-constexpr int NWORK = 256;                // worker threads (warps 0-7)
+constexpr int NWORK = 512;                // worker threads (warps 0-15)
 constexpr int NWW = NWORK / 32;
-constexpr int NTHR = NWORK + 64;          // + TMA warp + MMA warp
+constexpr int NI = 3;                     // MMA-issuing warps
+constexpr int NTHR = NWORK + 32 + 32 * NI; // + TMA warp + MMA-issuing warps
 constexpr int MAXACC = 16;                // accumulator slots (barriers) at most
 constexpr int NGD = 4;                    // ring of "group done" barriers
 constexpr int MAXNS = 4;
-constexpr int MAXJ = 8;                   // float4 chunks per worker thread and stage (R = 64 rows)
+constexpr int MAXJ = 4;                   // float4 chunks per worker thread and stage (R = 64 rows)
 
 struct SlabGeom {
     int R, PBI, NS, NPAD, NACC, tmem_cols, ntiles;
     int half_bytes;                       // one of hi/lo of a stage: 4 * R * 128
-    int w_half_bytes;                     // one of hi/lo of all tap weights: ntaps * NPAD * Cin * 4
+    int w_img_bytes;                      // one weight image: ntaps * 2*NPAD rows (hi rows, lo rows per tap) * Cin * 4
+    int w_bytes;                          // images resident in shared memory: 1 (per-tap MMAs) or 2 (stacked-tap MMAs need the zero-padded image)
+    int W;                                // accumulator slots released per mbarrier test of the MMA thread
+    int stack;                            // all taps of a slab in one MMA pair (N = ntaps * 2*NPAD <= 256)
     int dpmin, dpmax;
     int lbo_mn, sbo_mn;                   // MN-major SW128_BASE32B descriptor strides: 32-column blocks / 4-row K groups of the activation operand (bytes)
     long long units;                      // ntiles * Pout
+    int dbg;                              // measurement switches (WF_SLABTC_DBG): 1 no transform, 2 no MMA, 4 no epilogue memory traffic, 8 hi*hi only, 16 no TMA, 32 no TMEM load
 };
 
 // ---- TMA tensor load (3-D tile), completion on an mbarrier ----
@@ -79,8 +85,27 @@ __device__ __forceinline__ uint64_t umma_desc_l(uint32_t saddr, uint32_t lbo_byt
     return d;
 }
 
+// one lane polls the mbarrier, the warp reconverges behind it: 32 lanes spinning on try_wait only load the barrier unit
+__device__ __forceinline__ void warp_wait(uint32_t bar, uint32_t parity, int lane)
+{
+    if (lane == 0) mbar_wait(bar, parity);
+    __syncwarp();
+}
+
+// D[tmem] += A[smem] * B[smem], issued by the lanes whose `lead` is non-zero (one per warp); operands are warp-uniform
+__device__ __forceinline__ void umma_tf32_pred(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t lead)
+{
+    asm volatile("{\n\t.reg .pred pl, pa;\n\tsetp.ne.b32 pl, %4, 0;\n\tsetp.eq.b32 pa, 0, 0;\n\t@pl tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, pa;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(lead) : "memory");
+}
+
 // TMEM -> registers, 32 lanes x NV consecutive columns (thread = lane)
 template <int NV> __device__ __forceinline__ void tmem_ldn(uint32_t taddr, float* v);
+template <> __device__ __forceinline__ void tmem_ldn<2>(uint32_t taddr, float* v)
+{
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
 template <> __device__ __forceinline__ void tmem_ldn<4>(uint32_t taddr, float* v)
 {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -101,6 +126,22 @@ template <> __device__ __forceinline__ void tmem_ldn<16>(uint32_t taddr, float* 
                    "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr) : "memory");
 }
 
+// zero NV consecutive TMEM columns of this warp's 32 lanes
+template <int NV> __device__ __forceinline__ void tmem_zero(uint32_t taddr);
+template <> __device__ __forceinline__ void tmem_zero<2>(uint32_t taddr)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %1};" ::"r"(taddr), "r"(0u) : "memory");
+}
+template <> __device__ __forceinline__ void tmem_zero<4>(uint32_t taddr)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %1, %1, %1};" ::"r"(taddr), "r"(0u) : "memory");
+}
+template <> __device__ __forceinline__ void tmem_zero<8>(uint32_t taddr)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ float4 lds4(uint32_t a)
 {
     float4 v;
@@ -114,7 +155,6 @@ __device__ __forceinline__ void sts4(uint32_t a, float4 v)
 
 // ---- position bookkeeping shared by the three roles (all deterministic functions of the launch geometry) ----
 struct Seg { int ct, oa, ob, qa, qb; };
-__device__ __forceinline__ int fdiv(int x, int d) { return d == 1 ? x : (x >> 1); }                       // floor(x / d), d in {1, 2}
 __device__ __forceinline__ void seg_make(const ConvP& p, const SlabGeom& g, long long u, long long u1, Seg& s)
 {
     s.ct = (int)(u / p.Pout);
@@ -127,28 +167,27 @@ __device__ __forceinline__ void seg_make(const ConvP& p, const SlabGeom& g, long
     s.qb = hi > p.Pin - 1 ? p.Pin - 1 : hi;
 }
 // last input slab contributing to output position pp (clipped to the segment's slab range)
-__device__ __forceinline__ int q_last(const ConvP& p, const SlabGeom& g, const Seg& s, int pp)
+__device__ __forceinline__ int q_last(int pmul, int pdiv, int dpmax, int qb, int pp)
 {
-    const int q = fdiv(pp * p.pmul + g.dpmax, p.pdiv);
-    return q > s.qb ? s.qb : q;
+    int q = pp * pmul + dpmax;
+    if (pdiv == 2) q >>= 1;
+    return q > qb ? qb : q;
 }
-// output position that slab q feeds through tap t, or -1
-__device__ __forceinline__ int out_pos(const ConvP& p, const Seg& s, int q, int t)
+// output position that slab q feeds through the tap with offset dp, or -1
+__device__ __forceinline__ int out_pos(int pmul, int pdiv, int oa, int ob, int q, int dp)
 {
-    const int num = q * p.pdiv - p.dp[t];
+    int num = (pdiv == 2 ? 2 * q : q) - dp;
     if (num < 0) return -1;
-    if (p.pmul == 2 && (num & 1)) return -1;
-    const int pp = p.pmul == 2 ? (num >> 1) : num;
-    return (pp >= s.oa && pp < s.ob) ? pp : -1;
+    if (pmul == 2) { if (num & 1) return -1; num >>= 1; }
+    return (num >= oa && num < ob) ? num : -1;
 }
 __device__ __forceinline__ bool has_contrib(const ConvP& p, int pp)
 {
+    if (p.pdiv == 1) return true;                 // the centre tap (dp = 0) always lands inside the input
     for (int t = 0; t < p.ntaps; ++t) {
         const int num = pp * p.pmul + p.dp[t];
-        if (num < 0) continue;
-        if (p.pdiv == 2 && (num & 1)) continue;
-        const int q = p.pdiv == 2 ? (num >> 1) : num;
-        if (q < p.Pin) return true;
+        if (num < 0 || (num & 1)) continue;
+        if ((num >> 1) < p.Pin) return true;
     }
     return false;
 }
@@ -160,6 +199,100 @@ __device__ __forceinline__ float pro1(float x, float x2, float mk, float4 c4)
     if (PRO == PRO_AFFINE) return fmaf(c4.x, x - c4.w, c4.y);
     if (PRO == PRO_BNBWD) return fmaf(c4.x, x, fmaf(c4.y, x2 - c4.w, c4.z));
     return x;
+}
+
+// per-thread state of the epilogue that lives for the whole kernel
+template <int CH>
+struct EpiThread {
+    uint32_t t_lane;          // TMEM address of this warp's lane quarter
+    int ec0;                  // first output channel of this warp
+    int lane;
+    float s0[CH], s1[CH];     // running per-channel sums (BatchNorm statistics / BatchNorm-backward sums)
+};
+
+// epilogue of output positions [p_from, p_to) of one column tile; slot0 = accumulator slot of p_from.
+// Every global load of a position (raw tensor of the layer below, previous gradient) is issued before the accumulator is
+// read, so the tcgen05.ld latency and the memory latency overlap; offsets are 32-bit (the host declines larger tensors).
+template <int EPI, bool ACC, int CH>
+__device__ __forceinline__ void epi_run(const ConvP& p, const SlabGeom& g, EpiThread<CH>& e, const float* tab, uint32_t acc_empty0,
+                                        int slot0, int p_from, int p_to, bool nv, int obase_n, const float* mkp, int mk_sc, bool use_tmem)
+{
+    // A pass handles PB positions x SUB channels per thread (8 values): all its global loads and TMEM loads are issued before the
+    // first wait, so thin layers (2-4 channels per warp, hundreds of positions) pay one TMEM round trip per 2-4 positions.
+    constexpr int SUB = CH > 8 ? 8 : CH;
+    constexpr int PB = 8 / SUB;
+    const int out_sc = (int)p.out_sc, out_sp = (int)p.out_sp;
+    const int NACCm = g.NACC - 1;
+    const bool mem = nv && !(g.dbg & 4);
+    for (int pp = p_from; pp < p_to; pp += PB) {
+        const int nb = p_to - pp < PB ? p_to - pp : PB;
+#pragma unroll
+        for (int c0 = 0; c0 < CH; c0 += SUB) {
+            const int ch0 = e.ec0 + c0;
+            float rw[PB][SUB], old[PB][SUB], mk[SUB], v[PB][SUB], cr[PB][SUB];
+#pragma unroll
+            for (int c = 0; c < SUB; ++c) mk[c] = (EPI == EPI_DSILU && mkp && mem) ? __ldg(mkp + (ch0 + c) * mk_sc) : 1.f;
+#pragma unroll
+            for (int j = 0; j < PB; ++j) {
+                const int off0 = ch0 * out_sc + (pp + j) * out_sp + obase_n;
+#pragma unroll
+                for (int c = 0; c < SUB; ++c) {
+                    rw[j][c] = 0.f; old[j][c] = 0.f;
+                    if (mem && j < nb) {
+                        if (EPI == EPI_DSILU || EPI == EPI_DAFF) rw[j][c] = __ldg(p.eraw + off0 + c * out_sc);
+                        if (ACC) old[j][c] = p.out[off0 + c * out_sc];
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < PB; ++j) {
+                const bool contrib = j < nb && use_tmem && has_contrib(p, pp + j) && !(g.dbg & 32);
+                if (contrib) {
+                    const uint32_t ta = e.t_lane + (uint32_t)(((slot0 - (pp + j - p_from)) & NACCm) * 2 * g.NPAD + ch0);
+                    tmem_ldn<SUB>(ta, v[j]); tmem_ldn<SUB>(ta + g.NPAD, cr[j]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < SUB; ++c) { v[j][c] = 0.f; cr[j][c] = 0.f; }
+                }
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < PB; ++j) {
+                const bool contrib = j < nb && use_tmem && has_contrib(p, pp + j) && !(g.dbg & 32);
+                if (contrib) {                                            // accumulators are zero-initialised: every MMA accumulates
+                    const uint32_t ta = e.t_lane + (uint32_t)(((slot0 - (pp + j - p_from)) & NACCm) * 2 * g.NPAD + ch0);
+                    tmem_zero<SUB>(ta); tmem_zero<SUB>(ta + g.NPAD);
+                }
+            }
+            if (c0 + SUB >= CH) {                 // last TMEM access of these positions: hand the accumulator slots back
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (e.lane == 0)
+                    for (int j = 0; j < nb; ++j) mbar_arrive(acc_empty0 + 8u * ((slot0 - (pp + j - p_from)) & NACCm));
+            }
+            if (mem) {
+#pragma unroll
+                for (int j = 0; j < PB; ++j) {
+                    if (j < nb) {
+                        const int off0 = ch0 * out_sc + (pp + j) * out_sp + obase_n;
+#pragma unroll
+                        for (int c = 0; c < SUB; ++c) {
+                            float x = v[j][c] + cr[j][c] + tab[ch0 + c];
+                            if (ACC) x += old[j][c];
+                            if (EPI == EPI_STATS) { e.s0[c0 + c] += x; e.s1[c0 + c] = fmaf(x, x, e.s1[c0 + c]); }
+                            else if (EPI == EPI_DSILU || EPI == EPI_DAFF) {
+                                const float d = rw[j][c] - tab[192 + ch0 + c];
+                                if (EPI == EPI_DSILU) x = x * mk[c] * wf_dsilu(fmaf(tab[64 + ch0 + c], d, tab[128 + ch0 + c]));
+                                e.s0[c0 + c] += x; e.s1[c0 + c] = fmaf(x, d, e.s1[c0 + c]);
+                            }
+                            p.out[off0 + c * out_sc] = x;
+                        }
+                    }
+                }
+            }
+        }
+    }
 }
 
 // =========================================================================================================
@@ -174,7 +307,7 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int stage_bytes = 2 * g.half_bytes;
     uint8_t* wsm = smem + g.NS * stage_bytes;                                   // weights: hi images of all taps, then lo
-    float* tab = reinterpret_cast<float*>(wsm + 2 * g.w_half_bytes);            // epilogue tables: bias, e_scale, e_shift, e_mean [64] each
+    float* tab = reinterpret_cast<float*>(wsm + g.w_bytes);            // epilogue tables: bias, e_scale, e_shift, e_mean [64] each
     uint64_t* bars = reinterpret_cast<uint64_t*>(tab + 4 * 64);
     const uint32_t bar0 = smem_u32(bars);
     // barrier map: raw_full[NS] | op_full[NS] | slab_empty[NS] | grp_done[NGD] | acc_empty[MAXACC] | w_full
@@ -182,14 +315,14 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
     auto op_full = [&](int s) { return bar0 + 8u * (MAXNS + s); };
     auto slab_empty = [&](int s) { return bar0 + 8u * (2 * MAXNS + s); };
     auto grp_done = [&](int s) { return bar0 + 8u * (3 * MAXNS + s); };
-    auto acc_empty = [&](int s) { return bar0 + 8u * (3 * MAXNS + NGD + s); };
+    const uint32_t acc_empty0 = bar0 + 8u * (3 * MAXNS + NGD);
     const uint32_t w_full = bar0 + 8u * (3 * MAXNS + NGD + MAXACC);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAXNS + NGD + MAXACC + 1);
 
     if (tid == 0) {
-        for (int s = 0; s < g.NS; ++s) { mbar_init(raw_full(s), 1); mbar_init(op_full(s), NWW); mbar_init(slab_empty(s), 1); }
-        for (int s = 0; s < NGD; ++s) mbar_init(grp_done(s), 1);
-        for (int s = 0; s < g.NACC; ++s) mbar_init(acc_empty(s), NWW);
+        for (int s = 0; s < g.NS; ++s) { mbar_init(raw_full(s), 1); mbar_init(op_full(s), NWW); mbar_init(slab_empty(s), NI); }
+        for (int s = 0; s < NGD; ++s) mbar_init(grp_done(s), NI);
+        for (int s = 0; s < g.NACC; ++s) mbar_init(acc_empty0 + 8u * s, NWW);
         mbar_init(w_full, 1);
         fence_mbar_init();
     }
@@ -209,93 +342,69 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp < NWW) {                      // zero every accumulator slot: all MMAs accumulate, a slot is re-zeroed by the epilogue that drains it
+        constexpr int SUB = CH > 8 ? 8 : CH;
+        const uint32_t t0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * CH);
+        for (int sl = 0; sl < g.NACC; ++sl)
+#pragma unroll
+            for (int c0 = 0; c0 < CH; c0 += SUB) { tmem_zero<SUB>(t0 + sl * 2 * g.NPAD + c0); tmem_zero<SUB>(t0 + sl * 2 * g.NPAD + g.NPAD + c0); }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
     // this CTA's run of (column tile, output position) units
     const long long u0 = g.units * blockIdx.x / gridDim.x, u1 = g.units * (blockIdx.x + 1) / gridDim.x;
-    const int R = g.R, PBI = g.PBI, NS = g.NS, NACC = g.NACC;
+    const int R = g.R, PBI = g.PBI, NS = g.NS, NACCm = g.NACC - 1;
+    const int pmul = p.pmul, pdiv = p.pdiv;
     const uint32_t smem0 = smem_u32(smem);
 
     if (warp < NWW) {
         // =============================== workers: transform + epilogue ===============================
-        const int NJ = R >> 3;                                   // float4 chunks per thread and stage
+        const int NJ = (32 * R + NWORK - 1) / NWORK;              // float4 chunks per thread and stage (R = 64: 4)
         const int ch16 = tid & 7;
-        // channels of this thread's rows: row_j = ((tid >> 3) + 32 j) & (R - 1) alternates between two rows at most
-        const int rowA = (tid >> 3) & (R - 1), rowB = ((tid >> 3) + 32) & (R - 1);
-        const int cA = rowA & (p.Cin - 1), cB = rowB & (p.Cin - 1);
-        float4 coA = make_float4(1.f, 0.f, 0.f, 0.f), coB = coA;
-        if (PRO != PRO_NONE) {
-            coA = make_float4(p.pro_a[cA], p.pro_b[cA], PRO == PRO_BNBWD ? p.pro_c[cA] : 0.f, p.pro_d[cA]);
-            coB = make_float4(p.pro_a[cB], p.pro_b[cB], PRO == PRO_BNBWD ? p.pro_c[cB] : 0.f, p.pro_d[cB]);
-        }
-        // epilogue mapping
-        const int lq = warp & 3, half = warp >> 2;
-        const int ec0 = half * CH;                               // first channel of this warp half
-        const uint32_t t_lane = tmem_base + ((uint32_t)(lq * 32) << 16);
-        float s0[CH], s1[CH];
+        const int row = (tid >> 3) & (R - 1);                     // the same row (channel, position in group) for every chunk of a thread
+        const int cin_c = row & (p.Cin - 1);
+        float4 co4 = make_float4(1.f, 0.f, 0.f, 0.f);
+        if (PRO != PRO_NONE) co4 = make_float4(p.pro_a[cin_c], p.pro_b[cin_c], PRO == PRO_BNBWD ? p.pro_c[cin_c] : 0.f, p.pro_d[cin_c]);
+        const int nq = (ch16 ^ ((row & 3) << 1)) << 2;            // column of this thread's chunk inside its 32-column block
+        // epilogue mapping: TMEM lane quarter = warp mod 4, channels [ec0, ec0 + CH)
+        EpiThread<CH> et;
+        et.lane = lane;
+        et.ec0 = (warp >> 2) * CH;
+        et.t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll
-        for (int c = 0; c < CH; ++c) { s0[c] = 0.f; s1[c] = 0.f; }
-        const float* tb_bias = tab; const float* tb_es = tab + 64; const float* tb_et = tab + 128; const float* tb_em = tab + 192;
-        const bool do_stats = p.epi_mode != EPI_STORE && p.stat0 != nullptr;
+        for (int c = 0; c < CH; ++c) { et.s0[c] = 0.f; et.s1[c] = 0.f; }
+        const bool ch_ok = et.ec0 < p.Cout;                       // Cout = 8 with 16 worker warps: CH = 2 covers it exactly
+        const int epi = p.epi_mode;
+        const bool acc = p.accumulate != 0;
 
-        long long gg = 0;            // groups processed by this CTA so far (stage / barrier phases)
-        long long rbase = 0;         // output positions of earlier segments (accumulator slots)
-        // epilogue of the positions completed by a group: deferred by one group so that it overlaps the MMAs of the next one
-        struct Pend { bool valid; Seg s; int n0; long long gidx; int p_from, p_to; long long rbase; } pend;
+        int gg = 0;                  // groups processed by this CTA so far (stage / barrier phases)
+        int rbase = 0;               // output positions of earlier segments (accumulator slots)
+        struct Pend { bool valid; int n0, gidx, p_from, p_to, slot0; } pend;
         pend.valid = false;
-
         auto run_epilogue = [&](const Pend& e) {
-            if (e.gidx >= 0) {                                   // gidx < 0: positions no slab contributes to (pure bias / zeros)
-                mbar_wait(grp_done((int)(e.gidx % NGD)), (uint32_t)((e.gidx / NGD) & 1));
+            if (e.gidx >= 0) {                                    // gidx < 0: positions no slab contributes to (pure bias / zeros)
+                warp_wait(grp_done(e.gidx % NGD), (uint32_t)((e.gidx / NGD) & 1), lane);
                 tc_fence_after();
             }
-            const int n = e.n0 + lq * 32 + lane;
-            const bool nv = n < p.N;
+            const int n = e.n0 + (warp & 3) * 32 + lane;
+            const bool nv = n < p.N && ch_ok;
             const int b = n / WF_T, t = n - b * WF_T;
-            for (int pp = e.p_from; pp < e.p_to; ++pp) {
-                const long long r = e.rbase + (pp - e.s.oa);
-                const int slot = (int)(r % NACC);
-                const bool contrib = has_contrib(p, pp);
-                float v[CH];
-                if (contrib) {
-                    float cr[CH];
-                    const uint32_t ta = t_lane + (uint32_t)(slot * 2 * g.NPAD + ec0);
-                    constexpr int LC = CH > 16 ? 16 : CH;
-#pragma unroll
-                    for (int c = 0; c < CH; c += LC) { tmem_ldn<LC>(ta + c, v + c); tmem_ldn<LC>(ta + g.NPAD + c, cr + c); }
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < CH; ++c) v[c] += cr[c];
-                } else {
-#pragma unroll
-                    for (int c = 0; c < CH; ++c) v[c] = 0.f;
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty(slot));
-                if (nv) {
-                    const long long obase = (long long)pp * p.out_sp + (long long)b * p.out_sb + t;
-#pragma unroll
-                    for (int c = 0; c < CH; ++c) {
-                        const int co = ec0 + c;
-                        if (co < p.Cout) {
-                            const long long off = (long long)co * p.out_sc + obase;
-                            float x = v[c] + tb_bias[co];
-                            if (p.accumulate) x += p.out[off];
-                            if (p.epi_mode == EPI_STATS) { s0[c] += x; s1[c] = fmaf(x, x, s1[c]); }
-                            else if (p.epi_mode == EPI_DSILU || p.epi_mode == EPI_DAFF) {
-                                const float rw = p.eraw[off];
-                                const float em = tb_em[co];
-                                if (p.epi_mode == EPI_DSILU) {
-                                    float mk = 1.f;
-                                    if (p.emask) mk = p.emask[(long long)b * p.em_sb + (long long)co * p.em_sc + (long long)t * p.em_st];
-                                    x = x * mk * wf_dsilu(fmaf(tb_es[co], rw - em, tb_et[co]));
-                                }
-                                s0[c] += x; s1[c] = fmaf(x, rw - em, s1[c]);
-                            }
-                            p.out[off] = x;
-                        }
-                    }
-                }
+            const int obase_n = b * (int)p.out_sb + t;
+            // Dropout2d mask of the layer below: one value per (window, channel), read through L1 next to the raw tensor
+            const float* mkp = (epi == EPI_DSILU && p.emask && nv) ? p.emask + (long long)b * p.em_sb + (long long)t * p.em_st : nullptr;
+            const int mk_sc = (int)p.em_sc;
+            const bool ut = e.gidx >= 0;
+            switch (epi) {
+                case EPI_STORE:
+                    if (acc) epi_run<EPI_STORE, true, CH>(p, g, et, tab, acc_empty0, e.slot0, e.p_from, e.p_to, nv, obase_n, mkp, mk_sc, ut);
+                    else epi_run<EPI_STORE, false, CH>(p, g, et, tab, acc_empty0, e.slot0, e.p_from, e.p_to, nv, obase_n, mkp, mk_sc, ut);
+                    break;
+                case EPI_STATS: epi_run<EPI_STATS, false, CH>(p, g, et, tab, acc_empty0, e.slot0, e.p_from, e.p_to, nv, obase_n, mkp, mk_sc, ut); break;
+                case EPI_DSILU: epi_run<EPI_DSILU, false, CH>(p, g, et, tab, acc_empty0, e.slot0, e.p_from, e.p_to, nv, obase_n, mkp, mk_sc, ut); break;
+                default: epi_run<EPI_DAFF, false, CH>(p, g, et, tab, acc_empty0, e.slot0, e.p_from, e.p_to, nv, obase_n, mkp, mk_sc, ut); break;
             }
         };
 
@@ -309,37 +418,44 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
                 mk[j] = 1.f;
                 if (MASK && j < NJ) {
                     const int id = tid + NWORK * j;
-                    const int row = (id >> 3) & (R - 1), blk = id / (8 * R);
-                    const int n = n0 + blk * 32 + ((ch16 ^ ((row & 3) << 1)) << 2);     // 32-byte chunks are XORed with row mod 4
-                    const int c = row & (p.Cin - 1);
-                    if (n < p.N) mk[j] = p.mask[(long long)(n / WF_T) * p.m_sb + (long long)c * p.m_sc];
+                    const int n = n0 + (id / (8 * R)) * 32 + nq;
+                    if (n < p.N && id < 32 * R) mk[j] = p.mask[(long long)(n / WF_T) * p.m_sb + (long long)cin_c * p.m_sc];
                 }
             }
             int p_done = s.oa;
             const int ngroups = s.qb >= s.qa ? (s.qb - s.qa + PBI) / PBI : 0;
             for (int gi = 0; gi < ngroups; ++gi, ++gg) {
-                const int st = (int)(gg % NS);
+                const int st = gg % NS;
                 const uint32_t ph = (uint32_t)((gg / NS) & 1);
                 // ---- transform stage st in place ----
-                mbar_wait(raw_full(st), ph);
+                warp_wait(raw_full(st), ph, lane);
                 const uint32_t hi_base = smem0 + (uint32_t)(st * stage_bytes), lo_base = hi_base + (uint32_t)g.half_bytes;
+                if (!(g.dbg & 1)) {
+                    float4 x[MAXJ], x2[MAXJ];
 #pragma unroll
-                for (int j = 0; j < MAXJ; ++j) {
-                    if (j < NJ) {
+                    for (int j = 0; j < MAXJ; ++j) {
                         const uint32_t off = (uint32_t)(tid + NWORK * j) * 16u;
-                        float4 x = lds4(hi_base + off);
-                        float4 x2 = f4zero();
-                        if (PRO == PRO_BNBWD) x2 = lds4(lo_base + off);
-                        const float4 co = (j & 1) ? coB : coA;
-                        x.x = pro1<PRO>(x.x, x2.x, mk[j], co); x.y = pro1<PRO>(x.y, x2.y, mk[j], co);
-                        x.z = pro1<PRO>(x.z, x2.z, mk[j], co); x.w = pro1<PRO>(x.w, x2.w, mk[j], co);
-                        float4 h, l;
-                        tf32_split(x.x, h.x, l.x); tf32_split(x.y, h.y, l.y); tf32_split(x.z, h.z, l.z); tf32_split(x.w, h.w, l.w);
-                        sts4(hi_base + off, h);
-                        sts4(lo_base + off, l);
+                        x[j] = f4zero(); x2[j] = f4zero();
+                        if (j < NJ && tid + NWORK * j < 32 * R) {
+                            x[j] = lds4(hi_base + off);
+                            if (PRO == PRO_BNBWD) x2[j] = lds4(lo_base + off);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < MAXJ; ++j) {
+                        if (j < NJ && tid + NWORK * j < 32 * R) {
+                            const uint32_t off = (uint32_t)(tid + NWORK * j) * 16u;
+                            float4 y;
+                            y.x = pro1<PRO>(x[j].x, x2[j].x, mk[j], co4); y.y = pro1<PRO>(x[j].y, x2[j].y, mk[j], co4);
+                            y.z = pro1<PRO>(x[j].z, x2[j].z, mk[j], co4); y.w = pro1<PRO>(x[j].w, x2[j].w, mk[j], co4);
+                            float4 h, l;
+                            tf32_split(y.x, h.x, l.x); tf32_split(y.y, h.y, l.y); tf32_split(y.z, h.z, l.z); tf32_split(y.w, h.w, l.w);
+                            sts4(hi_base + off, h);
+                            sts4(lo_base + off, l);
+                        }
                     }
                 }
-                fence_proxy_async_smem();
+                if (!(g.dbg & 256)) fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(op_full(st));
                 // ---- epilogue of the previous group's completed positions ----
@@ -347,15 +463,16 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
                 // positions completed by this group
                 const int ql = min(s.qb, s.qa + (gi + 1) * PBI - 1);
                 int p_to = p_done;
-                while (p_to < s.ob && q_last(p, g, s, p_to) <= ql) ++p_to;
-                pend.valid = true; pend.s = s; pend.n0 = n0; pend.gidx = gg; pend.p_from = p_done; pend.p_to = p_to; pend.rbase = rbase;
+                while (p_to < s.ob && q_last(pmul, pdiv, g.dpmax, s.qb, p_to) <= ql) ++p_to;
+                pend.valid = true; pend.n0 = n0; pend.gidx = gg; pend.p_from = p_done; pend.p_to = p_to;
+                pend.slot0 = NACCm - ((rbase + (p_done - s.oa)) & NACCm);
                 p_done = p_to;
             }
             if (ngroups == 0) {
                 // a run of output positions that no input slab feeds (e.g. a single odd position of a stride-2 shortcut's
                 // backward-data): nothing to wait for, but the positions are still written and their slots still cycle
                 if (pend.valid) { run_epilogue(pend); pend.valid = false; }
-                Pend e; e.valid = true; e.s = s; e.n0 = n0; e.gidx = -1; e.p_from = s.oa; e.p_to = s.ob; e.rbase = rbase;
+                Pend e; e.valid = true; e.n0 = n0; e.gidx = -1; e.p_from = s.oa; e.p_to = s.ob; e.slot0 = NACCm - (rbase & NACCm);
                 run_epilogue(e);
             }
             rbase += s.ob - s.oa;
@@ -364,11 +481,11 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
         if (pend.valid) run_epilogue(pend);
 
         // ---- per-channel sums: one cross-lane reduction per CTA, fp64 atomics ----
-        if (do_stats) {
+        if (epi != EPI_STORE && p.stat0 != nullptr) {
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
-                const float a = warp_sum(s0[c]), bsum = warp_sum(s1[c]);
-                const int co = ec0 + c;
+                const float a = warp_sum(et.s0[c]), bsum = warp_sum(et.s1[c]);
+                const int co = et.ec0 + c;
                 if (lane == 0 && co < p.Cout) { atomicAdd(p.stat0 + co, (double)a); atomicAdd(p.stat1 + co, (double)bsum); }
             }
         }
@@ -378,18 +495,19 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
             tma_prefetch_desc(&tmA);
             if (PRO == PRO_BNBWD) tma_prefetch_desc(&tmB);
             // all tap weights (hi + lo images) once
-            mbar_arrive_expect_tx(w_full, 2 * g.w_half_bytes);
-            bulk_g2s(smem_u32(wsm), p.wtc, 2 * g.w_half_bytes, w_full);
-            long long gg = 0;
+            mbar_arrive_expect_tx(w_full, g.w_bytes);
+            bulk_g2s(smem_u32(wsm), p.wtc, g.w_bytes, w_full);
+            int gg = 0;
             const uint32_t tx = (uint32_t)g.half_bytes * (PRO == PRO_BNBWD ? 2u : 1u);
             for (long long u = u0; u < u1;) {
                 Seg s; seg_make(p, g, u, u1, s);
                 const int n0 = s.ct * TILE;
                 const int ngroups = s.qb >= s.qa ? (s.qb - s.qa + PBI) / PBI : 0;
                 for (int gi = 0; gi < ngroups; ++gi, ++gg) {
-                    const int st = (int)(gg % NS);
+                    const int st = gg % NS;
                     const uint32_t ph = (uint32_t)((gg / NS) & 1);
                     mbar_wait(slab_empty(st), ph ^ 1u);
+                    if (g.dbg & 16) { mbar_arrive(raw_full(st)); continue; }
                     mbar_arrive_expect_tx(raw_full(st), tx);
                     const uint32_t hi_base = smem0 + (uint32_t)(st * stage_bytes);
                     const int q0 = s.qa + gi * PBI;
@@ -404,66 +522,101 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
         }
     } else {
         // =============================== MMA issue ===============================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32(TILE, g.NPAD, 1, 0);          // A: MN-major (columns contiguous), B: K-major
-            const int KS = p.Cin >> 3;
-            const uint32_t w_hi = smem_u32(wsm), w_lo = w_hi + (uint32_t)g.w_half_bytes;
-            const uint32_t w_tap = (uint32_t)(g.NPAD * p.Cin * 4);                // bytes per tap image
-            const uint32_t b_lbo = 128, b_sbo = (uint32_t)(p.Cin / 4) * 128;
-            mbar_wait(w_full, 0);
-            long long gg = 0, rbase = 0;
-            uint32_t started = 0;
-            for (long long u = u0; u < u1;) {
-                Seg s; seg_make(p, g, u, u1, s);
-                int p_done = s.oa;
-                const int ngroups = s.qb >= s.qa ? (s.qb - s.qa + PBI) / PBI : 0;
-                for (int gi = 0; gi < ngroups; ++gi, ++gg) {
-                    const int st = (int)(gg % NS);
-                    const uint32_t ph = (uint32_t)((gg / NS) & 1);
-                    mbar_wait(op_full(st), ph);
-                    tc_fence_after();
-                    const uint32_t a_hi = smem0 + (uint32_t)(st * stage_bytes), a_lo = a_hi + (uint32_t)g.half_bytes;
-                    const int q0 = s.qa + gi * PBI;
-                    const int ql = min(s.qb, q0 + PBI - 1);
-                    for (int q = q0; q <= ql; ++q) {
-                        const uint32_t row_off = (uint32_t)((q - q0) * p.Cin) * 128u;
-                        for (int t = 0; t < p.ntaps; ++t) {
-                            const int pp = out_pos(p, s, q, t);
+        // Per K step (8 channels) of a slab there are TWO MMAs instead of the textbook three of 3xTF32:
+        //   D[main | cor] += A_hi * [B_hi ; B_lo]      (N = 2*NPAD: the hi*hi product lands in `main`, hi*lo in `cor`)
+        //   D[cor]        += A_lo * B_hi
+        // and where N allows (3 taps * 2*NPAD <= 256, stride-1 geometry) the three taps of a slab go into the SAME pair: the
+        // accumulator slots descend with the output position, so the positions q+1, q, q-1 a slab feeds are adjacent TMEM column
+        // blocks and B = the three taps' [hi ; lo] blocks stacked along N (second MMA: the zero-padded image [0 ; hi] per tap).
+        // Accumulators are zero-initialised by the epilogue, hence there are no accumulate flags and NO ORDER between contributions:
+        // the (slab, tap, K step) items of a group are dealt round-robin to NI issuing warps.  (One thread retires a dependent
+        // instruction every ~5 cycles and an MMA costs ~30 of them with its descriptors: a single issuer was the bottleneck, with
+        // the workers 60 % of their time waiting for it.)  Each warp runs the loop with warp-uniform values and lane 0 issues.
+        const int me = __shfl_sync(0xffffffffu, warp - (NWW + 1), 0);
+        const uint32_t lead = lane == 0 ? 1u : 0u;
+        const int KS = p.Cin >> 3, ntaps = p.ntaps, NPAD = g.NPAD;
+        const uint32_t idesc1 = umma_idesc_tf32(TILE, 2 * NPAD, 1, 0);           // A: MN-major (columns contiguous), B: K-major
+        const uint32_t idesc2 = umma_idesc_tf32(TILE, NPAD, 1, 0);
+        const uint32_t idescS = umma_idesc_tf32(TILE, ntaps * 2 * NPAD, 1, 0);
+        const uint32_t b_sbo = (uint32_t)(p.Cin / 4) * 128u;                     // bytes between 8-row groups of a weight image
+        const uint32_t w1_16 = (smem_u32(wsm) & 0x3FFFFu) >> 4, w2_16 = w1_16 + ((uint32_t)g.w_img_bytes >> 4);
+        const uint32_t tap16 = ((uint32_t)(2 * NPAD / 8) * b_sbo) >> 4;          // one tap's [hi ; lo] block, 16-byte units
+        // descriptor halves that never change: A = MN-major SWIZZLE_128B_BASE32B (layout 1), B = K-major no swizzle (layout 0)
+        const uint32_t a_hi32 = (((uint32_t)g.sbo_mn >> 4) & 0x3FFFu) | (1u << 14) | (1u << 29);
+        const uint32_t a_lbo = (((uint32_t)g.lbo_mn >> 4) & 0x3FFFu) << 16;
+        const uint32_t b_hi32 = ((b_sbo >> 4) & 0x3FFFu) | (1u << 14);
+        const uint32_t b_lbo = (128u >> 4) << 16;
+        auto mk_desc = [](uint32_t hi32, uint32_t lo32) { return ((uint64_t)hi32 << 32) | (uint64_t)lo32; };
+        // weight images hold the taps in order of ascending dp, i.e. descending output position for a given slab
+        int dps[3] = {p.dp[0], ntaps > 1 ? p.dp[1] : 0, ntaps > 2 ? p.dp[2] : 0};
+        if (ntaps == 3 && dps[0] > dps[2]) { const int t = dps[0]; dps[0] = dps[2]; dps[2] = t; }
+        mbar_wait(w_full, 0);
+        int gg = 0, rbase = 0;
+        // Position r may be written once the epilogue has drained position r - NACC (and re-zeroed the slot).  The epilogue drains in
+        // order, so ONE mbarrier test on the slot of position r - NACC + W - 1 covers W positions (a test costs ~100 cycles even when
+        // it succeeds); the host checks that this look-ahead never waits on the group being issued (ring_ok).
+        int drained = g.NACC;                                                    // positions < drained may be written
+        const int W = g.W;
+        auto acquire = [&](int r) {
+            if (r >= drained) {
+                const int rw_ = r - g.NACC + W - 1;
+                warp_wait(acc_empty0 + 8u * (NACCm - (rw_ & NACCm)), (uint32_t)((rw_ / g.NACC) & 1), lane);
+                tc_fence_after();
+                drained = rw_ + g.NACC + 1;
+            }
+        };
+        int item = 0;                                                            // running item counter: item % NI == me -> mine
+        for (long long u = u0; u < u1;) {
+            Seg s; seg_make(p, g, u, u1, s);
+            const int ngroups = s.qb >= s.qa ? (s.qb - s.qa + PBI) / PBI : 0;
+            for (int gi = 0; gi < ngroups; ++gi, ++gg) {
+                const int st = gg % NS;
+                const uint32_t ph = (uint32_t)((gg / NS) & 1);
+                warp_wait(op_full(st), ph, lane);
+                tc_fence_after();
+                const uint32_t a_hi16 = (((smem0 + (uint32_t)(st * stage_bytes)) & 0x3FFFFu) >> 4), a_lo16 = a_hi16 + ((uint32_t)g.half_bytes >> 4);
+                const int q0 = s.qa + gi * PBI;
+                const int ql = min(s.qb, q0 + PBI - 1);
+                for (int q = q0; q <= ql && !(g.dbg & 2); ++q) {
+                    const uint32_t row16 = (uint32_t)((q - q0) * p.Cin) * 8u;            // (rows * 128 B) >> 4
+                    const int pp0 = out_pos(pmul, pdiv, s.oa, s.ob, q, dps[0]);
+                    const int pp1 = ntaps > 1 ? out_pos(pmul, pdiv, s.oa, s.ob, q, dps[1]) : -1;
+                    const int pp2 = ntaps > 2 ? out_pos(pmul, pdiv, s.oa, s.ob, q, dps[2]) : -1;
+                    const int r0 = rbase + (pp0 - s.oa);
+                    if (g.stack && pp2 >= 0 && pp0 == pp2 + 2 && pp1 == pp2 + 1 && (r0 & NACCm) >= 2) {
+                        const uint32_t d = tmem_base + (uint32_t)((NACCm - (r0 & NACCm)) * 2 * NPAD);
+                        for (int ks = 0; ks < KS; ++ks, ++item) {
+                            if (item % NI != me) continue;
+                            acquire(r0);
+                            const uint32_t ao = row16 + (uint32_t)ks * 64u, bo = (uint32_t)ks * 16u;            // 1024 B / 256 B per K step
+                            umma_tf32_pred(d, mk_desc(a_hi32, (a_hi16 + ao) | a_lbo), mk_desc(b_hi32, (w1_16 + bo) | b_lbo), idescS, lead);
+                            umma_tf32_pred(d, mk_desc(a_hi32, (a_lo16 + ao) | a_lbo), mk_desc(b_hi32, (w2_16 + bo) | b_lbo), idescS, lead);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            const int pp = i == 0 ? pp0 : i == 1 ? pp1 : pp2;
                             if (pp < 0) continue;
-                            const long long r = rbase + (pp - s.oa);
-                            const int slot = (int)(r % NACC);
-                            uint32_t accf = 1u;
-                            if (!((started >> slot) & 1u)) {
-                                started |= 1u << slot;
-                                accf = 0u;
-                                const long long use = r / NACC;
-                                if (use > 0) { mbar_wait(acc_empty(slot), (uint32_t)((use - 1) & 1)); tc_fence_after(); }
-                            }
-                            const uint32_t d_main = tmem_base + (uint32_t)(slot * 2 * g.NPAD), d_cor = d_main + (uint32_t)g.NPAD;
-                            for (int ks = 0; ks < KS; ++ks) {
-                                const uint32_t ao = row_off + (uint32_t)ks * 1024u;
-                                const uint64_t dah = umma_desc_l(a_hi + ao, g.lbo_mn, g.sbo_mn, 1), dal = umma_desc_l(a_lo + ao, g.lbo_mn, g.sbo_mn, 1);
-                                const uint32_t bo = (uint32_t)t * w_tap + (uint32_t)ks * 256u;
-                                const uint64_t dbh = umma_desc_l(w_hi + bo, b_lbo, b_sbo, 0), dbl = umma_desc_l(w_lo + bo, b_lbo, b_sbo, 0);
-                                const uint32_t af = (ks == 0) ? accf : 1u;
-                                umma_tf32(d_cor, dal, dbh, idesc, af);
-                                umma_tf32(d_cor, dah, dbl, idesc, 1u);
-                                umma_tf32(d_main, dah, dbh, idesc, af);
+                            const int r = rbase + (pp - s.oa);
+                            const uint32_t d = tmem_base + (uint32_t)((NACCm - (r & NACCm)) * 2 * NPAD);
+                            for (int ks = 0; ks < KS; ++ks, ++item) {
+                                if (item % NI != me) continue;
+                                acquire(r);
+                                const uint32_t ao = row16 + (uint32_t)ks * 64u, bo = (uint32_t)i * tap16 + (uint32_t)ks * 16u;
+                                umma_tf32_pred(d, mk_desc(a_hi32, (a_hi16 + ao) | a_lbo), mk_desc(b_hi32, (w1_16 + bo) | b_lbo), idesc1, lead);
+                                umma_tf32_pred(d + (uint32_t)NPAD, mk_desc(a_hi32, (a_lo16 + ao) | a_lbo), mk_desc(b_hi32, (w1_16 + bo) | b_lbo), idesc2, lead);
                             }
                         }
                     }
-                    umma_commit(slab_empty(st));
-                    umma_commit(grp_done((int)(gg % NGD)));
-                    // positions completed by this group leave the "started" set
-                    while (p_done < s.ob && q_last(p, g, s, p_done) <= ql) {
-                        const long long r = rbase + (p_done - s.oa);
-                        started &= ~(1u << (int)(r % NACC));
-                        ++p_done;
-                    }
                 }
-                rbase += s.ob - s.oa;
-                u += s.ob - s.oa;
+                __syncwarp();
+                if (lane == 0) {
+                    if (g.dbg & 128) { mbar_arrive(slab_empty(st)); mbar_arrive(grp_done(gg % NGD)); }      // measurement only (with dbg 2)
+                    else { umma_commit(slab_empty(st)); umma_commit(grp_done(gg % NGD)); }
+                }
             }
+            rbase += s.ob - s.oa;
+            u += s.ob - s.oa;
         }
     }
     tc_fence_before();
@@ -480,25 +633,27 @@ __global__ void slab_pack_kernel(SlabPackTable tab, const float* params, float* 
     wf_pdl_enter();
     const SlabPackEntry e = tab.e[blockIdx.y];
     const int f_np = e.cout < 16 ? 16 : (e.cout + 15) / 16 * 16, b_np = e.cin < 16 ? 16 : (e.cin + 15) / 16 * 16;
-    const long long nf = (long long)e.ntaps * f_np * e.cin, nb = (long long)e.ntaps * b_np * e.cout;
+    // per direction: image 1 rows per tap = [hi (np) ; lo (np)], image 2 rows per tap = [0 (np) ; hi (np)]
+    const long long nf = (long long)e.ntaps * 2 * f_np * e.cin, nb = (long long)e.ntaps * 2 * b_np * e.cout;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nf + nb; i += (long long)gridDim.x * blockDim.x) {
         const bool bwd = i >= nf;
         const long long k_ = bwd ? i - nf : i;
         const int np = bwd ? b_np : f_np, K = bwd ? e.cout : e.cin;
-        const int per_tap = np * K;
-        const int tap = (int)(k_ / per_tap), within = (int)(k_ % per_tap);
-        // image order: [row group (np/8)][k quad (K/4)][row in group (8)][k in quad (4)]
-        const int c4 = within & 3, r8 = (within >> 2) & 7, kq = (within >> 5) % (K / 4), rg = within / (8 * K);
+        // image order: [row group (rows/8)][k quad (K/4)][row in group (8)][k in quad (4)], rows = (image tap, hi|lo half, channel)
+        const int c4 = (int)(k_ & 3), r8 = (int)((k_ >> 2) & 7), kq = (int)((k_ >> 5) % (K / 4)), rg = (int)(k_ / (8 * K));
         const int row = rg * 8 + r8, kk = kq * 4 + c4;
+        const int itap = row / (2 * np), within = row % (2 * np), half = within / np, ch = within % np;
+        // taps are stored in order of ascending dp: forward dp = (-1, 0, 1) keeps the reference order, backward-data dp = -dp reverses it
+        const int tap = bwd ? e.ntaps - 1 - itap : itap;
         float v = 0.f;
-        if (!bwd) { if (row < e.cout) v = params[e.param_off + ((long long)row * e.cin + kk) * e.ntaps + tap]; }
-        else { if (row < e.cin) v = params[e.param_off + ((long long)kk * e.cin + row) * e.ntaps + tap]; }
+        if (!bwd) { if (ch < e.cout) v = params[e.param_off + ((long long)ch * e.cin + kk) * e.ntaps + tap]; }
+        else { if (ch < e.cin) v = params[e.param_off + ((long long)kk * e.cin + ch) * e.ntaps + tap]; }
         float hi, lo;
         tf32_split(v, hi, lo);
         float* dst = packed + (bwd ? e.bwd_off : e.fwd_off);
-        const long long half = (long long)e.ntaps * per_tap;
-        dst[k_] = hi;
-        dst[half + k_] = lo;
+        const long long img = bwd ? nb : nf;
+        dst[k_] = half == 0 ? hi : lo;
+        dst[img + k_] = half == 0 ? 0.f : hi;
     }
 }
 
@@ -541,7 +696,7 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 // host-side simulation of the accumulator ring: every output position first touched in group gi must find its slot's previous
 // occupant completed by an EARLIER group (its epilogue runs before the workers transform group gi + 1), otherwise the MMA
 // thread would wait on an epilogue that waits on the MMA thread
-bool ring_ok(const ConvP& p, int dpmin, int dpmax, int PBI, int NACC)
+bool ring_ok(const ConvP& p, int dpmin, int dpmax, int PBI, int NACC, int W)
 {
     // worst case: a run over all positions of one tile
     const int oa = 0, ob = p.Pout;
@@ -553,14 +708,17 @@ bool ring_ok(const ConvP& p, int dpmin, int dpmax, int PBI, int NACC)
     for (int pp = NACC; pp < ob; ++pp) {
         // first contributing slab of pp
         int qf = -1;
-        for (int q = qa; q <= qb && qf < 0; ++q)
-            for (int t = 0; t < p.ntaps; ++t) {
-                const int num = q * p.pdiv - p.dp[t];
-                if (num < 0 || (p.pmul == 2 && (num & 1))) continue;
-                if ((p.pmul == 2 ? num >> 1 : num) == pp) { qf = q; break; }
-            }
+        for (int t = 0; t < p.ntaps; ++t) {
+            const int num = pp * p.pmul + p.dp[t];
+            if (num < 0 || (p.pdiv == 2 && (num & 1))) continue;
+            const int q = p.pdiv == 2 ? num >> 1 : num;
+            if (q < qa || q > qb) continue;
+            if (qf < 0 || q < qf) qf = q;
+        }
         if (qf < 0) continue;
-        if (grp_of(qlast(pp - NACC)) >= grp_of(qf)) return false;
+        // the MMA thread may wait for position pp - NACC + W - 1 (look-ahead) before touching pp
+        const int pw = pp - NACC + W - 1 < ob ? pp - NACC + W - 1 : ob - 1;
+        if (grp_of(qlast(pw)) >= grp_of(qf)) return false;
     }
     return true;
 }
@@ -576,12 +734,16 @@ bool plan(const ConvP& p, SlabGeom& g)
     if (g.NACC > MAXACC) g.NACC = MAXACC;
     g.tmem_cols = 32;
     while (g.tmem_cols < g.NACC * 2 * g.NPAD) g.tmem_cols *= 2;
-    g.w_half_bytes = p.ntaps * g.NPAD * p.Cin * 4;
-    const int fixed = 2 * g.w_half_bytes + 4 * 64 * 4 + (3 * MAXNS + NGD + MAXACC + 1) * 8 + 16 + 1024;
+    g.w_img_bytes = p.ntaps * 2 * g.NPAD * p.Cin * 4;
+    g.stack = (p.ntaps == 3 && p.pmul == 1 && p.ntaps * 2 * g.NPAD <= 256) ? 1 : 0;
+    g.w_bytes = g.w_img_bytes * (g.stack ? 2 : 1);
+    const int fixed = g.w_bytes + 4 * 64 * 4 + (3 * MAXNS + NGD + MAXACC + 1) * 8 + 16 + 1024;
     int PBI = 64 / p.Cin;
     if (PBI > p.Pin) { PBI = 1; while (PBI * 2 <= p.Pin && PBI * 2 * p.Cin <= 64) PBI *= 2; }
-    while (PBI > 1 && !ring_ok(p, dpmin, dpmax, PBI, g.NACC)) PBI >>= 1;
-    if (!ring_ok(p, dpmin, dpmax, PBI, g.NACC)) return false;
+    g.W = g.NACC / 4;
+    while (PBI > 1 && !ring_ok(p, dpmin, dpmax, PBI, g.NACC, g.W)) PBI >>= 1;
+    while (g.W > 1 && !ring_ok(p, dpmin, dpmax, PBI, g.NACC, g.W)) g.W >>= 1;
+    if (!ring_ok(p, dpmin, dpmax, PBI, g.NACC, g.W)) return false;
     g.PBI = PBI;
     g.R = PBI * p.Cin;
     g.half_bytes = 4 * g.R * 128;
@@ -597,14 +759,21 @@ bool plan(const ConvP& p, SlabGeom& g)
 
 size_t smem_bytes(const SlabGeom& g)
 {
-    return (size_t)g.NS * 2 * g.half_bytes + 2 * (size_t)g.w_half_bytes + 4 * 64 * 4 + (3 * MAXNS + NGD + MAXACC + 1) * 8 + 16;
+    return (size_t)g.NS * 2 * g.half_bytes + (size_t)g.w_bytes + 4 * 64 * 4 + (3 * MAXNS + NGD + MAXACC + 1) * 8 + 16;
 }
 
 template <int PRO, bool MASK, int CH>
 cudaError_t launch_t(const CUtensorMap& a, const CUtensorMap& b, const ConvP& p, const SlabGeom& g, int grid, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(slab_tc_kernel<PRO, MASK, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-    if (e != cudaSuccess) return e;
+    static std::atomic<unsigned long long> configured{0};          // one opt-in per device (bit = device ordinal)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(configured.load(std::memory_order_relaxed) & bit)) {
+        cudaError_t e = cudaFuncSetAttribute(slab_tc_kernel<PRO, MASK, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e != cudaSuccess) return e;
+        configured.fetch_or(bit, std::memory_order_relaxed);
+    }
     wf_launch_pdl(slab_tc_kernel<PRO, MASK, CH>, dim3(grid), dim3(NTHR), smem_bytes(g), st, a, b, p, g);
     return cudaGetLastError();
 }
@@ -612,12 +781,12 @@ cudaError_t launch_t(const CUtensorMap& a, const CUtensorMap& b, const ConvP& p,
 template <int PRO, bool MASK>
 cudaError_t launch_ch(const CUtensorMap& a, const CUtensorMap& b, const ConvP& p, const SlabGeom& g, int grid, cudaStream_t st)
 {
-    const int ch = p.Cout <= 8 ? 4 : p.Cout <= 16 ? 8 : p.Cout <= 32 ? 16 : 32;
+    const int ch = p.Cout <= 8 ? 2 : p.Cout <= 16 ? 4 : p.Cout <= 32 ? 8 : 16;        // channels per worker warp (4 warps per TMEM lane quarter)
     switch (ch) {
+        case 2: return launch_t<PRO, MASK, 2>(a, b, p, g, grid, st);
         case 4: return launch_t<PRO, MASK, 4>(a, b, p, g, grid, st);
         case 8: return launch_t<PRO, MASK, 8>(a, b, p, g, grid, st);
-        case 16: return launch_t<PRO, MASK, 16>(a, b, p, g, grid, st);
-        default: return launch_t<PRO, MASK, 32>(a, b, p, g, grid, st);
+        default: return launch_t<PRO, MASK, 16>(a, b, p, g, grid, st);
     }
 }
 
@@ -631,7 +800,7 @@ long long wf_slabtc_pack_floats(int cout, int cin, int ntaps, bool bwd)
 {
     const int rows = bwd ? cin : cout, k = bwd ? cout : cin;
     const int np = rows <= 16 ? 16 : (rows + 15) / 16 * 16;
-    return 2LL * ntaps * np * k;
+    return 4LL * ntaps * np * k;            // two images of ntaps * 2*np rows
 }
 
 cudaError_t wf_launch_slabtc_pack(const SlabPackTable& tab, const float* params, float* packed, cudaStream_t st)
@@ -654,12 +823,16 @@ bool wf_slabtc_conv_ok(const ConvP& p)
 {
     if (!g_enabled || p.wtc == nullptr) return false;
     if (!wf_slabtc_shape_ok(p.Cin, p.Cout, p.groups, p.ntaps, p.dn)) return false;
+    // taps: {0} or {-1, 0, +1} in ascending (forward image) or descending (backward-data image) order
+    if (p.ntaps == 1 ? p.dp[0] != 0 : (p.ntaps != 3 || p.dp[1] != 0 || p.dp[0] * p.dp[2] != -1 || p.dp[0] + p.dp[2] != 0)) return false;
     if (!(p.pmul == 1 || p.pmul == 2) || !(p.pdiv == 1 || p.pdiv == 2) || (p.pmul == 2 && p.pdiv == 2)) return false;
     if (p.in_sb != WF_T || p.out_sb != WF_T || (p.N & 3) || p.N % WF_T) return false;
     if ((reinterpret_cast<uintptr_t>(p.in) & 15) || ((p.in_sc * 4) & 15) || ((p.in_sp * 4) & 15)) return false;
     if (p.pro_mode == PRO_BNBWD && (!p.in2 || (reinterpret_cast<uintptr_t>(p.in2) & 15))) return false;
     if (p.pro_mode == PRO_BNSILU && p.mask && p.m_st != 0) return false;
     if (p.Pin > 4096 || p.Pout > 4096) return false;
+    if ((long long)p.Cout * p.out_sc >= (1LL << 31) || (long long)p.Pout * p.out_sp >= (1LL << 31)) return false;      // 32-bit offsets in the epilogue
+    if (p.accumulate && p.epi_mode != EPI_STORE) return false;
     SlabGeom g;
     return plan(p, g);
 }
@@ -669,6 +842,7 @@ cudaError_t wf_launch_slabtc_conv(const ConvP& p, cudaStream_t st)
     SlabGeom g;
     if (!plan(p, g)) return cudaErrorInvalidValue;
     if (g_swap_lbo) { const int t = g.lbo_mn; g.lbo_mn = g.sbo_mn; g.sbo_mn = t; }
+    { const char* e = std::getenv("WF_SLABTC_DBG"); g.dbg = e ? std::atoi(e) : 0; }
     CUtensorMap ta, tb;
     std::memset(&ta, 0, sizeof(ta)); std::memset(&tb, 0, sizeof(tb));
     if (!make_map(&ta, p.in, p.Cin, p.Pin, p.N, p.in_sc, p.in_sp, p.Cin, g.PBI)) return cudaErrorInvalidValue;

@@ -135,6 +135,18 @@ static int run_case(const Case& c, int verbose)
             printf(" dbg%d %7.1fus", d, ms * 50.f);
         }
         printf("\n");
+        {   // timeline of CTA 0 for one full launch
+            unsigned long long ts[32];
+            setenv("WF_SLABTC_DBG", "512", 1);
+            wf_slabtc_debug_ts(ts);
+            CK(wf_launch_slabtc_conv(p, 0)); CK(cudaDeviceSynchronize());
+            wf_slabtc_debug_ts(ts);
+            static const char* nm[] = {"entry", "tmem+bars", "zeroed", "TMA(6) issued", "w: raw_full(6)", "w: op_full(6) arrive", "i: weights in", "i: op_full(6)", "i: commit(6)",
+                                       "w: grp_done(6)", "w: epilogue(6) done", "w: loop end", "w: stats done", "final sync"};
+            printf("   timeline (us from entry):");
+            for (int i = 0; i < 14; ++i) printf(" %s %.1f |", nm[i], ts[i] ? (double)(ts[i] - ts[0]) / 1000.0 : -1.0);
+            printf("\n");
+        }
         unsetenv("WF_SLABTC_DBG");
         return 0;
     }
@@ -169,6 +181,7 @@ static int run_case(const Case& c, int verbose)
 
 int main(int argc, char** argv)
 {
+    setenv("WF_SLABTC_THIN", "1", 1);      // the self-test covers the 8-channel shapes too
     const int verbose = argc > 1 ? atoi(argv[1]) : 6;
     const int only = argc > 2 ? atoi(argv[2]) : -1;
     srand(1234);

@@ -62,6 +62,18 @@ struct SlabGeom {
     int dbg;                              // measurement switches (WF_SLABTC_DBG): 1 no transform, 2 no MMA, 4 no epilogue memory traffic, 8 hi*hi only, 16 no TMA, 32 no TMEM load
 };
 
+struct SlabGeom;
+// timeline probe of CTA 0 (WF_SLABTC_DBG bit 512): globaltimer stamps of the pipeline's milestones, read by the self-test
+__device__ unsigned long long g_ts[32];
+__device__ __forceinline__ void stamp(const SlabGeom& g, int slot)
+{
+    if ((g.dbg & 512) && blockIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (g_ts[slot] == 0) g_ts[slot] = t;
+    }
+}
+
 // ---- TMA tensor load (3-D tile), completion on an mbarrier ----
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar)
 {
@@ -213,42 +225,51 @@ struct EpiThread {
 // epilogue of output positions [p_from, p_to) of one column tile; slot0 = accumulator slot of p_from.
 // Every global load of a position (raw tensor of the layer below, previous gradient) is issued before the accumulator is
 // read, so the tcgen05.ld latency and the memory latency overlap; offsets are 32-bit (the host declines larger tensors).
+// Segment-invariant values of a worker thread's epilogue (a segment = one column tile)
+struct EpiSeg { int obase_n; bool nv; const float* mkp; };
+
 template <int EPI, bool ACC, int CH>
 __device__ __forceinline__ void epi_run(const ConvP& p, const SlabGeom& g, EpiThread<CH>& e, const float* tab, uint32_t acc_empty0,
-                                        int slot0, int p_from, int p_to, bool nv, int obase_n, const float* mkp, int mk_sc, bool use_tmem)
+                                        int r_from, int p_from, int cnt, const EpiSeg& sg, bool use_tmem)
 {
     // A pass handles PB positions x SUB channels per thread (8 values): all its global loads and TMEM loads are issued before the
     // first wait, so thin layers (2-4 channels per warp, hundreds of positions) pay one TMEM round trip per 2-4 positions.
+    // r_from = running index of position p_from in this CTA's walk: slot = NACC-1 - (r mod NACC); only positions with
+    // r mod W == W-1 signal their barrier (the MMA issuers wait on exactly those: in-order draining covers the others).
     constexpr int SUB = CH > 8 ? 8 : CH;
     constexpr int PB = 8 / SUB;
     const int out_sc = (int)p.out_sc, out_sp = (int)p.out_sp;
-    const int NACCm = g.NACC - 1;
-    const bool mem = nv && !(g.dbg & 4);
-    for (int pp = p_from; pp < p_to; pp += PB) {
-        const int nb = p_to - pp < PB ? p_to - pp : PB;
+    const int NACCm = g.NACC - 1, Wm = g.W - 1, slotw = 2 * g.NPAD;
+    const bool mem = sg.nv && !(g.dbg & 4);
+    const bool every = p.pdiv == 1;               // every position receives contributions (centre tap)
+    const bool tm = use_tmem && !(g.dbg & 32);
+    for (int i0 = 0; i0 < cnt; i0 += PB) {
+        const int pp = p_from + i0, r0 = r_from + i0;
+        const int nb = cnt - i0 < PB ? cnt - i0 : PB;
+        bool contrib[PB];
+#pragma unroll
+        for (int j = 0; j < PB; ++j) contrib[j] = j < nb && tm && (every || has_contrib(p, pp + j));
 #pragma unroll
         for (int c0 = 0; c0 < CH; c0 += SUB) {
             const int ch0 = e.ec0 + c0;
             float rw[PB][SUB], old[PB][SUB], mk[SUB], v[PB][SUB], cr[PB][SUB];
+            const int off00 = ch0 * out_sc + pp * out_sp + sg.obase_n;
 #pragma unroll
-            for (int c = 0; c < SUB; ++c) mk[c] = (EPI == EPI_DSILU && mkp && mem) ? __ldg(mkp + (ch0 + c) * mk_sc) : 1.f;
+            for (int c = 0; c < SUB; ++c) mk[c] = (EPI == EPI_DSILU && sg.mkp && mem) ? __ldg(sg.mkp + (ch0 + c) * (int)p.em_sc) : 1.f;
 #pragma unroll
-            for (int j = 0; j < PB; ++j) {
-                const int off0 = ch0 * out_sc + (pp + j) * out_sp + obase_n;
+            for (int j = 0; j < PB; ++j)
 #pragma unroll
                 for (int c = 0; c < SUB; ++c) {
                     rw[j][c] = 0.f; old[j][c] = 0.f;
                     if (mem && j < nb) {
-                        if (EPI == EPI_DSILU || EPI == EPI_DAFF) rw[j][c] = __ldg(p.eraw + off0 + c * out_sc);
-                        if (ACC) old[j][c] = p.out[off0 + c * out_sc];
+                        if (EPI == EPI_DSILU || EPI == EPI_DAFF) rw[j][c] = __ldg(p.eraw + off00 + j * out_sp + c * out_sc);
+                        if (ACC) old[j][c] = p.out[off00 + j * out_sp + c * out_sc];
                     }
                 }
-            }
 #pragma unroll
             for (int j = 0; j < PB; ++j) {
-                const bool contrib = j < nb && use_tmem && has_contrib(p, pp + j) && !(g.dbg & 32);
-                if (contrib) {
-                    const uint32_t ta = e.t_lane + (uint32_t)(((slot0 - (pp + j - p_from)) & NACCm) * 2 * g.NPAD + ch0);
+                if (contrib[j]) {
+                    const uint32_t ta = e.t_lane + (uint32_t)((NACCm - ((r0 + j) & NACCm)) * slotw + ch0);
                     tmem_ldn<SUB>(ta, v[j]); tmem_ldn<SUB>(ta + g.NPAD, cr[j]);
                 } else {
 #pragma unroll
@@ -257,25 +278,25 @@ __device__ __forceinline__ void epi_run(const ConvP& p, const SlabGeom& g, EpiTh
             }
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < PB; ++j) {
-                const bool contrib = j < nb && use_tmem && has_contrib(p, pp + j) && !(g.dbg & 32);
-                if (contrib) {                                            // accumulators are zero-initialised: every MMA accumulates
-                    const uint32_t ta = e.t_lane + (uint32_t)(((slot0 - (pp + j - p_from)) & NACCm) * 2 * g.NPAD + ch0);
+            for (int j = 0; j < PB; ++j)
+                if (contrib[j]) {                                         // accumulators are zero-initialised: every MMA accumulates
+                    const uint32_t ta = e.t_lane + (uint32_t)((NACCm - ((r0 + j) & NACCm)) * slotw + ch0);
                     tmem_zero<SUB>(ta); tmem_zero<SUB>(ta + g.NPAD);
                 }
-            }
             if (c0 + SUB >= CH) {                 // last TMEM access of these positions: hand the accumulator slots back
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (e.lane == 0)
-                    for (int j = 0; j < nb; ++j) mbar_arrive(acc_empty0 + 8u * ((slot0 - (pp + j - p_from)) & NACCm));
+                if (e.lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < PB; ++j)
+                        if (j < nb && ((r0 + j) & Wm) == Wm) mbar_arrive(acc_empty0 + 8u * (NACCm - ((r0 + j) & NACCm)));
+                }
             }
             if (mem) {
 #pragma unroll
                 for (int j = 0; j < PB; ++j) {
                     if (j < nb) {
-                        const int off0 = ch0 * out_sc + (pp + j) * out_sp + obase_n;
 #pragma unroll
                         for (int c = 0; c < SUB; ++c) {
                             float x = v[j][c] + cr[j][c] + tab[ch0 + c];
@@ -286,7 +307,7 @@ __device__ __forceinline__ void epi_run(const ConvP& p, const SlabGeom& g, EpiTh
                                 if (EPI == EPI_DSILU) x = x * mk[c] * wf_dsilu(fmaf(tab[64 + ch0 + c], d, tab[128 + ch0 + c]));
                                 e.s0[c0 + c] += x; e.s1[c0 + c] = fmaf(x, d, e.s1[c0 + c]);
                             }
-                            p.out[off0 + c * out_sc] = x;
+                            p.out[off00 + j * out_sp + c * out_sc] = x;
                         }
                     }
                 }
@@ -305,6 +326,7 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
     wf_pdl_enter();
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) stamp(g, 0);
     const int stage_bytes = 2 * g.half_bytes;
     uint8_t* wsm = smem + g.NS * stage_bytes;                                   // weights: hi images of all taps, then lo
     float* tab = reinterpret_cast<float*>(wsm + g.w_bytes);            // epilogue tables: bias, e_scale, e_shift, e_mean [64] each
@@ -342,6 +364,7 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) stamp(g, 1);
     if (warp < NWW) {                      // zero every accumulator slot: all MMAs accumulate, a slot is re-zeroed by the epilogue that drains it
         constexpr int SUB = CH > 8 ? 8 : CH;
         const uint32_t t0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * CH);
@@ -354,6 +377,7 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
     __syncthreads();
     tc_fence_after();
 
+    if (tid == 0) stamp(g, 2);
     // this CTA's run of (column tile, output position) units
     const long long u0 = g.units * blockIdx.x / gridDim.x, u1 = g.units * (blockIdx.x + 1) / gridDim.x;
     const int R = g.R, PBI = g.PBI, NS = g.NS, NACCm = g.NACC - 1;
@@ -380,38 +404,32 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
         const int epi = p.epi_mode;
         const bool acc = p.accumulate != 0;
 
-        int gg = 0;                  // groups processed by this CTA so far (stage / barrier phases)
-        int rbase = 0;               // output positions of earlier segments (accumulator slots)
-        struct Pend { bool valid; int n0, gidx, p_from, p_to, slot0; } pend;
-        pend.valid = false;
-        auto run_epilogue = [&](const Pend& e) {
-            if (e.gidx >= 0) {                                    // gidx < 0: positions no slab contributes to (pure bias / zeros)
-                warp_wait(grp_done(e.gidx % NGD), (uint32_t)((e.gidx / NGD) & 1), lane);
-                tc_fence_after();
-            }
-            const int n = e.n0 + (warp & 3) * 32 + lane;
-            const bool nv = n < p.N && ch_ok;
-            const int b = n / WF_T, t = n - b * WF_T;
-            const int obase_n = b * (int)p.out_sb + t;
-            // Dropout2d mask of the layer below: one value per (window, channel), read through L1 next to the raw tensor
-            const float* mkp = (epi == EPI_DSILU && p.emask && nv) ? p.emask + (long long)b * p.em_sb + (long long)t * p.em_st : nullptr;
-            const int mk_sc = (int)p.em_sc;
-            const bool ut = e.gidx >= 0;
+        // running state of the walk (kept incrementally: a worker warp retires one dependent instruction every ~5 cycles, so
+        // every division / modulo / loop in the per-group path is paid 16 times per group)
+        int st = 0; uint32_t ph = 0;                  // operand stage of the current group and its barrier phase
+        int gcount = 0;                               // groups done (timeline probe)
+        int gd = 0; uint32_t gdph = 0;                // "group done" barrier of the current group and its phase
+        int rbase = 0;                                // output positions of earlier segments (accumulator slot numbering)
+        struct Pend { int cnt, p_from, r_from; uint32_t bar, par; EpiSeg sg; } pend;
+        pend.cnt = 0;
+
+        auto run_epilogue = [&](const Pend& e, bool ut) {
+            if (ut) { warp_wait(e.bar, e.par, lane); tc_fence_after(); if (tid == 0 && gcount == 7) stamp(g, 9); }
             switch (epi) {
                 case EPI_STORE:
-                    if (acc) epi_run<EPI_STORE, true, CH>(p, g, et, tab, acc_empty0, e.slot0, e.p_from, e.p_to, nv, obase_n, mkp, mk_sc, ut);
-                    else epi_run<EPI_STORE, false, CH>(p, g, et, tab, acc_empty0, e.slot0, e.p_from, e.p_to, nv, obase_n, mkp, mk_sc, ut);
+                    if (acc) epi_run<EPI_STORE, true, CH>(p, g, et, tab, acc_empty0, e.r_from, e.p_from, e.cnt, e.sg, ut);
+                    else epi_run<EPI_STORE, false, CH>(p, g, et, tab, acc_empty0, e.r_from, e.p_from, e.cnt, e.sg, ut);
                     break;
-                case EPI_STATS: epi_run<EPI_STATS, false, CH>(p, g, et, tab, acc_empty0, e.slot0, e.p_from, e.p_to, nv, obase_n, mkp, mk_sc, ut); break;
-                case EPI_DSILU: epi_run<EPI_DSILU, false, CH>(p, g, et, tab, acc_empty0, e.slot0, e.p_from, e.p_to, nv, obase_n, mkp, mk_sc, ut); break;
-                default: epi_run<EPI_DAFF, false, CH>(p, g, et, tab, acc_empty0, e.slot0, e.p_from, e.p_to, nv, obase_n, mkp, mk_sc, ut); break;
+                case EPI_STATS: epi_run<EPI_STATS, false, CH>(p, g, et, tab, acc_empty0, e.r_from, e.p_from, e.cnt, e.sg, ut); break;
+                case EPI_DSILU: epi_run<EPI_DSILU, false, CH>(p, g, et, tab, acc_empty0, e.r_from, e.p_from, e.cnt, e.sg, ut); break;
+                default: epi_run<EPI_DAFF, false, CH>(p, g, et, tab, acc_empty0, e.r_from, e.p_from, e.cnt, e.sg, ut); break;
             }
         };
 
         for (long long u = u0; u < u1;) {
             Seg s; seg_make(p, g, u, u1, s);
             const int n0 = s.ct * TILE;
-            // per-segment dropout-mask values of this thread's chunks (Dropout2d: one value per (window, channel))
+            // per-segment values: dropout-mask values of this thread's chunks (Dropout2d: one value per (window, channel)) ...
             float mk[MAXJ];
 #pragma unroll
             for (int j = 0; j < MAXJ; ++j) {
@@ -422,13 +440,22 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
                     if (n < p.N && id < 32 * R) mk[j] = p.mask[(long long)(n / WF_T) * p.m_sb + (long long)cin_c * p.m_sc];
                 }
             }
+            // ... and the epilogue's column: thread = TMEM lane = column n of the tile
+            EpiSeg sg;
+            {
+                const int n = n0 + (warp & 3) * 32 + lane;
+                const int b = n / WF_T, t = n - b * WF_T;
+                sg.nv = n < p.N && ch_ok;
+                sg.obase_n = b * (int)p.out_sb + t;
+                sg.mkp = (epi == EPI_DSILU && p.emask && sg.nv) ? p.emask + (long long)b * p.em_sb + (long long)t * p.em_st : nullptr;
+            }
             int p_done = s.oa;
             const int ngroups = s.qb >= s.qa ? (s.qb - s.qa + PBI) / PBI : 0;
-            for (int gi = 0; gi < ngroups; ++gi, ++gg) {
-                const int st = gg % NS;
-                const uint32_t ph = (uint32_t)((gg / NS) & 1);
+            int ql = s.qa - 1;
+            for (int gi = 0; gi < ngroups; ++gi) {
                 // ---- transform stage st in place ----
                 warp_wait(raw_full(st), ph, lane);
+                if (tid == 0 && gcount == 6) stamp(g, 4);
                 const uint32_t hi_base = smem0 + (uint32_t)(st * stage_bytes), lo_base = hi_base + (uint32_t)g.half_bytes;
                 if (!(g.dbg & 1)) {
                     float4 x[MAXJ], x2[MAXJ];
@@ -458,27 +485,37 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
                 if (!(g.dbg & 256)) fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(op_full(st));
+                if (tid == 0 && gcount == 6) stamp(g, 5);
                 // ---- epilogue of the previous group's completed positions ----
-                if (pend.valid) { run_epilogue(pend); pend.valid = false; }
-                // positions completed by this group
-                const int ql = min(s.qb, s.qa + (gi + 1) * PBI - 1);
-                int p_to = p_done;
-                while (p_to < s.ob && q_last(pmul, pdiv, g.dpmax, s.qb, p_to) <= ql) ++p_to;
-                pend.valid = true; pend.n0 = n0; pend.gidx = gg; pend.p_from = p_done; pend.p_to = p_to;
-                pend.slot0 = NACCm - ((rbase + (p_done - s.oa)) & NACCm);
+                if (pend.cnt > 0) { run_epilogue(pend, true); pend.cnt = 0; if (tid == 0 && gcount == 7) stamp(g, 10); }
+                // positions completed by this group: q_last(pp) = floor((pp*pmul + dpmax) / pdiv) <= ql  (all of them after the last slab)
+                ql = min(s.qb, ql + PBI);
+                int p_to = s.ob;
+                if (ql < s.qb) {
+                    const int lim = ql * pdiv + pdiv - 1 - g.dpmax;
+                    const int pl = lim < 0 ? -1 : (pmul == 2 ? lim >> 1 : lim);
+                    p_to = min(s.ob, pl + 1);
+                    if (p_to < p_done) p_to = p_done;
+                }
+                pend.cnt = p_to - p_done; pend.p_from = p_done; pend.r_from = rbase + (p_done - s.oa);
+                pend.bar = grp_done(gd); pend.par = gdph; pend.sg = sg;
                 p_done = p_to;
+                ++gcount;
+                if (++st == NS) { st = 0; ph ^= 1u; }
+                if (++gd == NGD) { gd = 0; gdph ^= 1u; }
             }
             if (ngroups == 0) {
                 // a run of output positions that no input slab feeds (e.g. a single odd position of a stride-2 shortcut's
                 // backward-data): nothing to wait for, but the positions are still written and their slots still cycle
-                if (pend.valid) { run_epilogue(pend); pend.valid = false; }
-                Pend e; e.valid = true; e.n0 = n0; e.gidx = -1; e.p_from = s.oa; e.p_to = s.ob; e.slot0 = NACCm - (rbase & NACCm);
-                run_epilogue(e);
+                if (pend.cnt > 0) { run_epilogue(pend, true); pend.cnt = 0; }
+                Pend e; e.cnt = s.ob - s.oa; e.p_from = s.oa; e.r_from = rbase; e.bar = 0; e.par = 0; e.sg = sg;
+                run_epilogue(e, false);
             }
             rbase += s.ob - s.oa;
             u += s.ob - s.oa;
         }
-        if (pend.valid) run_epilogue(pend);
+        if (pend.cnt > 0) run_epilogue(pend, true);
+        if (tid == 0) stamp(g, 11);
 
         // ---- per-channel sums: one cross-lane reduction per CTA, fp64 atomics ----
         if (epi != EPI_STORE && p.stat0 != nullptr) {
@@ -489,6 +526,7 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
                 if (lane == 0 && co < p.Cout) { atomicAdd(p.stat0 + co, (double)a); atomicAdd(p.stat1 + co, (double)bsum); }
             }
         }
+        if (tid == 0) stamp(g, 12);
     } else if (warp == NWW) {
         // =============================== TMA producer ===============================
         if (lane == 0) {
@@ -514,6 +552,7 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
 #pragma unroll
                     for (int blk = 0; blk < 4; ++blk) {
                         tma_load_3d(hi_base + (uint32_t)(blk * R * 128), &tmA, n0 + blk * 32, 0, q0, raw_full(st));
+                        if (gg == 6) stamp(g, 3);
                         if (PRO == PRO_BNBWD) tma_load_3d(hi_base + (uint32_t)(g.half_bytes + blk * R * 128), &tmB, n0 + blk * 32, 0, q0, raw_full(st));
                     }
                 }
@@ -551,6 +590,7 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
         int dps[3] = {p.dp[0], ntaps > 1 ? p.dp[1] : 0, ntaps > 2 ? p.dp[2] : 0};
         if (ntaps == 3 && dps[0] > dps[2]) { const int t = dps[0]; dps[0] = dps[2]; dps[2] = t; }
         mbar_wait(w_full, 0);
+        if (me == 0 && lane == 0) stamp(g, 6);
         int gg = 0, rbase = 0;
         // Position r may be written once the epilogue has drained position r - NACC (and re-zeroed the slot).  The epilogue drains in
         // order, so ONE mbarrier test on the slot of position r - NACC + W - 1 covers W positions (a test costs ~100 cycles even when
@@ -559,12 +599,16 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
         const int W = g.W;
         auto acquire = [&](int r) {
             if (r >= drained) {
-                const int rw_ = r - g.NACC + W - 1;
+                const int rw_ = (r - g.NACC) | (W - 1);                                  // the signalling position at or after r - NACC
                 warp_wait(acc_empty0 + 8u * (NACCm - (rw_ & NACCm)), (uint32_t)((rw_ / g.NACC) & 1), lane);
                 tc_fence_after();
                 drained = rw_ + g.NACC + 1;
             }
         };
+        // work split between the NI issuing warps: whole slabs when a group has at least NI of them (thin layers: the per-slab
+        // scalar work is divided too), otherwise the K steps of every slab
+        const bool split_slabs = PBI >= NI;
+        int slab_no = 0;
         int item = 0;                                                            // running item counter: item % NI == me -> mine
         for (long long u = u0; u < u1;) {
             Seg s; seg_make(p, g, u, u1, s);
@@ -574,10 +618,12 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
                 const uint32_t ph = (uint32_t)((gg / NS) & 1);
                 warp_wait(op_full(st), ph, lane);
                 tc_fence_after();
+                if (me == 0 && lane == 0 && gg == 6) stamp(g, 7);
                 const uint32_t a_hi16 = (((smem0 + (uint32_t)(st * stage_bytes)) & 0x3FFFFu) >> 4), a_lo16 = a_hi16 + ((uint32_t)g.half_bytes >> 4);
                 const int q0 = s.qa + gi * PBI;
                 const int ql = min(s.qb, q0 + PBI - 1);
                 for (int q = q0; q <= ql && !(g.dbg & 2); ++q) {
+                    if (split_slabs) { if (slab_no++ % NI != me) continue; item = me; }      // my slab: all of its items are mine
                     const uint32_t row16 = (uint32_t)((q - q0) * p.Cin) * 8u;            // (rows * 128 B) >> 4
                     const int pp0 = out_pos(pmul, pdiv, s.oa, s.ob, q, dps[0]);
                     const int pp1 = ntaps > 1 ? out_pos(pmul, pdiv, s.oa, s.ob, q, dps[1]) : -1;
@@ -586,7 +632,7 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
                     if (g.stack && pp2 >= 0 && pp0 == pp2 + 2 && pp1 == pp2 + 1 && (r0 & NACCm) >= 2) {
                         const uint32_t d = tmem_base + (uint32_t)((NACCm - (r0 & NACCm)) * 2 * NPAD);
                         for (int ks = 0; ks < KS; ++ks, ++item) {
-                            if (item % NI != me) continue;
+                            if (!split_slabs && item % NI != me) continue;
                             acquire(r0);
                             const uint32_t ao = row16 + (uint32_t)ks * 64u, bo = (uint32_t)ks * 16u;            // 1024 B / 256 B per K step
                             umma_tf32_pred(d, mk_desc(a_hi32, (a_hi16 + ao) | a_lbo), mk_desc(b_hi32, (w1_16 + bo) | b_lbo), idescS, lead);
@@ -600,7 +646,7 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
                             const int r = rbase + (pp - s.oa);
                             const uint32_t d = tmem_base + (uint32_t)((NACCm - (r & NACCm)) * 2 * NPAD);
                             for (int ks = 0; ks < KS; ++ks, ++item) {
-                                if (item % NI != me) continue;
+                                if (!split_slabs && item % NI != me) continue;
                                 acquire(r);
                                 const uint32_t ao = row16 + (uint32_t)ks * 64u, bo = (uint32_t)i * tap16 + (uint32_t)ks * 16u;
                                 umma_tf32_pred(d, mk_desc(a_hi32, (a_hi16 + ao) | a_lbo), mk_desc(b_hi32, (w1_16 + bo) | b_lbo), idesc1, lead);
@@ -613,6 +659,7 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
                 if (lane == 0) {
                     if (g.dbg & 128) { mbar_arrive(slab_empty(st)); mbar_arrive(grp_done(gg % NGD)); }      // measurement only (with dbg 2)
                     else { umma_commit(slab_empty(st)); umma_commit(grp_done(gg % NGD)); }
+                    if (me == 0 && gg == 6) stamp(g, 8);
                 }
             }
             rbase += s.ob - s.oa;
@@ -621,6 +668,7 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) stamp(g, 13);
     if (warp == NWW) tmem_dealloc(tmem_base, g.tmem_cols);
 }
 
@@ -790,11 +838,21 @@ cudaError_t launch_ch(const CUtensorMap& a, const CUtensorMap& b, const ConvP& p
     }
 }
 
+bool thin_enabled() { static const bool v = [] { const char* e = std::getenv("WF_SLABTC_THIN"); return e && e[0] == '1'; }(); return v; }
 const bool g_enabled = [] { const char* e = std::getenv("WF_DISABLE_SLABTC"); return !(e && e[0] == '1'); }();
 // debugging aid of the self-test: swap the two stride fields of the MN-major descriptor
 const bool g_swap_lbo = [] { const char* e = std::getenv("WF_SLABTC_SWAP_LBO"); return e && e[0] == '1'; }();
 
 }  // namespace
+
+// timeline probe (WF_SLABTC_DBG bit 512): copies and clears the 32 globaltimer stamps of CTA 0
+cudaError_t wf_slabtc_debug_ts(unsigned long long* out)
+{
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_ts, sizeof(g_ts));
+    if (e != cudaSuccess) return e;
+    unsigned long long z[32] = {0};
+    return cudaMemcpyToSymbol(g_ts, z, sizeof(z));
+}
 
 long long wf_slabtc_pack_floats(int cout, int cin, int ntaps, bool bwd)
 {
@@ -822,6 +880,9 @@ bool wf_slabtc_shape_ok(int cin, int cout, int groups, int ntaps, const int* dn)
 bool wf_slabtc_conv_ok(const ConvP& p)
 {
     if (!g_enabled || p.wtc == nullptr) return false;
+    // 8 -> 8 channel layers: the per-position cost of the TMEM round trips is not amortised (measured 147 us vs 141 us for the
+    // mma.sync kernel on up.block.4); they stay on wf_slide.cu unless WF_SLABTC_THIN=1
+    if (p.Cin <= 8 && p.Cout <= 8 && !thin_enabled()) return false;
     if (!wf_slabtc_shape_ok(p.Cin, p.Cout, p.groups, p.ntaps, p.dn)) return false;
     // taps: {0} or {-1, 0, +1} in ascending (forward image) or descending (backward-data image) order
     if (p.ntaps == 1 ? p.dp[0] != 0 : (p.ntaps != 3 || p.dp[1] != 0 || p.dp[0] * p.dp[2] != -1 || p.dp[0] + p.dp[2] != 0)) return false;

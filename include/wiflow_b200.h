@@ -124,6 +124,7 @@ WF_API int wf_keypoint_sequences(float* frames, const long long* seq_off, int n_
 WF_API long long wf_launch_count(void);
 WF_API int wf_profile_count(void);
 WF_API int wf_profile_read(int i, char* name, int name_cap, float* ms, double* flops);
+WF_API int wf_profile_bytes(int i, double* bytes);   /* algorithmic HBM bytes of launch i (every operand tensor once) */
 WF_API void wf_profile_reset(void);
 
 /* ---- test / debug introspection (not part of the reference-facing surface) ----

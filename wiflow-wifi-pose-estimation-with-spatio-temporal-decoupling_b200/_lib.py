@@ -73,6 +73,8 @@ def lib():
     L.wf_profile_read.restype = ip
     L.wf_profile_read.argtypes = [ip, ctypes.c_char_p, ip, ctypes.POINTER(f), ctypes.POINTER(ctypes.c_double)]
     L.wf_profile_reset.restype = None
+    L.wf_profile_bytes.restype = ip
+    L.wf_profile_bytes.argtypes = [ip, ctypes.POINTER(ctypes.c_double)]
     _lib = L
     return L
 
@@ -107,15 +109,20 @@ def debug_tensors(desc, B, flags):
     return out
 
 
-def profile_records():
-    """[(name, ms, flops)] of the launches recorded with FLAG_PROFILE on this thread; clears the records."""
+def profile_records(with_bytes=False):
+    """[(name, ms, flops[, algorithmic HBM bytes])] of the launches recorded with FLAG_PROFILE on this thread; clears the records."""
     L = lib()
     out = []
     name = ctypes.create_string_buffer(256)
     ms = ctypes.c_float()
     fl = ctypes.c_double()
+    by = ctypes.c_double()
     for i in range(L.wf_profile_count()):
         check(L.wf_profile_read(i, name, 256, ctypes.byref(ms), ctypes.byref(fl)), 'wf_profile_read')
-        out.append((name.value.decode(), ms.value, fl.value))
+        if with_bytes:
+            check(L.wf_profile_bytes(i, ctypes.byref(by)), 'wf_profile_bytes')
+            out.append((name.value.decode(), ms.value, fl.value, by.value))
+        else:
+            out.append((name.value.decode(), ms.value, fl.value))
     L.wf_profile_reset()
     return out

@@ -50,7 +50,7 @@ class _BlockFunction(torch.autograd.Function):
     def forward(ctx, blk, x, *params):
         flat, running, nbt = blk._wf_state()
         train = blk.training
-        need_grad = train and any(ctx.needs_input_grad)
+        need_grad = any(ctx.needs_input_grad)          # eval mode too: BatchNorm back-propagates as the fixed affine it is
         flags = (_lib.FLAG_TRAIN if train else 0) | (_lib.FLAG_SAVE if need_grad else 0)
         desc = list(blk._wf_desc_key())
         B = x.shape[0]

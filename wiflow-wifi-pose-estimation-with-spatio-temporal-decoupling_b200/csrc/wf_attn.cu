@@ -361,12 +361,8 @@ cudaError_t launch_attn(const AttnP& p, cudaStream_t st)
     if (MODE == ATT_BWD) smem += (size_t)2 * RT * GH * L * LP * sizeof(float);
     if (smem < (size_t)RT * GH * L * sizeof(float2)) smem = (size_t)RT * GH * L * sizeof(float2);      // statistics passes reuse the tile
     auto kern = attn_kernel<L, LP, RT, GH, WIDTH, MODE>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static WfSmemOptIn optin;
+    if (cudaError_t e = wf_smem_optin(optin, kern, smem)) return e;
     const int nrows = WIDTH ? 15 * p.B : p.N;
     wf_launch_pdl(kern, dim3(dim3((nrows + RT - 1) / RT, 8 / GH)), dim3(RT * GH * L), smem, st, p);
     return cudaGetLastError();

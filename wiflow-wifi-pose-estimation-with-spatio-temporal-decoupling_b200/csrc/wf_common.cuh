@@ -221,8 +221,40 @@ __device__ __forceinline__ void block_accum2(float a, float b, double* d0, doubl
     __syncthreads();
 }
 
-// ---- host side: launch with the programmatic-stream-serialisation attribute (CUDA-graph capturable) ----
+// ---- host side ----
+#include <atomic>
 #include <cstdlib>
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only, so the opt-in is remembered per device
+// (a process may drive several GPUs: model.to('cuda:1'), tests on another ordinal) and is safe to race on (autograd's backward
+// runs on its own thread).  `st` is a function-local static of the call site; it holds the largest size opted in per device.
+struct WfSmemOptIn { std::atomic<int> bytes[32]; };
+template <class K>
+inline cudaError_t wf_smem_optin(WfSmemOptIn& st, K kern, size_t bytes)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    dev &= 31;
+    if ((int)bytes <= st.bytes[dev].load(std::memory_order_relaxed)) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    st.bytes[dev].store((int)bytes, std::memory_order_relaxed);
+    return cudaSuccess;
+}
+// multiprocessor count of the current device (cached per device ordinal)
+inline int wf_device_sms()
+{
+    static std::atomic<int> cache[32];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    int v = cache[dev & 31].load(std::memory_order_relaxed);
+    if (v <= 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cache[dev & 31].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+// launch with the programmatic-stream-serialisation attribute (CUDA-graph capturable)
 // Set per call by the forward / backward schedules (wf_model.cu): on for small batches, where the step is a chain of short launches
 // (B = 64: 2.64 -> 2.53 ms), off for large ones, where early-resident dependents only take slots from the running kernel
 // (measured: eval forward at 4096 windows per pass 232.9 k samples/s without, 220.6 k with; B = 1024 training: no difference).

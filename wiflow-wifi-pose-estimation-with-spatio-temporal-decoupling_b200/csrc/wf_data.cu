@@ -243,12 +243,9 @@ cudaError_t wf_launch_window_load(const float* src, const long long* idx, long l
 {
     const int W = C * T;
     const size_t smem = spans ? (size_t)((W + 3) / 4 * 4) * sizeof(float) : 0;     // only masked windows are staged in shared memory
-    static size_t opted = 0;
-    if (smem > 48 * 1024 && smem > opted) {
-        cudaError_t e = cudaFuncSetAttribute(window_load_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        opted = smem;
-    }
+    static WfSmemOptIn optin;
+    if (smem > 48 * 1024)
+        if (cudaError_t e = wf_smem_optin(optin, window_load_kernel, smem)) return e;
     window_load_kernel<<<B, DATA_THREADS, smem, stream>>>(src, idx, n_src, dst, W, C, T, sc, st, spans, stats);
     return cudaGetLastError();
 }

@@ -55,6 +55,12 @@ __global__ void bn_finalize_bwd_kernel(BnBwdFin a, BnBwdFin b, int n)
     double c1 = s0 / cnt, c2 = sx / cnt;
     double be = -alpha * c2 * rstd;
     d.alpha[c] = (float)alpha;
+    if (d.frozen) {          // statistics are constants: no mean / variance terms; the conv bias in front has a real gradient
+        d.beta_c[c] = 0.f;
+        d.delta[c] = 0.f;
+        if (d.conv_dbias) d.conv_dbias[c] = (float)(alpha * s0);
+        return;
+    }
     d.beta_c[c] = (float)be;
     d.delta[c] = (float)(-alpha * c1);
 }

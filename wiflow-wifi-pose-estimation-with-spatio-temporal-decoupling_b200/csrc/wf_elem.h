@@ -22,6 +22,8 @@ struct BnBwdFin {
     const float *gamma, *mean, *rstd;
     float *dgamma, *dbeta;              // may be nullptr
     float *alpha, *beta_c, *delta;
+    int frozen;                         // eval-mode BatchNorm (running statistics): a fixed per-channel affine, dx = gamma*rstd*dy
+    float* conv_dbias;                  // frozen only: gradient of the bias of the conv feeding this BatchNorm (or nullptr)
 };
 struct BnEvalEntry { int C, Cpad, gamma_off, run_off, coef_off; };
 struct BnEvalTable { int n; BnEvalEntry e[WF_MAX_BN]; };

@@ -232,12 +232,8 @@ template <int BM>
 cudaError_t launch_group(const ConvP& p, cudaStream_t st)
 {
     constexpr int smem = (2 * G_KMAX * G_XS + 2 * 3 * G_KMAX * (BM + 8)) * 4;
-    static bool cfg = false;
-    if (!cfg) {
-        cudaError_t e = cudaFuncSetAttribute(group_conv_kernel<BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        cfg = true;
-    }
+    static WfSmemOptIn optin;
+    if (cudaError_t e = wf_smem_optin(optin, group_conv_kernel<BM>, smem)) return e;
     dim3 grid((p.N + G_BN - 1) / G_BN, 1, p.groups);
     wf_launch_pdl(group_conv_kernel<BM>, dim3(grid), dim3(G_NT), smem, st, p);
     return cudaGetLastError();
@@ -462,12 +458,8 @@ cudaError_t wf_launch_group_wgrad(const WgradP& p, int num_sms, cudaStream_t st)
 {
     constexpr int smem = 2 * GW_STAGE * 4;
     static_assert(2 * GW_STAGE >= 3 * 32 * 32, "reduction buffer must fit the stage buffers");
-    static bool cfg = false;
-    if (!cfg) {
-        cudaError_t e = cudaFuncSetAttribute(group_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        cfg = true;
-    }
+    static WfSmemOptIn optin;
+    if (cudaError_t e = wf_smem_optin(optin, group_wgrad_kernel, smem)) return e;
     static const int rounds = [] { const char* e = std::getenv("WF_GROUP_WGRAD_ROUNDS"); const int v = e ? std::atoi(e) : 0; return v > 0 ? v : 1; }();
     long long splits = ((long long)rounds * num_sms) / p.groups;         // one round of one-CTA-per-SM (measured: every extra round costs 14 us per launch in prime + reduction)
     const long long max_splits = (p.N + 8LL * GW_KCH - 1) / (8LL * GW_KCH);

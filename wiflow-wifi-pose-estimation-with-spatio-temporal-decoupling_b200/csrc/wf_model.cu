@@ -26,7 +26,7 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 constexpr int T = WF_T;
 
 // opt-in per-launch timing (WF_FLAG_PROFILE): CUDA events around every kernel launch, read back with wf_profile_read
-struct ProfRec { std::string name; cudaEvent_t a, b; double flops; };
+struct ProfRec { std::string name; cudaEvent_t a, b; double flops, bytes; };
 thread_local std::vector<ProfRec> g_prof;
 std::atomic<long long> g_launches{0};
 // windows per pass of an eval-mode forward (bounds the workspace); WF_EVAL_CHUNK overrides it for measurements
@@ -418,11 +418,11 @@ bool side_stream(SideStream& out)
 
 struct Scope {          // one kernel launch (or launch pair): counts it and, when profiling, brackets it with events
     Ctx& c; int idx = -1;
-    Scope(Ctx& c_, const std::string& name, double flops = 0.0) : c(c_)
+    Scope(Ctx& c_, const std::string& name, double flops = 0.0, double bytes = 0.0) : c(c_)
     {
         g_launches.fetch_add(1, std::memory_order_relaxed);
         if (!c.profile) return;
-        ProfRec r{name, nullptr, nullptr, flops};
+        ProfRec r{name, nullptr, nullptr, flops, bytes};
         cudaEventCreate(&r.a); cudaEventCreate(&r.b);
         cudaEventRecord(r.a, c.st);
         g_prof.push_back(r);
@@ -433,6 +433,14 @@ struct Scope {          // one kernel launch (or launch pair): counts it and, wh
 
 // dense multiply-add count of one pass over conv unit u (forward, backward-data and backward-weights all do this many)
 double conv_flops(const ConvUnit& u, long long N) { return 2.0 * u.groups * u.cout_g * u.cin_g * u.ntaps * u.pout * (double)N; }
+
+// algorithmic HBM bytes of one pass over conv unit u: every operand tensor once (kind 0 forward: input + output; 1 backward-data:
+// dy + raw of the output side, the input-side raw for the SiLU', the input gradient; 2 backward-weights: dy + raw + input)
+double conv_bytes(const ConvUnit& u, long long N, int kind)
+{
+    const double in = 4.0 * u.groups * u.cin_g * u.pin * (double)N, out = 4.0 * u.groups * u.cout_g * u.pout * (double)N;
+    return kind == 0 ? in + out : kind == 1 ? 2 * out + 2 * in : 2 * out + in;
+}
 
 struct Pro { int mode; int bn; Mask mask; };
 Pro pro_none() { return Pro{PRO_NONE, -1, no_mask()}; }
@@ -457,7 +465,7 @@ void fwd_conv(Ctx& c, int ui, Act in, Pro pro)
     p.epi_mode = c.train ? EPI_STATS : EPI_STORE;
     p.stat0 = bo.f0; p.stat1 = bo.f1;
     if (u.sl) p.wtc = c.n.slpacked + u.sl_fpack;
-    Scope sc(c, std::string(u.tc ? "tc_fwd " : wf_slabtc_conv_ok(p) ? "slab_fwd " : wf_slide_conv_ok(p) ? (wf_slide_conv_is_thin(p) ? "slidethin_fwd " : "slide_fwd ") : wf_thin_conv_ok(p) ? "thin_fwd " : wf_group_conv_ok(p) ? "group_fwd " : "conv_fwd ") + u.name, conv_flops(u, c.N));
+    Scope sc(c, std::string(u.tc ? "tc_fwd " : wf_slabtc_conv_ok(p) ? "slab_fwd " : wf_slide_conv_ok(p) ? (wf_slide_conv_is_thin(p) ? "slidethin_fwd " : "slide_fwd ") : wf_thin_conv_ok(p) ? "thin_fwd " : wf_group_conv_ok(p) ? "group_fwd " : "conv_fwd ") + u.name, conv_flops(u, c.N), conv_bytes(u, c.N, 0));
     if (u.tc) { p.wtc = c.n.tcpacked + u.tc_fpack; p.tc_kt = (u.cin_g + TC_KC - 1) / TC_KC; c.ck(wf_launch_tc_conv(p, c.sms, c.st)); }
     else c.ck(wf_launch_conv(p, c.st));
 }
@@ -497,6 +505,10 @@ void bwd_fin(Ctx& c, int bn_a, int bn_b = -1)
         f.gamma = c.params + b.gamma_off; f.mean = b.mean(); f.rstd = b.rstd();
         f.dgamma = c.grads + b.gamma_off; f.dbeta = c.grads + b.gamma_off + b.C;
         f.alpha = b.alpha(); f.beta_c = b.betac(); f.delta = b.delta();
+        f.frozen = c.train ? 0 : 1;
+        if (f.frozen)
+            for (const ConvUnit& u : c.n.conv)
+                if (u.bn == bi && u.b_off >= 0) f.conv_dbias = c.grads + u.b_off;
         d[k++] = f;
     }
     Scope sc(c, "bn_fin_bwd");
@@ -527,7 +539,7 @@ void dgrad_conv(Ctx& c, int ui, float* out, int epi, int src_bn, const float* sr
         p.stat0 = bs.b0; p.stat1 = bs.b1;
     }
     if (u.sl) p.wtc = c.n.slpacked + u.sl_bpack;
-    Scope sc(c, std::string(u.tc ? "tc_dgrad " : wf_slabtc_conv_ok(p) ? "slab_dgrad " : wf_slide_conv_ok(p) ? (wf_slide_conv_is_thin(p) ? "slidethin_dgrad " : "slide_dgrad ") : wf_thin_conv_ok(p) ? "thin_dgrad " : wf_group_conv_ok(p) ? "group_dgrad " : "conv_dgrad ") + u.name, conv_flops(u, c.N));
+    Scope sc(c, std::string(u.tc ? "tc_dgrad " : wf_slabtc_conv_ok(p) ? "slab_dgrad " : wf_slide_conv_ok(p) ? (wf_slide_conv_is_thin(p) ? "slidethin_dgrad " : "slide_dgrad ") : wf_thin_conv_ok(p) ? "thin_dgrad " : wf_group_conv_ok(p) ? "group_dgrad " : "conv_dgrad ") + u.name, conv_flops(u, c.N), conv_bytes(u, c.N, 1));
     if (u.tc) { p.wtc = c.n.tcpacked + u.tc_bpack; p.tc_kt = (u.cout_g + TC_KC - 1) / TC_KC; c.ck(wf_launch_tc_conv(p, c.sms, c.st)); }
     else c.ck(wf_launch_conv(p, c.st));
 }
@@ -546,7 +558,7 @@ void wgrad_conv(Ctx& c, int ui, Act in, Pro pro)
     p.pmul = u.stride;
     for (int t = 0; t < u.ntaps; ++t) { p.dp[t] = u.dpf[t]; p.dn[t] = u.dnf[t]; }
     p.dw = c.grads + u.w_off;
-    Scope sc(c, std::string(u.tc ? "tc_wgrad " : wf_slide_wgrad_ok(p) ? "slide_wgrad " : wf_thin_wgrad_ok(p) ? "thin_wgrad " : wf_group_wgrad_ok(p) ? "group_wgrad " : "conv_wgrad ") + u.name, conv_flops(u, c.N));
+    Scope sc(c, std::string(u.tc ? "tc_wgrad " : wf_slide_wgrad_ok(p) ? "slide_wgrad " : wf_thin_wgrad_ok(p) ? "thin_wgrad " : wf_group_wgrad_ok(p) ? "group_wgrad " : "conv_wgrad ") + u.name, conv_flops(u, c.N), conv_bytes(u, c.N, 2));
     cudaStream_t ws = c.st;
     if (c.side) {                     // fork: everything this kernel reads has been enqueued on the main stream by now
         c.ck(cudaEventRecord(c.fork, c.st));
@@ -803,27 +815,18 @@ void eval_coefs(Ctx& c)
     c.ck(wf_launch_bn_eval_coefs(tab, c.params, c.running, n.bn[0].coef, c.st));
 }
 
-int num_sms()
-{
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
-        sms = v;
-    }
-    return sms;
-}
+int num_sms() { return wf_device_sms(); }
 
 int check_device()
 {
-    static int ok = 0;
-    if (ok) return 0;
+    static std::atomic<unsigned> ok_mask{0};           // bit = device ordinal already checked
     int dev = 0, major = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return fail((int)e, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (ok_mask.load(std::memory_order_relaxed) & (1u << (dev & 31))) return 0;
     cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
     if (major != 10) return fail(WF_E_ARCH, "libwiflow_b200 is compiled for sm_100a only; device compute capability major = " + std::to_string(major));
-    ok = 1;
+    ok_mask.fetch_or(1u << (dev & 31), std::memory_order_relaxed);
     return 0;
 }
 
@@ -853,7 +856,8 @@ int run_forward(const wf_block_desc* d, const float* x, const float* params, flo
     if (!d || !x || !params || !y || !ws || B <= 0) return fail(WF_E_ARG, "null pointer or non-positive batch");
     const bool train = (flags & WF_FLAG_TRAIN) != 0;
     if (!train && !running) return fail(WF_E_ARG, "eval mode needs the running statistics");
-    if (!train && (flags & WF_FLAG_SAVE_FOR_BACKWARD)) return fail(WF_E_UNSUPPORTED, "backward is only implemented for train-mode BatchNorm");
+    if (!train && (flags & WF_FLAG_SAVE_FOR_BACKWARD) && B > EVAL_CHUNK)
+        return fail(WF_E_UNSUPPORTED, "eval-mode forward with saved activations takes at most " + std::to_string(EVAL_CHUNK) + " windows per call");
     Net n;
     if (int e = build_net(d, n)) return e;
     const size_t need = layout(n, B, flags, (char*)ws);
@@ -917,13 +921,14 @@ int run_backward(const wf_block_desc* d, const float* x, const float* params, co
     if (int e = check_device()) return e;
     wf_pdl_mode = B <= WF_PDL_MAX_B ? 1 : 0;
     if (!d || !x || !params || !dy || !grads || !ws || B <= 0) return fail(WF_E_ARG, "null pointer or non-positive batch");
-    if ((flags & (WF_FLAG_TRAIN | WF_FLAG_SAVE_FOR_BACKWARD)) != (WF_FLAG_TRAIN | WF_FLAG_SAVE_FOR_BACKWARD))
-        return fail(WF_E_UNSUPPORTED, "backward needs a forward run with WF_FLAG_TRAIN|WF_FLAG_SAVE_FOR_BACKWARD");
+    if (!(flags & WF_FLAG_SAVE_FOR_BACKWARD))
+        return fail(WF_E_UNSUPPORTED, "backward needs a forward run with WF_FLAG_SAVE_FOR_BACKWARD");
+    const bool train = (flags & WF_FLAG_TRAIN) != 0;          // eval mode: BatchNorm is a fixed affine of the running statistics, dropout is off
     Net n;
     if (int e = build_net(d, n)) return e;
     const size_t need = layout(n, B, flags, (char*)ws);
     if (need > ws_bytes) return fail(WF_E_WORKSPACE, "workspace too small: need " + std::to_string(need) + " bytes");
-    Ctx c{n, params, grads, nullptr, nullptr, masks, B, (long long)B * T, true, true, st, num_sms()};
+    Ctx c{n, params, grads, nullptr, nullptr, masks, B, (long long)B * T, train, true, st, num_sms()};
     c.profile = (flags & WF_FLAG_PROFILE) != 0;
     SideStream ss{};
     if (!c.profile && g_overlap_wgrad && side_stream(ss)) { c.side = ss.s; c.fork = ss.fork; }     // profiling times every kernel alone
@@ -1062,6 +1067,12 @@ WF_API int wf_profile_read(int i, char* name, int name_cap, float* ms, double* f
     if (name && name_cap > 0) { std::strncpy(name, r.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
     if (ms) cudaEventElapsedTime(ms, r.a, r.b);
     if (flops) *flops = r.flops;
+    return 0;
+}
+WF_API int wf_profile_bytes(int i, double* bytes)
+{
+    if (i < 0 || i >= (int)g_prof.size() || !bytes) return WF_E_ARG;
+    *bytes = g_prof[i].bytes;
     return 0;
 }
 WF_API void wf_profile_reset(void)

@@ -732,12 +732,7 @@ bool make_map(CUtensorMap* tm, const float* base, int C, int P, long long N, lon
               CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-int dev_sms()
-{
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
-    return v;
-}
+int dev_sms() { return wf_device_sms(); }
 
 constexpr int SMEM_LIMIT = 227 * 1024;
 
@@ -813,15 +808,8 @@ size_t smem_bytes(const SlabGeom& g)
 template <int PRO, bool MASK, int CH>
 cudaError_t launch_t(const CUtensorMap& a, const CUtensorMap& b, const ConvP& p, const SlabGeom& g, int grid, cudaStream_t st)
 {
-    static std::atomic<unsigned long long> configured{0};          // one opt-in per device (bit = device ordinal)
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const unsigned long long bit = 1ull << (dev & 63);
-    if (!(configured.load(std::memory_order_relaxed) & bit)) {
-        cudaError_t e = cudaFuncSetAttribute(slab_tc_kernel<PRO, MASK, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-        if (e != cudaSuccess) return e;
-        configured.fetch_or(bit, std::memory_order_relaxed);
-    }
+    static WfSmemOptIn optin;
+    if (cudaError_t e = wf_smem_optin(optin, slab_tc_kernel<PRO, MASK, CH>, SMEM_LIMIT)) return e;
     wf_launch_pdl(slab_tc_kernel<PRO, MASK, CH>, dim3(grid), dim3(NTHR), smem_bytes(g), st, a, b, p, g);
     return cudaGetLastError();
 }

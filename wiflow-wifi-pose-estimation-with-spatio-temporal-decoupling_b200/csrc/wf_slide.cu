@@ -908,16 +908,7 @@ const int g_slide_min_ch_wgrad = [] { const char* e = std::getenv("WF_SLIDE_MIN_
 constexpr int SMEM_MAX = 227 * 1024;
 constexpr int PS_MAX = 4;
 
-int device_sms()
-{
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
-        sms = v;
-    }
-    return sms;
-}
+int device_sms() { return wf_device_sms(); }
 
 // window geometry for steps of PS positions: widest step (slabs one step reads), the ring that lets the next step land while
 // the current one is read, and the most slabs a step adds
@@ -987,12 +978,8 @@ cudaError_t launch_slide_conv(const ConvP& p, int num_sms, cudaStream_t st, bool
     if (!g.PS) return cudaErrorInvalidConfiguration;
     const size_t smem = wbytes + g.R * slab;
     if (dry) return cudaSuccess;
-    static size_t cfg = 0;
-    if (smem > cfg) {
-        cudaError_t e = cudaFuncSetAttribute(slide_conv_kernel<MI, NI, MW, NW, LD, MINB, PRO, HASDN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        cfg = smem;
-    }
+    static WfSmemOptIn optin;
+    if (cudaError_t e = wf_smem_optin(optin, slide_conv_kernel<MI, NI, MW, NW, LD, MINB, PRO, HASDN>, smem)) return e;
     int occ = (int)((size_t)SMEM_MAX / (smem + 2048));
     if (occ > MINB) occ = MINB;
     if (occ < 1) occ = 1;
@@ -1045,12 +1032,8 @@ cudaError_t launch_slide_thin(const ConvP& p, int num_sms, cudaStream_t st, bool
     if (!g.PS) return cudaErrorInvalidConfiguration;
     const size_t smem = fixed + g.R * slab;
     if (dry) return cudaSuccess;
-    static size_t cfg = 0;
-    if (smem > cfg) {
-        cudaError_t e = cudaFuncSetAttribute(slide_thin_kernel<MI, NTAPS, K8S, LD, MINB, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        cfg = smem;
-    }
+    static WfSmemOptIn optin;
+    if (cudaError_t e = wf_smem_optin(optin, slide_thin_kernel<MI, NTAPS, K8S, LD, MINB, PRO>, smem)) return e;
     int occ = (int)((size_t)SMEM_MAX / (smem + 2048));
     if (occ > MINB) occ = MINB;
     if (occ < 1) occ = 1;
@@ -1139,12 +1122,8 @@ cudaError_t launch_slide_wgrad(const WgradP& p, const WgCfg& c, int num_sms, cud
     if (smem < image) smem = image;
     if (smem > (size_t)SMEM_MAX - 1024) return cudaErrorInvalidConfiguration;
     if (dry) return cudaSuccess;
-    static size_t cfg = 0;
-    if (smem > cfg) {
-        cudaError_t e = cudaFuncSetAttribute(slide_wgrad_kernel<MTW, NTW, NTAPS, LDG, LDX, MINB, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        cfg = smem;
-    }
+    static WfSmemOptIn optin;
+    if (cudaError_t e = wf_smem_optin(optin, slide_wgrad_kernel<MTW, NTW, NTAPS, LDG, LDX, MINB, PRO>, smem)) return e;
     int occ = (int)((size_t)SMEM_MAX / (smem + 1024));
     if (occ > MINB) occ = MINB;
     if (occ < 1) occ = 1;

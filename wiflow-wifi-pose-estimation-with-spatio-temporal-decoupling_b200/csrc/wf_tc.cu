@@ -515,12 +515,8 @@ constexpr int SMEM_MAX = 200 * 1024;
 template <int PRO, bool MASK>
 cudaError_t launch_conv_t(const ConvP& p, const TcGeom& g, dim3 grid, int smem, cudaStream_t st)
 {
-    static bool cfg = false;
-    if (!cfg) {
-        cudaError_t e = cudaFuncSetAttribute(pw_tc_kernel<PRO, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
-        if (e != cudaSuccess) return e;
-        cfg = true;
-    }
+    static WfSmemOptIn optin;
+    if (cudaError_t e = wf_smem_optin(optin, pw_tc_kernel<PRO, MASK>, SMEM_MAX)) return e;
     wf_launch_pdl(pw_tc_kernel<PRO, MASK>, dim3(grid), dim3(NTHREADS), smem, st, p, g);
     return cudaGetLastError();
 }
@@ -529,12 +525,8 @@ template <int GPRO, int XPRO, bool MASK>
 cudaError_t launch_wgrad_t(const WgradP& p, int bn, int nt, long long per, dim3 grid, cudaStream_t st)
 {
     constexpr int smem = WG_STAGES * WG_STAGE_BYTES + (2 * WG_STAGES + 1) * 8 + 16;
-    static bool cfg = false;
-    if (!cfg) {
-        cudaError_t e = cudaFuncSetAttribute(pw_wgrad_tc_kernel<GPRO, XPRO, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        cfg = true;
-    }
+    static WfSmemOptIn optin;
+    if (cudaError_t e = wf_smem_optin(optin, pw_wgrad_tc_kernel<GPRO, XPRO, MASK>, smem)) return e;
     wf_launch_pdl(pw_wgrad_tc_kernel<GPRO, XPRO, MASK>, dim3(grid), dim3(NTHREADS), smem, st, p, bn, nt, per);
     return cudaGetLastError();
 }

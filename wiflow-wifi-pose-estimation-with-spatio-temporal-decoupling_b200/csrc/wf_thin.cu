@@ -197,12 +197,12 @@ cudaError_t wf_launch_thin_conv(const ConvP& p, cudaStream_t st)
     const int threads = (THIN_NT / 4) * PC;
     cudaError_t e;
     if (coutp == 8) {
-        static bool cfg = false;
-        if (!cfg) { e = cudaFuncSetAttribute(thin_conv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); if (e) return e; cfg = true; }
+        static WfSmemOptIn optin;
+        if ((e = wf_smem_optin(optin, thin_conv_kernel<8>, 100 * 1024))) return e;
         wf_launch_pdl(thin_conv_kernel<8>, dim3(grid), dim3(threads), smem, st, p, PC);
     } else {
-        static bool cfg = false;
-        if (!cfg) { e = cudaFuncSetAttribute(thin_conv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); if (e) return e; cfg = true; }
+        static WfSmemOptIn optin;
+        if ((e = wf_smem_optin(optin, thin_conv_kernel<16>, 100 * 1024))) return e;
         wf_launch_pdl(thin_conv_kernel<16>, dim3(grid), dim3(threads), smem, st, p, PC);
     }
     return cudaGetLastError();
@@ -230,12 +230,8 @@ static cudaError_t launch_thin_wgrad_t(const WgradP& p, int num_sms, cudaStream_
     const int nregions = ((p.N + TW_NT - 1) / TW_NT) * ((p.Pout + TW_PC - 1) / TW_PC);
     int grid = num_sms * 2;
     if (grid > nregions) grid = nregions;
-    static bool cfg = false;
-    if (!cfg) {
-        cudaError_t e = cudaFuncSetAttribute(thin_wgrad_kernel<CINP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        if (e) return e;
-        cfg = true;
-    }
+    static WfSmemOptIn optin;
+    if (cudaError_t e = wf_smem_optin(optin, thin_wgrad_kernel<CINP>, 100 * 1024)) return e;
     wf_launch_pdl(thin_wgrad_kernel<CINP>, dim3(grid), dim3(warps * 32), smem, st, p, coutp, PS, nregions);
     return cudaGetLastError();
 }

@@ -57,17 +57,32 @@ def split_files(n_files, window_ranges, random_seed=42):
     return out, parts
 
 
-def shard_epoch(indices, batch_size, shuffle, drop_last=False, rank=0, world=1):
+def shard_epoch(indices, batch_size, shuffle, drop_last=False, rank=0, world=1, order_seed=None):
     """This rank's batches of one epoch: the DataLoader order over `indices` cut into global batches of batch_size * world windows,
-    of which rank keeps its contiguous shard (at most one window more or less than the other ranks in a ragged last batch)."""
+    of which rank keeps its contiguous shard (at most one window more or less than the other ranks in a ragged last batch).
+
+    order_seed: None replays torch's DataLoader draws on the default CPU generator (one process: the reference's batches bit for
+    bit).  With several ranks that generator does not stay in lock step (a ragged shard makes draw_augmentation consume a
+    data-dependent number of draws per rank), so the order then comes from a private generator seeded by order_seed -- the same
+    on every rank whatever else the ranks drew -- and a ragged global batch with fewer windows than ranks is dropped (a rank
+    with an empty shard would leave its peers waiting in the gradient all-reduce)."""
     from .engine import shard_bounds
     indices = np.asarray(indices, dtype=np.int64)
-    order = indices[sampler_order(len(indices), shuffle)]
+    if order_seed is None:
+        order = indices[sampler_order(len(indices), shuffle)]
+    elif shuffle:
+        g_ = torch.Generator()
+        g_.manual_seed(int(order_seed))
+        order = indices[torch.randperm(len(indices), generator=g_).numpy().astype(np.int64)]
+    else:
+        order = indices
     g = batch_size * max(1, world)
     nb = len(order) // g if drop_last else (len(order) + g - 1) // g
     out = []
     for i in range(nb):
         glob = order[i * g:(i + 1) * g]
+        if world > 1 and len(glob) < world:
+            break
         lo, hi = shard_bounds(len(glob), rank, world)
         out.append(glob[lo:hi])
     return out
@@ -191,11 +206,12 @@ class DeviceBatchLoader:
     """Iterates (x, y) CUDA batches over `indices` of a dataset in DataLoader order (batch_size, shuffle, drop_last as torch's).
     Yielded tensors stay valid until the second following batch is requested (two device slots)."""
 
-    def __init__(self, dataset, indices=None, batch_size=64, shuffle=False, drop_last=False, augment=False, rank=0, world=1):
+    def __init__(self, dataset, indices=None, batch_size=64, shuffle=False, drop_last=False, augment=False, rank=0, world=1, seed=0):
         """rank / world: data-parallel training with one process per GPU.  Every rank walks the SAME epoch order (seed
         the default torch generator identically on all ranks) in global batches of batch_size * world windows and keeps its
         contiguous shard of each (engine.shard_bounds), so world processes together see exactly the batches one process would."""
         self.rank, self.world = int(rank), max(1, int(world))
+        self.seed, self.epoch = int(seed), 0         # world > 1: the epoch order comes from a generator seeded by (seed, epoch)
         self.dataset = dataset
         self.indices = np.arange(len(dataset), dtype=np.int64) if indices is None else np.asarray(indices, dtype=np.int64)
         self.batch_size = int(batch_size)
@@ -213,10 +229,15 @@ class DeviceBatchLoader:
 
     def __len__(self):
         n, g = len(self.indices), self.batch_size * self.world
-        return n // g if self.drop_last else (n + g - 1) // g
+        nb = n // g if self.drop_last else (n + g - 1) // g
+        if self.world > 1 and not self.drop_last and 0 < n % g < self.world:
+            nb -= 1                                  # a last global batch smaller than the number of ranks is dropped
+        return nb
 
     def epoch_batches(self):
-        return shard_epoch(self.indices, self.batch_size, self.shuffle, self.drop_last, self.rank, self.world)
+        order_seed = None if self.world == 1 else self.seed * 1000003 + self.epoch
+        self.epoch += 1
+        return shard_epoch(self.indices, self.batch_size, self.shuffle, self.drop_last, self.rank, self.world, order_seed)
 
     # streaming mode: worker thread fills pinned slot k (gather out of the memory map), then the copy stream moves it
     def _fill(self, slot, idx):

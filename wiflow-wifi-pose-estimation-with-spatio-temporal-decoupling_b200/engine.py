@@ -79,6 +79,20 @@ class TrainStep:
         # [total, position, bone, mpjpe, pck(thr_0), ..., windows], each weighted by the batch size
         self.sums = torch.zeros(5 + len(self.thresholds), device=dev, dtype=torch.float64)
         self._metric_scratch = torch.zeros(16, device=dev, dtype=torch.float64)
+        if self.world > 1:
+            self.sync_replicas()
+
+    def sync_replicas(self):
+        """Rank 0's parameters, BatchNorm running statistics and optimizer state become every rank's (what nn.DataParallel's
+        replicate() does each forward, train.py:91-93: replica 0 wins).  After this the ranks stay bit-identical: they apply the
+        same all-reduced gradient through a deterministic clip + AdamW.  Called at construction; call it again after loading a
+        checkpoint on rank 0 only, or at epoch boundaries to give every rank rank 0's running statistics before validation."""
+        if self.world <= 1:
+            return
+        g = self.pg
+        src = dist.get_global_rank(g, 0) if g is not None else 0
+        for t in (self.params, self.running, self.nbt, self.exp_avg, self.exp_avg_sq, self.adam_state):
+            dist.broadcast(t, src=src, group=g)
 
     # -- pieces -----------------------------------------------------------------------------------------
     def _fwd_bwd_on(self, x, y):
@@ -120,6 +134,7 @@ class TrainStep:
 
     def _capture(self):
         saved_sums = self.sums.clone()
+        saved_acc = self.acc.clone() if self.acc is not None else None      # micro-batches accumulated before the first full-size step
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(s):
@@ -131,7 +146,7 @@ class TrainStep:
         with torch.cuda.graph(self._graph_a):
             self._fwd_bwd()
         if self.acc is not None:
-            self.acc.zero_()
+            self.acc.copy_(saved_acc)
         self.sums.copy_(saved_sums)
 
     def _capture_optim(self):

@@ -13,6 +13,7 @@ this implementation computes in fp32 (3xTF32 on the tensor cores), which is what
 import copy
 
 import torch
+import torch.distributed as dist
 from torch.optim.lr_scheduler import ReduceLROnPlateau
 
 from . import _lib, ops
@@ -105,12 +106,34 @@ class Trainer:
         self.model.train()
         return out
 
+    def _all_ranks(self, stats):
+        """window-weighted mean of per-rank epoch statistics over the process group: every rank then takes the same scheduler,
+        best-checkpoint and early-stop decisions (a rank that stopped alone would leave the others hanging in the all-reduce)"""
+        ts = self.ts
+        if ts.world <= 1:
+            return stats
+        keys = [k for k in stats if k != 'windows']
+        n = float(stats['windows'])
+        v = torch.tensor([stats[k] * n if n > 0 else 0.0 for k in keys] + [n], device=ts.dev, dtype=torch.float64)
+        dist.all_reduce(v, op=dist.ReduceOp.SUM, group=ts.pg)
+        v = v.tolist()
+        tot = v[-1]
+        out = {k: (x / tot if tot > 0 else float('inf')) for k, x in zip(keys, v[:-1])}
+        out['windows'] = int(tot)
+        return out
+
     def fit(self, train_batches, val_batches, n_epochs, checkpoint_path=None, log=None):
         bad_epochs = 0
         t0, t1 = (f'pck@{t:g}' for t in self.thresholds[:2])
         for epoch in range(n_epochs):
-            tr = self.train_epoch(train_batches())
-            va = self.validate(val_batches())
+            tr = self._all_ranks(self.train_epoch(train_batches()))
+            if self.ts.world > 1:
+                # BatchNorm statistics are local per rank (nn.DataParallel semantics, train.py:91-93: replica 0's persist):
+                # validate, checkpoint and continue with rank 0's running buffers on every rank
+                src = dist.get_global_rank(self.ts.pg, 0) if self.ts.pg is not None else 0
+                dist.broadcast(self.ts.running, src=src, group=self.ts.pg)
+                dist.broadcast(self.ts.nbt, src=src, group=self.ts.pg)
+            va = self._all_ranks(self.validate(val_batches()))
             h = self.history
             h['train_loss'].append(tr['loss']); h['val_loss'].append(va['loss'])
             h['train_position_loss'].append(tr['position']); h['train_bone_loss'].append(tr['bone'])
@@ -126,7 +149,7 @@ class Trainer:
             if va['mpjpe'] < self.best_val_mpe:
                 self.best_val_mpe = va['mpjpe']
                 self.best_state = copy.deepcopy(self.model.state_dict())
-                if checkpoint_path:
+                if checkpoint_path and (self.ts.world <= 1 or dist.get_rank(self.ts.pg) == 0):
                     torch.save(self.best_state, checkpoint_path)
                 bad_epochs = 0
             else:

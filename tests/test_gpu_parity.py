@@ -202,8 +202,9 @@ def test_autograd_path_equals_raw_ops(wf, golden):
     out = model(x)
     loss, ld = crit(out, y)
     loss.backward()
-    assert torch.equal(out.detach(), pred)
-    assert abs(loss.item() - out3[0].item()) < 1e-7 and abs(ld['position'] - out3[1].item()) < 1e-7
+    # not bitwise: the slab kernels' MMA contributions are issued by three warps and retire in varying order (fp32 rounding, ~1e-7)
+    assert rel_err(out.detach(), pred) < 2e-6
+    assert abs(loss.item() - out3[0].item()) < 1e-6 and abs(ld['position'] - out3[1].item()) < 1e-6
     flat_g = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
     assert rel_err(flat_g, grads) < 1e-5           # wgrad uses fp32 atomics: summation order may differ run to run
     assert abs(ld['bone'] - golden['nodrop_f32.loss'][2]) < 1e-4

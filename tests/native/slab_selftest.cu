@@ -182,6 +182,7 @@ static int run_case(const Case& c, int verbose)
 int main(int argc, char** argv)
 {
     setenv("WF_SLABTC_THIN", "1", 1);      // the self-test covers the 8-channel shapes too
+    setenv("WF_SLABTC_MIN_N", "0", 1);     // ... and batches below the size the model switches to these kernels at
     const int verbose = argc > 1 ? atoi(argv[1]) : 6;
     const int only = argc > 2 ? atoi(argv[2]) : -1;
     srand(1234);

@@ -826,6 +826,7 @@ cudaError_t launch_ch(const CUtensorMap& a, const CUtensorMap& b, const ConvP& p
     }
 }
 
+int min_columns() { static const int v = [] { const char* e = std::getenv("WF_SLABTC_MIN_N"); return e ? std::atoi(e) : 4096; }(); return v; }
 bool thin_enabled() { static const bool v = [] { const char* e = std::getenv("WF_SLABTC_THIN"); return e && e[0] == '1'; }(); return v; }
 const bool g_enabled = [] { const char* e = std::getenv("WF_DISABLE_SLABTC"); return !(e && e[0] == '1'); }();
 // debugging aid of the self-test: swap the two stride fields of the MN-major descriptor
@@ -871,6 +872,9 @@ bool wf_slabtc_conv_ok(const ConvP& p)
     // 8 -> 8 channel layers: the per-position cost of the TMEM round trips is not amortised (measured 147 us vs 141 us for the
     // mma.sync kernel on up.block.4); they stay on wf_slide.cu unless WF_SLABTC_THIN=1
     if (p.Cin <= 8 && p.Cout <= 8 && !thin_enabled()) return false;
+    // small batches: the kernel's fixed cost (~30 us: 227 KB CTAs, weight images, TMEM set-up, pipeline fill) exceeds the whole
+    // layer on the mma.sync path (B = 64: 2.73 ms per step with the slab kernels, 2.50 ms without)
+    if (p.N < min_columns()) return false;
     if (!wf_slabtc_shape_ok(p.Cin, p.Cout, p.groups, p.ntaps, p.dn)) return false;
     // taps: {0} or {-1, 0, +1} in ascending (forward image) or descending (backward-data image) order
     if (p.ntaps == 1 ? p.dp[0] != 0 : (p.ntaps != 3 || p.dp[1] != 0 || p.dp[0] * p.dp[2] != -1 || p.dp[0] + p.dp[2] != 0)) return false;

@@ -225,3 +225,22 @@ def test_eval_mode_backward_vs_oracle(wf):
     for k, v in model.state_dict().items():
         if k.endswith('running_mean') or k.endswith('running_var'):
             assert torch.equal(v.cpu().double(), st[k]) or rel_err(v.cpu(), st[k]) < 1e-7
+
+
+def test_train_step_b64_through_slab_kernels():
+    """the model switches the conv stack to the TMA + tcgen05 slab kernels from 4096 columns (B >= 205) up; this re-runs the B = 64
+    step test (activations, activation gradients, parameter gradients, AdamW) and the B = 4 fixture tests with the switch forced on, so
+    the slab forward AND backward-data kernels are compared with the oracle layer by layer inside the full model"""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get('WF_SLABTC_MIN_N') == '0':
+        pytest.skip('already running with the slab kernels forced on')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, WF_SLABTC_MIN_N='0')
+    r = subprocess.run([sys.executable, '-m', 'pytest', '-x', '-q', '-m', 'gpu',
+                        'tests/test_gpu_parity_sizes.py::test_train_step_b64_vs_oracle',
+                        'tests/test_gpu_parity.py::test_train_step_matches_reference_fixture',
+                        'tests/test_gpu_parity.py::test_train_intermediates_vs_oracle',
+                        'tests/test_gpu_blocks.py'], cwd=root, env=env, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]

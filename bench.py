@@ -493,6 +493,7 @@ def run_ours(args, rank, world, local_rank):
         kernels = {'pw_tc_kernel (tcgen05 3xTF32 pointwise conv, fwd + dgrad)': ('tc_fwd', 'tc_dgrad'),
                    'pw_wgrad_tc_kernel (tcgen05 3xTF32 pointwise wgrad)': ('tc_wgrad',),
                    'slab_tc_kernel (TMA + tcgen05 3xTF32 position-tap conv, fwd + dgrad)': ('slab_fwd', 'slab_dgrad'),
+                   'slab_wgrad_kernel (TMA + tcgen05 3xTF32 position-tap wgrad)': ('slab_wgrad',),
                    'slide_conv_kernel (sliding-window mma.sync 3xTF32 position-tap conv, fwd + dgrad)': ('slide_fwd', 'slide_dgrad'),
                    'slide_thin_kernel (sliding-window mma.sync 3xTF32 conv, <= 8 output channels, fwd + dgrad)': ('slidethin_fwd', 'slidethin_dgrad'),
                    'slide_wgrad_kernel (sliding-window mma.sync 3xTF32 wgrad)': ('slide_wgrad',),

@@ -179,6 +179,108 @@ static int run_case(const Case& c, int verbose)
     return ok ? 0 : 1;
 }
 
+struct WCase { const char* name; int cin, cout, ntaps, pin, pout, pmul, B; int dp[3]; int pro, mask; };
+
+static int run_wgrad_case(const WCase& c, int verbose, int bench)
+{
+    const int N = c.B * WF_T;
+    std::vector<float> X((size_t)c.cin * c.pin * N), DY((size_t)c.cout * c.pout * N), RAW(DY.size());
+    for (auto& v : X) v = frand();
+    for (size_t i = 0; i < DY.size(); ++i) { DY[i] = frand(); RAW[i] = frand(); }
+    std::vector<float> pa(c.cin), pb(c.cin), pd(c.cin), ga(c.cout), gb(c.cout), gc(c.cout), gd(c.cout), mask((size_t)c.B * c.cin);
+    for (int i = 0; i < c.cin; ++i) { pa[i] = 0.5f + 0.5f * fabsf(frand()); pb[i] = frand() * 0.2f; pd[i] = frand() * 0.3f; }
+    for (int i = 0; i < c.cout; ++i) { ga[i] = 0.5f + fabsf(frand()); gb[i] = frand() * 0.2f; gc[i] = frand() * 0.1f; gd[i] = frand() * 0.3f; }
+    for (auto& v : mask) v = (rand() % 10 < 3) ? 0.f : 1.f / 0.7f;
+    std::vector<double> R((size_t)c.cout * c.cin * c.ntaps, 0.0);
+    if (!bench) {
+        std::vector<double> Xp(X.size()), Gp(DY.size());
+        for (int ci = 0; ci < c.cin; ++ci) for (int q = 0; q < c.pin; ++q) for (int n = 0; n < N; ++n) {
+            const size_t i = ((size_t)ci * c.pin + q) * N + n;
+            double x = X[i];
+            if (c.pro == PRO_BNSILU) { x = silu((double)pa[ci] * ((double)X[i] - pd[ci]) + pb[ci]); if (c.mask) x *= mask[(size_t)(n / WF_T) * c.cin + ci]; }
+            else if (c.pro == PRO_AFFINE) x = (double)pa[ci] * ((double)X[i] - pd[ci]) + pb[ci];
+            Xp[i] = x;
+        }
+        for (int o = 0; o < c.cout; ++o) for (size_t j = 0; j < (size_t)c.pout * N; ++j) {
+            const size_t i = (size_t)o * c.pout * N + j;
+            Gp[i] = (double)ga[o] * DY[i] + (double)gb[o] * ((double)RAW[i] - gd[o]) + gc[o];
+        }
+        for (int o = 0; o < c.cout; ++o) for (int ci = 0; ci < c.cin; ++ci) for (int t = 0; t < c.ntaps; ++t) {
+            double a = 0;
+            for (int pp = 0; pp < c.pout; ++pp) {
+                const int q = pp * c.pmul + c.dp[t];
+                if (q < 0 || q >= c.pin) continue;
+                const double* gp = &Gp[((size_t)o * c.pout + pp) * N];
+                const double* xp = &Xp[((size_t)ci * c.pin + q) * N];
+                for (int n = 0; n < N; ++n) a += gp[n] * xp[n];
+            }
+            R[((size_t)o * c.cin + ci) * c.ntaps + t] = a;
+        }
+    }
+    float *dX = dev(X), *dDY = dev(DY), *dRAW = dev(RAW), *dpa = dev(pa), *dpb = dev(pb), *dpd = dev(pd), *dga = dev(ga), *dgb = dev(gb), *dgc = dev(gc), *dgd = dev(gd), *dmask = dev(mask);
+    float* dW; CK(cudaMalloc(&dW, R.size() * 4)); CK(cudaMemset(dW, 0, R.size() * 4));
+    WgradP p{};
+    p.g = dDY; p.g2 = dRAW; p.g_pro = PRO_BNBWD; p.g_a = dga; p.g_b = dgb; p.g_c = dgc; p.g_d = dgd;
+    p.in = dX; p.in_sc = (long long)c.pin * N; p.in_sp = N; p.in_sb = WF_T;
+    p.pro_mode = c.pro; p.pro_a = dpa; p.pro_b = dpb; p.pro_d = dpd;
+    if (c.pro == PRO_BNSILU && c.mask) { p.mask = dmask; p.m_sb = c.cin; p.m_sc = 1; p.m_st = 0; }
+    p.Cin = c.cin; p.Cout = c.cout; p.groups = 1; p.Pin = c.pin; p.Pout = c.pout; p.N = N; p.ntaps = c.ntaps; p.pmul = c.pmul;
+    for (int t = 0; t < c.ntaps; ++t) { p.dp[t] = c.dp[t]; p.dn[t] = 0; }
+    p.dw = dW;
+    if (!wf_slabtc_wgrad_ok(p)) { printf("%-30s: shape declined by wf_slabtc_wgrad_ok -> FAIL\n", c.name); return 1; }
+    CK(wf_launch_slabtc_wgrad(p, 0));
+    CK(cudaDeviceSynchronize());
+    int rc = 0;
+    if (bench) {
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        for (int it = 0; it < 20; ++it) CK(wf_launch_slabtc_wgrad(p, 0));
+        cudaEventRecord(e1);
+        CK(cudaDeviceSynchronize());
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        printf("%-30s wgrad %7.1fus\n", c.name, ms * 50.f);
+    } else {
+        std::vector<float> D(R.size());
+        CK(cudaMemcpy(D.data(), dW, D.size() * 4, cudaMemcpyDeviceToHost));
+        double maxe = 0, maxr = 0; int bad = 0;
+        for (size_t i = 0; i < D.size(); ++i) maxr = fmax(maxr, fabs(R[i]));
+        for (size_t i = 0; i < D.size(); ++i) {
+            double e = fabs((double)D[i] - R[i]); if (!(e <= 1e30)) e = 1e30;
+            maxe = fmax(maxe, e);
+            if (e > 2e-5 * maxr && bad < verbose) {
+                const int t = (int)(i % c.ntaps), ci = (int)((i / c.ntaps) % c.cin), o = (int)(i / ((size_t)c.ntaps * c.cin));
+                printf("   mismatch dW[%d][%d][%d] = %g expected %g\n", o, ci, t, D[i], R[i]); ++bad;
+            }
+        }
+        const bool ok = maxe <= 2e-5 * maxr;
+        printf("%-30s: max abs err %.3g (max |ref| %.3g, rel %.3g) -> %s\n", c.name, maxe, maxr, maxe / (maxr + 1e-30), ok ? "ok" : "FAIL");
+        rc = ok ? 0 : 1;
+    }
+    cudaFree(dX); cudaFree(dDY); cudaFree(dRAW); cudaFree(dpa); cudaFree(dpb); cudaFree(dpd); cudaFree(dga); cudaFree(dgb); cudaFree(dgc); cudaFree(dgd); cudaFree(dmask); cudaFree(dW);
+    return rc;
+}
+
+static const WCase g_wcases[] = {
+    {"wgrad 8->8 s1 P=24",            8,  8, 3, 24, 24, 1, 13, {-1, 0, 1}, PRO_BNSILU, 1},
+    {"wgrad 8->8 s2 P=60->30",        8,  8, 3, 60, 30, 2, 7,  {-1, 0, 1}, PRO_NONE, 0},
+    {"wgrad 8->16 s2 P=120->60",      8, 16, 3, 120, 60, 2, 5, {-1, 0, 1}, PRO_NONE, 0},
+    {"wgrad 8->16 shortcut 1 tap",    8, 16, 1, 120, 60, 2, 5, {0, 0, 0},  PRO_NONE, 0},
+    {"wgrad 16->16 s1 P=60",         16, 16, 3, 60, 60, 1, 9,  {-1, 0, 1}, PRO_BNSILU, 1},
+    {"wgrad 16->32 s2 P=60->30",     16, 32, 3, 60, 30, 2, 11, {-1, 0, 1}, PRO_NONE, 0},
+    {"wgrad 32->32 s1 P=30",         32, 32, 3, 30, 30, 1, 10, {-1, 0, 1}, PRO_BNSILU, 0},
+    {"wgrad 32->64 s2 P=30->15",     32, 64, 3, 30, 15, 2, 12, {-1, 0, 1}, PRO_NONE, 0},
+    {"wgrad 32->64 shortcut 1 tap",  32, 64, 1, 30, 15, 2, 12, {0, 0, 0},  PRO_NONE, 0},
+    {"wgrad 64->64 s1 P=15",         64, 64, 3, 15, 15, 1, 21, {-1, 0, 1}, PRO_BNSILU, 1},
+    {"wgrad 64->32 affine 1 tap",    64, 32, 1, 15, 15, 1, 8,  {0, 0, 0},  PRO_AFFINE, 0},
+};
+static const WCase g_wbench[] = {
+    {"wgrad 8->8 s1 P=240 B=1024",    8,  8, 3, 240, 240, 1, 1024, {-1, 0, 1}, PRO_BNSILU, 1},
+    {"wgrad 16->16 s1 P=60 B=1024",  16, 16, 3, 60, 60, 1, 1024,  {-1, 0, 1}, PRO_BNSILU, 1},
+    {"wgrad 32->32 s1 P=30 B=1024",  32, 32, 3, 30, 30, 1, 1024,  {-1, 0, 1}, PRO_BNSILU, 1},
+    {"wgrad 64->64 s1 P=15 B=1024",  64, 64, 3, 15, 15, 1, 1024,  {-1, 0, 1}, PRO_BNSILU, 1},
+    {"wgrad 32->64 s2 P=30 B=1024",  32, 64, 3, 30, 15, 2, 1024,  {-1, 0, 1}, PRO_NONE, 0},
+};
+
 int main(int argc, char** argv)
 {
     setenv("WF_SLABTC_THIN", "1", 1);      // the self-test covers the 8-channel shapes too
@@ -223,12 +325,26 @@ int main(int argc, char** argv)
             {"8->8 s1 P=240 B=1024 dgrad",    8,  8, 3, 240, 240, 1, 1, 1024, {1, 0, -1}, PRO_BNBWD,  EPI_DSILU, 1, 0, 0, 1, 0},
         };
         for (const Case& c : bc) if (run_case(c, 0) == 2) return 2;
+        for (const WCase& c : g_wbench) if (run_wgrad_case(c, 0, 1) == 2) return 2;
         return 0;
+    }
+    if (argc > 1 && !strcmp(argv[1], "wgrad")) {
+        int f = 0;
+        for (const WCase& c : g_wcases) { const int r = run_wgrad_case(c, 6, 0); if (r == 2) return 2; f += r; }
+        for (const WCase& c : g_wbench) if (run_wgrad_case(c, 0, 1) == 2) return 2;
+        printf(f ? "WGRAD FAILED (%d)\n" : "WGRAD PASSED\n", f);
+        return f ? 1 : 0;
     }
     int fails = 0, idx = 0;
     for (const Case& c : cases) {
         if (only >= 0 && idx++ != only) continue;
         const int r = run_case(c, verbose);
+        if (r == 2) { printf("SELFTEST ABORTED (CUDA error)\n"); return 2; }
+        fails += r;
+    }
+    for (const WCase& c : g_wcases) {
+        if (only >= 0) break;
+        const int r = run_wgrad_case(c, verbose, 0);
         if (r == 2) { printf("SELFTEST ABORTED (CUDA error)\n"); return 2; }
         fails += r;
     }

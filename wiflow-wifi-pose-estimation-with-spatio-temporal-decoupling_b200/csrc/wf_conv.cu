@@ -496,6 +496,7 @@ static cudaError_t launch_wgrad_t(WgradP p, int target_ctas, cudaStream_t st)
 
 cudaError_t wf_launch_wgrad(const WgradP& p, int num_sms, cudaStream_t st)
 {
+    if (wf_slabtc_wgrad_ok(p)) return wf_launch_slabtc_wgrad(p, st);
     if (wf_slide_wgrad_ok(p)) return wf_launch_slide_wgrad(p, num_sms, st);
     if (wf_thin_wgrad_ok(p)) return wf_launch_thin_wgrad(p, num_sms, st);
     if (wf_group_wgrad_ok(p)) return wf_launch_group_wgrad(p, num_sms, st);

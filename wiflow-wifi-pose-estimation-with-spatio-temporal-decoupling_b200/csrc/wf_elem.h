@@ -94,6 +94,8 @@ long long wf_slabtc_pack_floats(int cout, int cin, int ntaps, bool bwd);
 cudaError_t wf_launch_slabtc_pack(const SlabPackTable& tab, const float* params, float* packed, cudaStream_t st);
 bool wf_slabtc_conv_ok(const ConvP& p);
 cudaError_t wf_slabtc_debug_ts(unsigned long long* out);
+bool wf_slabtc_wgrad_ok(const WgradP& p);
+cudaError_t wf_launch_slabtc_wgrad(const WgradP& p, cudaStream_t st);
 cudaError_t wf_launch_slabtc_conv(const ConvP& p, cudaStream_t st);
 // tcgen05 pointwise-conv path (wf_tc.cu)
 long long wf_tc_pack_floats(int m, int k);

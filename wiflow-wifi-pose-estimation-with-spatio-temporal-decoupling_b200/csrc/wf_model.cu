@@ -558,7 +558,7 @@ void wgrad_conv(Ctx& c, int ui, Act in, Pro pro)
     p.pmul = u.stride;
     for (int t = 0; t < u.ntaps; ++t) { p.dp[t] = u.dpf[t]; p.dn[t] = u.dnf[t]; }
     p.dw = c.grads + u.w_off;
-    Scope sc(c, std::string(u.tc ? "tc_wgrad " : wf_slide_wgrad_ok(p) ? "slide_wgrad " : wf_thin_wgrad_ok(p) ? "thin_wgrad " : wf_group_wgrad_ok(p) ? "group_wgrad " : "conv_wgrad ") + u.name, conv_flops(u, c.N), conv_bytes(u, c.N, 2));
+    Scope sc(c, std::string(u.tc ? "tc_wgrad " : wf_slabtc_wgrad_ok(p) ? "slab_wgrad " : wf_slide_wgrad_ok(p) ? "slide_wgrad " : wf_thin_wgrad_ok(p) ? "thin_wgrad " : wf_group_wgrad_ok(p) ? "group_wgrad " : "conv_wgrad ") + u.name, conv_flops(u, c.N), conv_bytes(u, c.N, 2));
     cudaStream_t ws = c.st;
     if (c.side) {                     // fork: everything this kernel reads has been enqueued on the main stream by now
         c.ck(cudaEventRecord(c.fork, c.st));

@@ -827,7 +827,283 @@ cudaError_t launch_ch(const CUtensorMap& a, const CUtensorMap& b, const ConvP& p
 }
 
 int min_columns() { static const int v = [] { const char* e = std::getenv("WF_SLABTC_MIN_N"); return e ? std::atoi(e) : 4096; }(); return v; }
+bool wgrad_enabled() { static const bool v = [] { const char* e = std::getenv("WF_DISABLE_SLABTC_WGRAD"); return !(e && e[0] == '1'); }(); return v; }
 bool thin_enabled() { static const bool v = [] { const char* e = std::getenv("WF_SLABTC_THIN"); return e && e[0] == '1'; }(); return v; }
+// =========================================================================================================
+// backward-weights:  dW[o][i][t] = sum over output positions p and columns n of  G'[o][p][n] * X'[i][p*s + dp[t]][n]
+//
+// Both operands are K-major here (K = the column n, contiguous in the [channel][position][n] layout), so plain SWIZZLE_128B TMA
+// boxes {32 n, channels, positions} are the canonical UMMA layout.  One MMA covers a BLOCK of positions at once:
+//   A rows = (input position q0 .. q0+PA-1, input channel)        M = PA*Cin  (one or two 128-row tiles)
+//   B rows = (output position p0 .. p0+PBk-1, output channel)      N = PBk*Cout <= 128
+// so D[(q_rel, i)][(p_rel, o)] holds ALL pairs of the block; the pairs with q_rel = p_rel*s + dp[t] - dpmin are the taps.  The
+// relative layout is the same for every position block and every column range, hence a CTA accumulates its whole share of the
+// (block, 32-column stage) list into ONE set of TMEM accumulators and extracts the tap diagonals once, at the end (shared-memory
+// reduction over the block's positions, one fp32 reduction per weight and CTA into the gradient).  3xTF32 as in the forward
+// kernel: D[main | cor] += A_hi * [B_hi ; B_lo],  D[cor] += A_lo * B_hi, accumulators zero-initialised, contributions dealt to
+// the NI issuing warps.  Rows of positions outside the tensor and columns beyond N are zeroed by the transform (the activation
+// of a zero-filled element is not zero).
+// =========================================================================================================
+struct WgGeom {
+    int MT;                 // 128-row tiles of A
+    int PA, PBk;            // input / output positions per block
+    int NBr;                // B rows = PBk*Cout rounded up to 8
+    int NS, a_half, b_half; // stages; bytes of one of hi/lo of the A / B tile of a stage
+    int nblocks, ncol32;    // position blocks, 32-column stages per block
+    int s, dpmin;           // effective position stride and smallest tap offset
+    int Pin_eff;            // input positions of the (possibly strided) view
+    int tmem_cols;
+    long long stages;       // nblocks * ncol32
+    int dbg;
+};
+
+template <int XPRO, bool MASK>
+__global__ void __launch_bounds__(NTHR, 1) slab_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
+                                                             const __grid_constant__ CUtensorMap tmR, const WgradP p, const WgGeom g)
+{
+    wf_pdl_enter();
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int stage_bytes = 2 * (g.a_half + g.b_half);
+    float* tab = reinterpret_cast<float*>(smem + g.NS * stage_bytes);          // X coefficients a, b, d [64] each; G' coefficients a, b, c, d [64] each
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tab + 7 * 64);
+    const uint32_t bar0 = smem_u32(bars);
+    auto raw_full = [&](int s) { return bar0 + 8u * s; };
+    auto op_full = [&](int s) { return bar0 + 8u * (MAXNS + s); };
+    auto slab_empty = [&](int s) { return bar0 + 8u * (2 * MAXNS + s); };
+    const uint32_t all_done = bar0 + 8u * (3 * MAXNS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAXNS + 1);
+
+    if (tid == 0) {
+        for (int s = 0; s < g.NS; ++s) { mbar_init(raw_full(s), 1); mbar_init(op_full(s), NWW); mbar_init(slab_empty(s), NI); }
+        mbar_init(all_done, NI);
+        fence_mbar_init();
+    }
+    if (warp == NWW) { tmem_alloc(smem_u32(tmem_slot), g.tmem_cols); tmem_relinquish(); }
+    for (int i = tid; i < 7 * 64; i += NTHR) {
+        const int which = i >> 6, c = i & 63;
+        float v = 0.f;
+        if (which < 3) { if (XPRO != PRO_NONE && c < p.Cin) v = which == 0 ? p.pro_a[c] : which == 1 ? p.pro_b[c] : p.pro_d[c]; }
+        else if (c < p.Cout) v = which == 3 ? p.g_a[c] : which == 4 ? p.g_b[c] : which == 5 ? p.g_c[c] : p.g_d[c];
+        tab[i] = v;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp < NWW) {                      // zero the accumulators: every MMA accumulates
+        const uint32_t t0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const int ncols = g.MT * 2 * g.NBr;
+        for (int c = (warp >> 2) * 8; c < ncols; c += 32) tmem_zero<8>(t0 + c);
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const long long u0 = g.stages * blockIdx.x / gridDim.x, u1 = g.stages * (blockIdx.x + 1) / gridDim.x;
+    const int NS = g.NS;
+    const uint32_t smem0 = smem_u32(smem);
+    const int arows = g.PA * p.Cin, brows = g.PBk * p.Cout;
+
+    if (warp < NWW) {
+        // =============================== workers: transform, then the final extraction ===============================
+        // chunk id = tid + 512 j over [A rows | B rows] x 8 sixteen-byte chunks; K-major SWIZZLE_128B: chunk c of row r holds the
+        // columns 4*(c ^ (r & 7)) .. +3 of the stage.  (Decoding a thread's chunks once into registers was tried: at the 96-register
+        // budget of a 20-warp CTA it spills and runs 10-100 % slower than this loop.)
+        const int a_chunks = arows * 8, tot_chunks = a_chunks + brows * 8;
+        const int cin_sh = 31 - __clz(p.Cin), cout_sh = 31 - __clz(p.Cout);
+        int st = 0; uint32_t ph = 0;
+        int blk = (int)(u0 / g.ncol32), c32 = (int)(u0 - (long long)blk * g.ncol32);
+        for (long long u = u0; u < u1; ++u) {
+            const int n0 = c32 * 32, p0 = blk * g.PBk, q0 = p0 * g.s + g.dpmin;
+            warp_wait(raw_full(st), ph, lane);
+            const uint32_t a_hi = smem0 + (uint32_t)(st * stage_bytes), a_lo = a_hi + (uint32_t)g.a_half;
+            const uint32_t b_hi = a_lo + (uint32_t)g.a_half, b_lo = b_hi + (uint32_t)g.b_half;
+            for (int id = tid; id < tot_chunks; id += NWORK) {
+                const bool isA = id < a_chunks;
+                const int cid = isA ? id : id - a_chunks;
+                const int row = cid >> 3, quad = (cid & 7) ^ (row & 7);
+                const int n = n0 + quad * 4;
+                const uint32_t off = (uint32_t)cid * 16u;
+                float4 y;
+                if (isA) {
+                    const int pos = row >> cin_sh, c = row & (p.Cin - 1);
+                    const float4 x = lds4(a_hi + off);
+                    const bool ok = n < p.N && q0 + pos >= 0 && q0 + pos < g.Pin_eff;
+                    float mk = 1.f;
+                    if (MASK && ok) mk = __ldg(p.mask + (long long)(n / WF_T) * p.m_sb + (long long)c * p.m_sc);
+                    const float4 co = make_float4(tab[c], tab[64 + c], 0.f, tab[128 + c]);
+                    y.x = ok ? pro1<XPRO>(x.x, 0.f, mk, co) : 0.f; y.y = ok ? pro1<XPRO>(x.y, 0.f, mk, co) : 0.f;
+                    y.z = ok ? pro1<XPRO>(x.z, 0.f, mk, co) : 0.f; y.w = ok ? pro1<XPRO>(x.w, 0.f, mk, co) : 0.f;
+                } else {
+                    const int pos = row >> cout_sh, o = row & (p.Cout - 1);
+                    const float4 x = lds4(b_hi + off), x2 = lds4(b_lo + off);
+                    const bool ok = n < p.N && p0 + pos < p.Pout;
+                    const float4 co = make_float4(tab[192 + o], tab[256 + o], tab[320 + o], tab[384 + o]);
+                    y.x = ok ? pro1<PRO_BNBWD>(x.x, x2.x, 1.f, co) : 0.f; y.y = ok ? pro1<PRO_BNBWD>(x.y, x2.y, 1.f, co) : 0.f;
+                    y.z = ok ? pro1<PRO_BNBWD>(x.z, x2.z, 1.f, co) : 0.f; y.w = ok ? pro1<PRO_BNBWD>(x.w, x2.w, 1.f, co) : 0.f;
+                }
+                float4 h, l;
+                tf32_split(y.x, h.x, l.x); tf32_split(y.y, h.y, l.y); tf32_split(y.z, h.z, l.z); tf32_split(y.w, h.w, l.w);
+                sts4((isA ? a_hi : b_hi) + off, h);
+                sts4((isA ? a_lo : b_lo) + off, l);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(op_full(st));
+            if (++st == NS) { st = 0; ph ^= 1u; }
+            if (++c32 == g.ncol32) { c32 = 0; ++blk; }
+        }
+        // ---- extraction: thread = accumulator row (q_rel, i); the taps are the diagonals q_rel = p_rel*s + dp[t] - dpmin ----
+        warp_wait(all_done, 0, lane);
+        tc_fence_after();
+        float* red = reinterpret_cast<float*>(smem);                      // [Cout][Cin][ntaps], reuses the stage memory
+        const int nw = p.Cout * p.Cin * p.ntaps;
+        for (int i = tid; i < nw; i += NWORK) red[i] = 0.f;
+        asm volatile("bar.sync 1, %0;" ::"r"(NWORK) : "memory");
+        if (u1 > u0) {
+            const int lq = warp & 3, part = warp >> 2;
+            for (int mt = 0; mt < g.MT; ++mt) {
+                const int row = mt * 128 + lq * 32 + lane;
+                const int q_rel = row / p.Cin, ci = row - q_rel * p.Cin;
+                const bool rv = row < arows;
+                const uint32_t t_row = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(mt * 2 * g.NBr);
+                for (int pr = part; pr < g.PBk; pr += 4) {                // the four warps of a lane quarter share the output positions
+                    const int dq = q_rel - pr * g.s + g.dpmin;           // tap offset this (row, position) pair would be
+                    int t = -1;
+                    for (int k = 0; k < p.ntaps; ++k) if (p.dp[k] == dq) t = k;
+                    for (int o0 = 0; o0 < p.Cout; o0 += 8) {
+                        float v[8], cr[8];
+                        tmem_ldn<8>(t_row + (uint32_t)(pr * p.Cout + o0), v);
+                        tmem_ldn<8>(t_row + (uint32_t)(g.NBr + pr * p.Cout + o0), cr);
+                        tmem_ld_wait();
+                        if (rv && t >= 0) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) atomicAdd(red + ((o0 + k) * p.Cin + ci) * p.ntaps + t, v[k] + cr[k]);
+                        }
+                    }
+                }
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(NWORK) : "memory");
+        if (u1 > u0)
+            for (int i = tid; i < nw; i += NWORK) atomicAdd(p.dw + i, red[i]);
+    } else if (warp == NWW) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmR);
+            const uint32_t tx = (uint32_t)(arows + 2 * brows) * 128u;
+            int st = 0; uint32_t ph = 0;
+            int blk = (int)(u0 / g.ncol32), c32 = (int)(u0 - (long long)blk * g.ncol32);
+            for (long long u = u0; u < u1; ++u) {
+                const int n0 = c32 * 32, p0 = blk * g.PBk, q0 = p0 * g.s + g.dpmin;
+                mbar_wait(slab_empty(st), ph ^ 1u);
+                mbar_arrive_expect_tx(raw_full(st), tx);
+                const uint32_t a_hi = smem0 + (uint32_t)(st * stage_bytes);
+                const uint32_t b_hi = a_hi + 2u * (uint32_t)g.a_half, b_lo = b_hi + (uint32_t)g.b_half;
+                tma_load_3d(a_hi, &tmX, n0, 0, q0, raw_full(st));
+                tma_load_3d(b_hi, &tmG, n0, 0, p0, raw_full(st));
+                tma_load_3d(b_lo, &tmR, n0, 0, p0, raw_full(st));
+                if (++st == NS) { st = 0; ph ^= 1u; }
+                if (++c32 == g.ncol32) { c32 = 0; ++blk; }
+            }
+        }
+    } else {
+        // =============================== MMA issue ===============================
+        const int me = __shfl_sync(0xffffffffu, warp - (NWW + 1), 0);
+        const uint32_t lead = lane == 0 ? 1u : 0u;
+        const uint32_t idesc1 = umma_idesc_tf32(TILE, 2 * g.NBr, 0, 0), idesc2 = umma_idesc_tf32(TILE, g.NBr, 0, 0);     // both operands K-major
+        const uint32_t hi32 = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);           // SBO = 1024 B (8 rows), SWIZZLE_128B
+        const uint32_t lbo = 1u << 16;
+        auto mk_desc = [](uint32_t h, uint32_t l) { return ((uint64_t)h << 32) | (uint64_t)l; };
+        int st = 0; uint32_t ph = 0;
+        int item = 0;
+        for (long long u = u0; u < u1; ++u) {
+            warp_wait(op_full(st), ph, lane);
+            tc_fence_after();
+            const uint32_t a_hi16 = ((smem0 + (uint32_t)(st * stage_bytes)) & 0x3FFFFu) >> 4, a_lo16 = a_hi16 + ((uint32_t)g.a_half >> 4);
+            const uint32_t b_hi16 = a_lo16 + ((uint32_t)g.a_half >> 4);
+            for (int ks = 0; ks < 4; ++ks)
+                for (int mt = 0; mt < g.MT; ++mt, ++item) {
+                    if (item % NI != me) continue;
+                    const uint32_t ao = (uint32_t)(mt * 128 * 128 + ks * 32) >> 4, bo = (uint32_t)(ks * 32) >> 4;    // 32 B per K step inside the 128 B row
+                    const uint32_t d = tmem_base + (uint32_t)(mt * 2 * g.NBr);
+                    umma_tf32_pred(d, mk_desc(hi32, (a_hi16 + ao) | lbo), mk_desc(hi32, (b_hi16 + bo) | lbo), idesc1, lead);
+                    umma_tf32_pred(d + (uint32_t)g.NBr, mk_desc(hi32, (a_lo16 + ao) | lbo), mk_desc(hi32, (b_hi16 + bo) | lbo), idesc2, lead);
+                }
+            __syncwarp();
+            if (lane == 0) umma_commit(slab_empty(st));
+            if (++st == NS) { st = 0; ph ^= 1u; }
+        }
+        if (lane == 0) umma_commit(all_done);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == NWW) tmem_dealloc(tmem_base, g.tmem_cols);
+}
+
+// TMA map with SWIZZLE_128B over a [C][P][N] tensor viewed with a position stride (1-tap strided shortcuts read every s-th position)
+bool make_map_k(CUtensorMap* tm, const float* base, int C, int P, long long N, long long sc, long long sp, int boxC, int boxP)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)C, (cuuint64_t)P};
+    const cuuint64_t strides[2] = {(cuuint64_t)sc * 4, (cuuint64_t)sp * 4};
+    const cuuint32_t box[3] = {32, (cuuint32_t)boxC, (cuuint32_t)boxP};
+    const cuuint32_t es[3] = {1, 1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool plan_wgrad(const WgradP& p, WgGeom& g)
+{
+    g = WgGeom{};
+    int dpmin = p.dp[0], dpmax = p.dp[0];
+    for (int t = 1; t < p.ntaps; ++t) { dpmin = p.dp[t] < dpmin ? p.dp[t] : dpmin; dpmax = p.dp[t] > dpmax ? p.dp[t] : dpmax; }
+    // a single tap reads every pmul-th input position: the tensor map strides over them and the kernel sees stride 1, offset 0
+    g.s = p.ntaps == 1 ? 1 : p.pmul;
+    g.dpmin = p.ntaps == 1 ? 0 : dpmin;
+    g.Pin_eff = p.ntaps == 1 ? p.Pout : p.Pin;
+    const int span = p.ntaps == 1 ? 0 : dpmax - dpmin;
+    int best = 0;
+    for (int mt = 1; mt <= 2; ++mt) {
+        int pbk = 128 / p.Cout;
+        while (pbk > 0 && ((pbk - 1) * g.s + span + 1) * p.Cin > 128 * mt) --pbk;
+        if (pbk > p.Pout) pbk = p.Pout;
+        if (pbk <= 0) continue;
+        // cost per output position ~ (MMA work + staging of mt A tiles) / pbk
+        if (best == 0 || pbk * g.MT >= g.PBk * mt) { g.MT = mt; g.PBk = pbk; best = 1; }      // twice the rows only for at least twice the positions
+    }
+    if (!best) return false;
+    g.PA = (g.PBk - 1) * g.s + span + 1;
+    if (g.PA > 256 || g.PBk > 256) return false;
+    g.NBr = (g.PBk * p.Cout + 15) / 16 * 16;          // UMMA N granularity at M = 128
+    g.a_half = g.MT * 128 * 128;
+    g.b_half = g.NBr * 128;
+    const int fixed = 7 * 64 * 4 + (3 * MAXNS + 2) * 8 + 16 + 1024;
+    g.NS = (SMEM_LIMIT - fixed) / (2 * (g.a_half + g.b_half));
+    if (g.NS > 4) g.NS = 4;
+    if (g.NS < 2) return false;
+    if ((size_t)p.Cout * p.Cin * p.ntaps * 4 > (size_t)g.NS * 2 * (g.a_half + g.b_half)) return false;
+    g.nblocks = (p.Pout + g.PBk - 1) / g.PBk;
+    g.ncol32 = (p.N + 31) / 32;
+    g.stages = (long long)g.nblocks * g.ncol32;
+    g.tmem_cols = 32;
+    while (g.tmem_cols < g.MT * 2 * g.NBr) g.tmem_cols *= 2;
+    return g.tmem_cols <= 512;
+}
+
+template <int XPRO, bool MASK>
+cudaError_t launch_wg(const CUtensorMap& tx, const CUtensorMap& tg, const CUtensorMap& tr, const WgradP& p, const WgGeom& g, int grid, cudaStream_t st)
+{
+    static WfSmemOptIn optin;
+    if (cudaError_t e = wf_smem_optin(optin, slab_wgrad_kernel<XPRO, MASK>, SMEM_LIMIT)) return e;
+    const size_t smem = (size_t)g.NS * 2 * (g.a_half + g.b_half) + 7 * 64 * 4 + (3 * MAXNS + 2) * 8 + 16;
+    wf_launch_pdl(slab_wgrad_kernel<XPRO, MASK>, dim3(grid), dim3(NTHR), smem, st, tx, tg, tr, p, g);
+    return cudaGetLastError();
+}
+
 const bool g_enabled = [] { const char* e = std::getenv("WF_DISABLE_SLABTC"); return !(e && e[0] == '1'); }();
 // debugging aid of the self-test: swap the two stride fields of the MN-major descriptor
 const bool g_swap_lbo = [] { const char* e = std::getenv("WF_SLABTC_SWAP_LBO"); return e && e[0] == '1'; }();
@@ -909,5 +1185,43 @@ cudaError_t wf_launch_slabtc_conv(const ConvP& p, cudaStream_t st)
         case PRO_BNSILU: return mask ? launch_ch<PRO_BNSILU, true>(ta, tb, p, g, grid, st) : launch_ch<PRO_BNSILU, false>(ta, tb, p, g, grid, st);
         case PRO_AFFINE: return launch_ch<PRO_AFFINE, false>(ta, tb, p, g, grid, st);
         default: return launch_ch<PRO_BNBWD, false>(ta, tb, p, g, grid, st);
+    }
+}
+
+bool wf_slabtc_wgrad_ok(const WgradP& p)
+{
+    if (!g_enabled || !wgrad_enabled()) return false;
+    if (p.groups != 1 || !(p.ntaps == 1 || p.ntaps == 3) || p.g_pro != PRO_BNBWD || !p.g2) return false;
+    for (int t = 0; t < p.ntaps; ++t) if (p.dn[t] != 0) return false;
+    if (p.ntaps == 1 ? p.dp[0] != 0 : (p.dp[1] != 0 || p.dp[0] * p.dp[2] != -1 || p.dp[0] + p.dp[2] != 0)) return false;
+    if (!(p.Cin == 8 || p.Cin == 16 || p.Cin == 32 || p.Cin == 64) || !(p.Cout == 8 || p.Cout == 16 || p.Cout == 32 || p.Cout == 64)) return false;
+    if (p.Cin <= 8 && p.Cout <= 8 && !thin_enabled()) return false;
+    if (!(p.pmul == 1 || p.pmul == 2) || p.in_sb != WF_T || (p.N & 3) || p.N % WF_T || p.N < min_columns()) return false;
+    if (p.pro_mode == PRO_BNBWD || (p.pro_mode == PRO_BNSILU && p.mask && p.m_st != 0)) return false;
+    if ((reinterpret_cast<uintptr_t>(p.in) & 15) || (reinterpret_cast<uintptr_t>(p.g) & 15) || (reinterpret_cast<uintptr_t>(p.g2) & 15)) return false;
+    if (((p.in_sc * 4) & 15) || ((p.in_sp * 4) & 15)) return false;
+    WgGeom g;
+    return plan_wgrad(p, g);
+}
+
+cudaError_t wf_launch_slabtc_wgrad(const WgradP& p, cudaStream_t st)
+{
+    WgGeom g;
+    if (!plan_wgrad(p, g)) return cudaErrorInvalidValue;
+    { const char* e = std::getenv("WF_SLABTC_DBG"); g.dbg = e ? std::atoi(e) : 0; }
+    CUtensorMap tx, tg, tr;
+    std::memset(&tx, 0, sizeof(tx)); std::memset(&tg, 0, sizeof(tg)); std::memset(&tr, 0, sizeof(tr));
+    const bool one = p.ntaps == 1;
+    if (!make_map_k(&tx, p.in, p.Cin, one ? p.Pout : p.Pin, p.N, p.in_sc, one ? p.in_sp * p.pmul : p.in_sp, p.Cin, g.PA)) return cudaErrorInvalidValue;
+    const long long g_sc = (long long)p.Pout * p.N;
+    if (!make_map_k(&tg, p.g, p.Cout, p.Pout, p.N, g_sc, p.N, p.Cout, g.PBk)) return cudaErrorInvalidValue;
+    if (!make_map_k(&tr, p.g2, p.Cout, p.Pout, p.N, g_sc, p.N, p.Cout, g.PBk)) return cudaErrorInvalidValue;
+    int grid = dev_sms();
+    if ((long long)grid > g.stages) grid = (int)g.stages;
+    const bool mask = p.pro_mode == PRO_BNSILU && p.mask != nullptr;
+    switch (p.pro_mode) {
+        case PRO_NONE: return launch_wg<PRO_NONE, false>(tx, tg, tr, p, g, grid, st);
+        case PRO_BNSILU: return mask ? launch_wg<PRO_BNSILU, true>(tx, tg, tr, p, g, grid, st) : launch_wg<PRO_BNSILU, false>(tx, tg, tr, p, g, grid, st);
+        default: return launch_wg<PRO_AFFINE, false>(tx, tg, tr, p, g, grid, st);
     }
 }

@@ -517,13 +517,22 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
         if (pend.cnt > 0) run_epilogue(pend, true);
         if (tid == 0) stamp(g, 11);
 
-        // ---- per-channel sums: one cross-lane reduction per CTA, fp64 atomics ----
+        // ---- per-channel sums: lanes -> warp (shuffles), the four lane-quarter warps of a channel group -> CTA (shared memory),
+        //      then ONE fp64 atomic pair per channel and CTA (148 x 4 contending atomics per address made the tail 8 us long) ----
         if (epi != EPI_STORE && p.stat0 != nullptr) {
+            float* sred = reinterpret_cast<float*>(smem);            // [64 channels][4 lane quarters][2]: the operand stages are idle by now
+            asm volatile("bar.sync 1, %0;" ::"r"(NWORK) : "memory");
 #pragma unroll
             for (int c = 0; c < CH; ++c) {
                 const float a = warp_sum(et.s0[c]), bsum = warp_sum(et.s1[c]);
                 const int co = et.ec0 + c;
-                if (lane == 0 && co < p.Cout) { atomicAdd(p.stat0 + co, (double)a); atomicAdd(p.stat1 + co, (double)bsum); }
+                if (lane == 0 && co < 64) { sred[(co * 4 + (warp & 3)) * 2] = a; sred[(co * 4 + (warp & 3)) * 2 + 1] = bsum; }
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(NWORK) : "memory");
+            if (tid < 2 * p.Cout) {
+                const int co = tid >> 1, k = tid & 1;
+                const double v = (double)sred[(co * 4 + 0) * 2 + k] + (double)sred[(co * 4 + 1) * 2 + k] + (double)sred[(co * 4 + 2) * 2 + k] + (double)sred[(co * 4 + 3) * 2 + k];
+                atomicAdd((k == 0 ? p.stat0 : p.stat1) + co, v);
             }
         }
         if (tid == 0) stamp(g, 12);
@@ -920,6 +929,7 @@ __global__ void __launch_bounds__(NTHR, 1) slab_wgrad_kernel(const __grid_consta
             warp_wait(raw_full(st), ph, lane);
             const uint32_t a_hi = smem0 + (uint32_t)(st * stage_bytes), a_lo = a_hi + (uint32_t)g.a_half;
             const uint32_t b_hi = a_lo + (uint32_t)g.a_half, b_lo = b_hi + (uint32_t)g.b_half;
+            // (two chunks per trip with their loads batched was tried: 5-10 % slower at the 96-register budget)
             for (int id = tid; id < tot_chunks; id += NWORK) {
                 const bool isA = id < a_chunks;
                 const int cid = isA ? id : id - a_chunks;

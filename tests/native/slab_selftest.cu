@@ -324,8 +324,11 @@ int main(int argc, char** argv)
             {"64->64 s1 P=15 B=1024 dgrad",  64, 64, 3, 15, 15, 1, 1, 1024, {1, 0, -1},   PRO_BNBWD,  EPI_DSILU, 1, 0, 0, 1, 0},
             {"8->8 s1 P=240 B=1024 dgrad",    8,  8, 3, 240, 240, 1, 1, 1024, {1, 0, -1}, PRO_BNBWD,  EPI_DSILU, 1, 0, 0, 1, 0},
         };
-        for (const Case& c : bc) if (run_case(c, 0) == 2) return 2;
-        for (const WCase& c : g_wbench) if (run_wgrad_case(c, 0, 1) == 2) return 2;
+        const int pick = argc > 2 ? atoi(argv[2]) : -1;          // bench <i>: only case i (conv cases first, then the wgrad cases) -- for ncu
+        int k = 0;
+        for (const Case& c : bc) if ((pick < 0 || pick == k++) && run_case(c, 0) == 2) return 2;
+        k = (int)(sizeof(bc) / sizeof(bc[0]));
+        for (const WCase& c : g_wbench) if ((pick < 0 || pick == k++) && run_wgrad_case(c, 0, 1) == 2) return 2;
         return 0;
     }
     if (argc > 1 && !strcmp(argv[1], "wgrad")) {

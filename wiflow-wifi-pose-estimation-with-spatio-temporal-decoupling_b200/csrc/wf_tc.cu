@@ -11,8 +11,8 @@
 //   * weights are split and laid out ONCE per step by tc_pack_kernel as ready-to-use shared-memory images
 //     ([M tile][K chunk][hi|lo]) and arrive by one 32 KB bulk async copy (cp.async.bulk + mbarrier complete_tx) per stage;
 //   * activations go global -> registers -> (BatchNorm + SiLU + Dropout | BatchNorm-backward) -> hi/lo split -> shared
-//     memory, written by 16 producer warps so that 8 lanes always cover one 128-byte core matrix (conflict free),
-//     so the previous layer's normalisation never costs an HBM round trip.
+//     memory as an MN-major SWIZZLE_128B_BASE32B image (forward / backward-data: columns contiguous, as in HBM, no transpose;
+//     a quarter warp fills one 128-byte row), so the previous layer's normalisation never costs an HBM round trip.
 // One elected thread issues tcgen05.mma (M=128, N<=256, K=8 per instruction); tcgen05.commit releases the stage and
 // finally hands the accumulators to the same 16 warps, which run the epilogue (bias / SiLU' / BatchNorm statistics) out of
 // TMEM with one thread per output channel: the per-channel sums need no shuffles at all.
@@ -109,11 +109,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
 
     if (warp < NPW) {
         // ------------------------------ activation producers ------------------------------
-        // The tensor core wants the activation tile K-major (16 bytes = 4 consecutive channels of one column), HBM holds it
-        // column-contiguous.  A thread owns a 4-channel x 4-column micro block: four coalesced 128-bit loads (one per
-        // channel), prologue, a register transpose, four 128-bit shared stores (one per column).  Lane l stores column
-        // (s xor (l/2 mod 4)) in its s-th store so that 8 consecutive lanes always hit 8 different rows of the 8x16-byte
-        // core matrices: no bank conflicts without padding.
+        // HBM holds the activations column-contiguous, i.e. as an MN-major operand.  A thread owns 4 channels x 4 columns: four
+        // coalesced 128-bit loads (one per channel), prologue, split, and each float4 goes to shared memory as it is (round 1
+        // transposed 4x4 micro blocks in registers into a K-major image: 32 selects per chunk and thread).
         const bool active = tid < (KC / 4) * NQ;
         const int q = tid % NQ, kq = tid / NQ;
         const long long col = col0 + q * 4;
@@ -131,12 +129,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
         const long long in_sc = p.in_sc, m_sc = p.m_sc;
         const int m_st = p.m_st, Cin = p.Cin;
         const float *ca_p = p.pro_a + kq * 4, *cb_p = p.pro_b + kq * 4, *cc_p = p.pro_c + kq * 4, *cd_p = p.pro_d + kq * 4;
-        const int rot = (q >> 1) & 3;
-        const bool b0 = rot & 1, b1 = rot & 2;
-        const uint32_t sbase = (uint32_t)((q >> 1) * A_SBO + kq * A_LBO + (q & 1) * 64);
+        // MN-major operand image (SWIZZLE_128B_BASE32B): row = channel (K) of the stage, 128 bytes = 32 columns, 32-byte chunks XORed
+        // with the row index mod 4; 32-column blocks KC*128 bytes apart.  A thread's float4 (4 columns of one channel) is one 16-byte
+        // chunk of that image: no transpose, and a quarter warp (8 lanes = 8 consecutive column quads) fills one 128-byte row.
         uint32_t soff[4];
 #pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) soff[s4] = sbase + (uint32_t)((s4 ^ rot) * 16);
+        for (int j = 0; j < 4; ++j) {
+            const int row = kq * 4 + j;
+            soff[j] = (uint32_t)((q >> 3) * (KC * 128) + row * 128 + (((q & 7) ^ ((row & 3) << 1)) << 4));
+        }
         int s = 0; uint32_t ph = 0;
         for (int kc = 0; kc < KT; ++kc) {
             const int c0 = kc * KC + kq * 4;
@@ -172,19 +173,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
             pin += KC * in_sc;
             if (PRO == PRO_BNBWD) pin2 += KC * in_sc;
             if (MASK) pm += KC * m_sc;
-            // 4x4 transpose: column i of the micro block = (v[0].i, v[1].i, v[2].i, v[3].i); z[s] = column (s xor rot)
-            const float4 c0v = make_float4(v[0].x, v[1].x, v[2].x, v[3].x), c1v = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
-            const float4 c2v = make_float4(v[0].z, v[1].z, v[2].z, v[3].z), c3v = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
-            const float4 y0 = sel4(b0, c1v, c0v), y1 = sel4(b0, c0v, c1v), y2 = sel4(b0, c3v, c2v), y3 = sel4(b0, c2v, c3v);
-            const float4 z0 = sel4(b1, y2, y0), z1 = sel4(b1, y3, y1), z2 = sel4(b1, y0, y2), z3 = sel4(b1, y1, y3);
             mbar_wait(empty(s), ph ^ 1u);
             if (active) {
                 uint8_t* bh = smem + s * STAGE_BYTES + 2 * A_HALF;
                 uint8_t* bl = bh + B_HALF;
-                split_store(bh, bl, soff[0], z0);
-                split_store(bh, bl, soff[1], z1);
-                split_store(bh, bl, soff[2], z2);
-                split_store(bh, bl, soff[3], z3);
+                split_store(bh, bl, soff[0], v[0]);
+                split_store(bh, bl, soff[1], v[1]);
+                split_store(bh, bl, soff[2], v[2]);
+                split_store(bh, bl, soff[3], v[3]);
             }
             fence_proxy_async_smem();
             __syncwarp();
@@ -234,7 +230,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
     } else if (warp == NPW) {
         // ------------------------------ MMA issue (one thread) ------------------------------
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32(BM, BN, 0, 0);
+            const uint32_t idesc = umma_idesc_tf32(BM, BN, 0, 1);             // A (weights) K-major, B (activations) MN-major
             const uint32_t tmem_cor = tmem_base + (uint32_t)g.bnp;
             int s = 0; uint32_t ph = 0;
             for (int kc = 0; kc < KT; ++kc) {
@@ -246,7 +242,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
 #pragma unroll
                 for (int kk = 0; kk < KC / 8; ++kk) {
                     const uint64_t dah = umma_desc(a_hi + kk * 2 * A_LBO, A_LBO, A_SBO), dal = umma_desc(a_lo + kk * 2 * A_LBO, A_LBO, A_SBO);
-                    const uint64_t dbh = umma_desc(b_hi + kk * 2 * A_LBO, A_LBO, A_SBO), dbl = umma_desc(b_lo + kk * 2 * A_LBO, A_LBO, A_SBO);
+                    // 8 channels = 8 rows of 128 bytes per K step; 32-column blocks KC*128 bytes apart; groups of 4 rows 512 bytes apart
+                    const uint64_t dbh = umma_desc_l(b_hi + kk * 1024, KC * 128, 512, 1), dbl = umma_desc_l(b_lo + kk * 1024, KC * 128, 512, 1);
                     const uint32_t accf = (kc | kk) != 0 ? 1u : 0u;
                     umma_tf32(tmem_cor, dal, dbh, idesc, accf);
                     umma_tf32(tmem_cor, dah, dbl, idesc, 1u);
@@ -547,9 +544,9 @@ cudaError_t wf_launch_tc_conv(const ConvP& p, int num_sms, cudaStream_t st)
 {
     const long long NC = (long long)p.Pout * p.N;
     const long long mt = (p.Cout + BM - 1) / BM;
-    // column-tile width: the multiple of 16 in [64, 256] that minimises (rounds of tiles per SM) x (cost of one tile)
+    // column-tile width: the multiple of 32 in [64, 256] that minimises (rounds of tiles per SM) x (cost of one tile)
     int best_bn = 256; long long best_cost = -1;
-    for (int bn = 256; bn >= 64; bn -= 16) {
+    for (int bn = 256; bn >= 64; bn -= 32) {       // whole 32-column blocks of the MN-major activation image
         const long long tiles = mt * ((NC + bn - 1) / bn);
         const long long cost = ((tiles + num_sms - 1) / num_sms) * (bn + 64);
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_bn = bn; }

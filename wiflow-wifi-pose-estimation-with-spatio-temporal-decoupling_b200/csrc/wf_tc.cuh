@@ -73,6 +73,13 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
     return d;                                    // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
 }
+// The same with a layout type: 0 none, 1 SWIZZLE_128B_BASE32B (the ONLY layout of MN-major 32-bit operands: rows of 128 bytes =
+// 32 elements of the contiguous M/N dimension, 32-byte chunks XORed with the row (= K) index mod 4, LBO = byte stride between
+// 32-element blocks, SBO = byte stride between groups of 4 K rows), 2 SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc_l(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout)
+{
+    return umma_desc(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)(layout & 7u) << 61);
+}
 // Instruction descriptor for kind::tf32, fp32 accumulate.  a_mn / b_mn: 1 = MN-major operand, 0 = K-major.
 __host__ __device__ inline uint32_t umma_idesc_tf32(int M, int N, int a_mn, int b_mn)
 {

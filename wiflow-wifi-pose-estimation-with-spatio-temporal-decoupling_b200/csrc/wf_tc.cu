@@ -71,15 +71,17 @@ __device__ __forceinline__ float4 sel4(bool c, float4 a, float4 b)
 // to columns [bnp, bnp + bn).  The tensor core truncates when it adds into the fp32 accumulator, an error that grows with the
 // number of accumulations; keeping the 2^-11-sized corrections out of the main accumulator cuts that count by three and
 // makes their own truncation irrelevant.  The epilogue adds the two in fp32.
-struct TcGeom { int bn, bnp, nst, tmem_cols; };
+struct TcGeom { int bn, bnp, nst, tmem_cols, mp, mtiles; };      // mp: 128-row M tiles per CTA (they share the staged activation tile)
 
 template <int PRO, bool MASK>
 __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const TcGeom g)
 {
     wf_pdl_enter();
     const int BN = g.bn, STAGES = g.nst;
-    const int B_HALF = KC * BN * 4;                       // one of hi/lo of the BN x KC K-major activation tile
-    const int STAGE_BYTES = 2 * A_HALF + 2 * B_HALF;
+    const int B_HALF = KC * BN * 4;                       // one of hi/lo of the BN x KC activation tile
+    const int MP = g.mp;
+    const int A_BYTES = MP * 2 * A_HALF;                  // weight images (hi, lo) of this CTA's M tiles
+    const int STAGE_BYTES = A_BYTES + 2 * B_HALF;
     const int NQ = BN / 4;                                // column quads per tile
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -92,7 +94,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int KT = p.tc_kt;
-    const int m0 = blockIdx.y * BM;
+    const int mt0 = blockIdx.y * MP;                      // first M tile of this CTA
+    const int ntile = min(MP, g.mtiles - mt0);
+    const int m0 = mt0 * BM;
     const long long NC = (long long)p.Pout * p.N;
     const long long col0 = (long long)blockIdx.x * BN;
 
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
             if (MASK) pm += KC * m_sc;
             mbar_wait(empty(s), ph ^ 1u);
             if (active) {
-                uint8_t* bh = smem + s * STAGE_BYTES + 2 * A_HALF;
+                uint8_t* bh = smem + s * STAGE_BYTES + A_BYTES;
                 uint8_t* bl = bh + B_HALF;
                 split_store(bh, bl, soff[0], v[0]);
                 split_store(bh, bl, soff[1], v[1]);
@@ -192,7 +196,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
         mbar_wait(accum_bar, 0);
         tc_fence_after();
         const int quarter = warp & 3, cgrp = warp >> 2;
-        const int m = m0 + quarter * 32 + lane;
+        for (int tj = 0; tj < ntile; ++tj) {
+        const int m = m0 + tj * BM + quarter * 32 + lane;
         const bool mv = m < p.Cout;
         const int co = m;
         float bias = 0.f, es = 0.f, et = 0.f, em = 0.f;
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
             if (p.epi_mode == EPI_DSILU || p.epi_mode == EPI_DAFF) em = p.e_mean[co];
         }
         float s0 = 0.f, s1 = 0.f;
-        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tj * 2 * g.bnp);
         for (int cb0 = 0; cb0 < BN; cb0 += 32) {
             if (((cb0 >> 5) % (NPW / 4)) != cgrp) continue;
             float acc[32], cor[32];
@@ -227,27 +232,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
             atomicAdd(p.stat0 + co, (double)s0);
             atomicAdd(p.stat1 + co, (double)s1);
         }
+        }
     } else if (warp == NPW) {
         // ------------------------------ MMA issue (one thread) ------------------------------
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(BM, BN, 0, 1);             // A (weights) K-major, B (activations) MN-major
-            const uint32_t tmem_cor = tmem_base + (uint32_t)g.bnp;
             int s = 0; uint32_t ph = 0;
             for (int kc = 0; kc < KT; ++kc) {
                 mbar_wait(full_a(s), ph);
                 mbar_wait(full_b(s), ph);
                 tc_fence_after();
-                const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_HALF;
-                const uint32_t b_hi = a_hi + 2 * A_HALF, b_lo = b_hi + B_HALF;
+                const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES);
+                const uint32_t b_hi = a0 + A_BYTES, b_lo = b_hi + B_HALF;
 #pragma unroll
                 for (int kk = 0; kk < KC / 8; ++kk) {
-                    const uint64_t dah = umma_desc(a_hi + kk * 2 * A_LBO, A_LBO, A_SBO), dal = umma_desc(a_lo + kk * 2 * A_LBO, A_LBO, A_SBO);
                     // 8 channels = 8 rows of 128 bytes per K step; 32-column blocks KC*128 bytes apart; groups of 4 rows 512 bytes apart
                     const uint64_t dbh = umma_desc_l(b_hi + kk * 1024, KC * 128, 512, 1), dbl = umma_desc_l(b_lo + kk * 1024, KC * 128, 512, 1);
                     const uint32_t accf = (kc | kk) != 0 ? 1u : 0u;
-                    umma_tf32(tmem_cor, dal, dbh, idesc, accf);
-                    umma_tf32(tmem_cor, dah, dbl, idesc, 1u);
-                    umma_tf32(tmem_base, dah, dbh, idesc, accf);
+                    for (int tj = 0; tj < ntile; ++tj) {          // the M tiles of this CTA share the activation descriptors
+                        const uint32_t a_hi = a0 + tj * 2 * A_HALF, a_lo = a_hi + A_HALF;
+                        const uint64_t dah = umma_desc(a_hi + kk * 2 * A_LBO, A_LBO, A_SBO), dal = umma_desc(a_lo + kk * 2 * A_LBO, A_LBO, A_SBO);
+                        const uint32_t t_main = tmem_base + (uint32_t)(tj * 2 * g.bnp), t_cor = t_main + (uint32_t)g.bnp;
+                        umma_tf32(t_cor, dal, dbh, idesc, accf);
+                        umma_tf32(t_cor, dah, dbl, idesc, 1u);
+                        umma_tf32(t_main, dah, dbh, idesc, accf);
+                    }
                 }
                 umma_commit(empty(s));
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -257,12 +266,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
     } else {
         // ------------------------------ weight tiles: one 32 KB bulk copy per stage ------------------------------
         if (lane == 0) {
-            const float* wsrc = p.wtc + (size_t)blockIdx.y * KT * (2 * A_HALF / 4);
             int s = 0; uint32_t ph = 0;
             for (int kc = 0; kc < KT; ++kc) {
                 mbar_wait(empty(s), ph ^ 1u);
-                mbar_arrive_expect_tx(full_a(s), 2 * A_HALF);
-                bulk_g2s(smem_u32(smem + s * STAGE_BYTES), wsrc + (size_t)kc * (2 * A_HALF / 4), 2 * A_HALF, full_a(s));
+                mbar_arrive_expect_tx(full_a(s), ntile * 2 * A_HALF);
+                for (int tj = 0; tj < ntile; ++tj) {
+                    const float* wsrc = p.wtc + ((size_t)(mt0 + tj) * KT + kc) * (2 * A_HALF / 4);
+                    bulk_g2s(smem_u32(smem + s * STAGE_BYTES + tj * 2 * A_HALF), wsrc, 2 * A_HALF, full_a(s));
+                }
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
         }
@@ -544,25 +555,33 @@ cudaError_t wf_launch_tc_conv(const ConvP& p, int num_sms, cudaStream_t st)
 {
     const long long NC = (long long)p.Pout * p.N;
     const long long mt = (p.Cout + BM - 1) / BM;
-    // column-tile width: the multiple of 32 in [64, 256] that minimises (rounds of tiles per SM) x (cost of one tile)
-    int best_bn = 256; long long best_cost = -1;
-    for (int bn = 256; bn >= 64; bn -= 32) {       // whole 32-column blocks of the MN-major activation image
-        const long long tiles = mt * ((NC + bn - 1) / bn);
+    // M tiles per CTA.  WF_TC_MP=2 lets two 128-row tiles share one staged activation tile (2 x 2 accumulators x bn <= 512 TMEM
+    // columns then limit the column tile to 128 and the ring to two stages).  Measured at B = 1024: forward 1.54 ms vs 1.31 ms,
+    // backward-data 1.67 vs 1.47 ms with one tile per CTA -- halving the re-staged activation work does not pay for the narrower
+    // tiles and the shallower ring, i.e. the one-shot CTA (fill, drain, serial epilogue), not the producers, is what bounds the kernel.
+    static const int mp_env = [] { const char* e = std::getenv("WF_TC_MP"); const int v = e ? std::atoi(e) : 0; return v; }();
+    const int mp = (mp_env == 2 && mt >= 2) ? 2 : 1;
+    const int bn_max = mp == 2 ? 128 : 256;
+    // column-tile width: the multiple of 32 in [64, bn_max] that minimises (rounds of tiles per SM) x (cost of one tile)
+    int best_bn = bn_max; long long best_cost = -1;
+    for (int bn = bn_max; bn >= 64; bn -= 32) {       // whole 32-column blocks of the MN-major activation image
+        const long long tiles = ((mt + mp - 1) / mp) * ((NC + bn - 1) / bn);
         const long long cost = ((tiles + num_sms - 1) / num_sms) * (bn + 64);
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_bn = bn; }
     }
     TcGeom g{};
+    g.mp = mp; g.mtiles = (int)mt;
     g.bn = best_bn;
     g.bnp = (best_bn + 31) / 32 * 32;
     g.tmem_cols = 32;
-    while (g.tmem_cols < 2 * g.bnp) g.tmem_cols *= 2;
-    const int stage = 2 * A_HALF + 2 * KC * g.bn * 4;
-    const int budget = g.tmem_cols <= 256 ? 100 * 1024 : SMEM_MAX - 256;       // narrow tiles: leave room for a second CTA per SM
+    while (g.tmem_cols < mp * 2 * g.bnp) g.tmem_cols *= 2;
+    const int stage = mp * 2 * A_HALF + 2 * KC * g.bn * 4;
+    const int budget = (g.tmem_cols <= 256 && mp == 1) ? 100 * 1024 : SMEM_MAX - 256;       // narrow tiles: leave room for a second CTA per SM
     g.nst = budget / stage;
     if (g.nst > 4) g.nst = 4;
     if (g.nst < 2) g.nst = 2;
     const int smem = g.nst * stage + (3 * g.nst + 1) * 8 + 16;
-    dim3 grid((unsigned)((NC + g.bn - 1) / g.bn), (unsigned)mt);
+    dim3 grid((unsigned)((NC + g.bn - 1) / g.bn), (unsigned)((mt + mp - 1) / mp));
     const bool mask = p.pro_mode == PRO_BNSILU && p.mask != nullptr;
     switch (p.pro_mode) {
         case PRO_NONE: return launch_conv_t<PRO_NONE, false>(p, g, grid, smem, st);

@@ -161,7 +161,14 @@ def test_state_dict_round_trip_with_reference_keys():
     x = torch.randn(4, 540, 20, generator=torch.Generator().manual_seed(1)).cuda()
     a.eval(); b.eval()
     with torch.no_grad():
-        assert torch.equal(a(x), b(x))
+        ya, yb = a(x), b(x)
+    # the TMA + tcgen05 conv-stack kernels (B >= 205, or forced by WF_SLABTC_MIN_N=0) feed one TMEM accumulator from three issuing
+    # warps, so the order of the fp32 additions -- not the set of products -- depends on timing: equal to ~1e-7, not bit for bit
+    import os
+    if os.environ.get('WF_SLABTC_MIN_N') == '0':
+        assert rel_err(ya.cpu(), yb.cpu()) < 2e-6
+    else:
+        assert torch.equal(ya, yb)
 
 
 def test_empty_batch_follows_the_reference():

@@ -569,6 +569,8 @@ cudaError_t wf_launch_tc_conv(const ConvP& p, int num_sms, cudaStream_t st)
         const long long cost = ((tiles + num_sms - 1) / num_sms) * (bn + 64);
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_bn = bn; }
     }
+    static const int bn_env = [] { const char* e = std::getenv("WF_TC_BN"); return e ? std::atoi(e) : 0; }();       // experiments only
+    if (bn_env >= 64 && bn_env <= bn_max && bn_env % 32 == 0) best_bn = bn_env;
     TcGeom g{};
     g.mp = mp; g.mtiles = (int)mt;
     g.bn = best_bn;

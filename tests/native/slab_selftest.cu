@@ -146,6 +146,21 @@ static int run_case(const Case& c, int verbose)
             printf("   timeline (us from entry):");
             for (int i = 0; i < 14; ++i) printf(" %s %.1f |", nm[i], ts[i] ? (double)(ts[i] - ts[0]) / 1000.0 : -1.0);
             printf("\n");
+            // all CTAs, two back-to-back launches: spread of entry / end times and the gap between the launches
+            static unsigned long long ct[6][160];
+            wf_slabtc_debug_cta(&ct[0][0]);
+            CK(wf_launch_slabtc_conv(p, 0)); CK(wf_launch_slabtc_conv(p, 0)); CK(cudaDeviceSynchronize());
+            wf_slabtc_debug_cta(&ct[0][0]);
+            unsigned long long t0 = ~0ULL;
+            for (int b = 0; b < 160; ++b) if (ct[0][b] && ct[0][b] < t0) t0 = ct[0][b];
+            static const char* cn[] = {"L1 launch", "L1 entry", "L1 end", "L2 launch", "L2 entry", "L2 end"};
+            printf("   all CTAs (us from the first CTA's start):");
+            for (int k = 0; k < 6; ++k) {
+                unsigned long long lo = ~0ULL, hi = 0; int n = 0;
+                for (int b = 0; b < 160; ++b) if (ct[k][b]) { ++n; lo = ct[k][b] < lo ? ct[k][b] : lo; hi = ct[k][b] > hi ? ct[k][b] : hi; }
+                if (n) printf(" %s %.1f..%.1f (%d) |", cn[k], (double)(lo - t0) / 1000.0, (double)(hi - t0) / 1000.0, n);
+            }
+            printf("\n");
         }
         unsetenv("WF_SLABTC_DBG");
         return 0;

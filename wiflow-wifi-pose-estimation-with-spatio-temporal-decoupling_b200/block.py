@@ -43,6 +43,8 @@ def _flat_view(ts):
     return base.as_strided((total,), (1,), base.storage_offset())
 
 
+_ONES = {}
+
 class _BlockFunction(torch.autograd.Function):
     """autograd bridge: forward saves the library workspace, backward returns per-parameter views of one flat gradient."""
 
@@ -107,11 +109,19 @@ class WFBlock(nn.Module):
         if all(p == 0 for p, _, _ in sites):
             return []
         masks = []
+        cache = _ONES       # the all-ones inputs of the draws, filled once per shape (not per step); module-level: never pickled / deep-copied
         for p, kind, C in sites:
+            shape = (B, C, 20) if kind == 'elem' else (B, C, 1, 1)
+            key = (shape, str(device))
+            ones = cache.get(key)
+            if ones is None:
+                if len(cache) > 64:
+                    cache.clear()
+                ones = cache[key] = torch.ones(*shape, device=device)
             if kind == 'elem':
-                masks.append(F.dropout(torch.ones(B, C, 20, device=device), p, True))
+                masks.append(F.dropout(ones, p, True))
             else:
-                masks.append(F.dropout2d(torch.ones(B, C, 1, 1, device=device), p, True).view(B, C))
+                masks.append(F.dropout2d(ones, p, True).view(B, C))
         return masks
 
     def forward(self, x):

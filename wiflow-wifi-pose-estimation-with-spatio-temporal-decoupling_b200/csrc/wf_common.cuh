@@ -23,6 +23,34 @@ enum { EPI_STORE = 0,      // out = acc + bias
        EPI_DSILU = 2,      // dy = acc * mask * silu'(s*(raw-mean)+t); stats: sum dy, sum dy*(raw-mean)
        EPI_DAFF = 3 };     // dy = acc;                          stats: sum dy, sum dy*(raw-mean)
 
+struct BnFwdFin {
+    int C; double count;
+    const double *s0, *s1;
+    const float *gamma, *beta;
+    float *scale, *shift, *mean, *rstd;
+    float *run_mean, *run_var;          // nullptr: do not touch running statistics
+    long long* nbt;
+};
+struct BnBwdFin {
+    int C; double count;
+    const double *s0, *s1;              // sum dy, sum dy*(raw - mean)
+    const float *gamma, *mean, *rstd;
+    float *dgamma, *dbeta;              // may be nullptr
+    float *alpha, *beta_c, *delta;
+    int frozen;                         // eval-mode BatchNorm (running statistics): a fixed per-channel affine, dx = gamma*rstd*dy
+    float* conv_dbias;                  // frozen only: gradient of the bias of the conv feeding this BatchNorm (or nullptr)
+};
+// BatchNorm finalize folded into the kernel whose epilogue completes the per-channel sums (training mode): every CTA of that kernel
+// calls wf_bn_tail() once after its last statistics atomic, and the CTA that draws the last ticket does the work of the
+// bn_finalize_{fwd,bwd} kernels (coefficients for the consumers, running statistics / gamma-beta gradients) -- one launch and one
+// dependent-launch gap less per BatchNorm and direction.
+struct BnTail {
+    unsigned* counter;                  // nullptr: no tail.  Zero before the launch; reset by the last CTA
+    int nf, nb;                         // forward finalizes (0/1), backward finalizes (0..2)
+    BnFwdFin f;
+    BnBwdFin b[2];
+};
+
 struct ConvP {
     // B operand ("input" of the conv)
     const float* in;
@@ -50,6 +78,7 @@ struct ConvP {
     const float *e_scale, *e_shift, *e_mean;
     const float* emask; long long em_sb, em_sc; int em_st;
     double *stat0, *stat1;            // per output channel
+    BnTail tail;                      // finalize of the BatchNorm the statistics belong to (or counter == nullptr)
 };
 
 struct WgradP {
@@ -87,6 +116,66 @@ __device__ __forceinline__ void wf_pdl_enter()
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// one channel of the forward / backward BatchNorm finalize (models/tcn.py:28 ... nn.BatchNorm1d training semantics: biased variance for
+// the normalisation, unbiased for the running estimate, momentum 0.1).  The sums come from other CTAs' atomics: read them at L2.
+__device__ __forceinline__ void wf_bn_fwd_fin_channel(const BnFwdFin& d, int c)
+{
+    const double cnt = d.count;
+    const double mean = __ldcg(d.s0 + c) / cnt;
+    double var = __ldcg(d.s1 + c) / cnt - mean * mean;
+    if (var < 0) var = 0;
+    const double rstd = 1.0 / sqrt(var + 1e-5);
+    const float gam = d.gamma[c], bet = d.beta[c];
+    d.scale[c] = (float)(gam * rstd);
+    d.shift[c] = bet;
+    d.mean[c] = (float)mean;
+    d.rstd[c] = (float)rstd;
+    if (d.run_mean) {
+        const double unb = cnt > 1 ? var * cnt / (cnt - 1) : var;
+        d.run_mean[c] = (float)(0.9 * d.run_mean[c] + 0.1 * mean);
+        d.run_var[c] = (float)(0.9 * d.run_var[c] + 0.1 * unb);
+        if (c == 0 && d.nbt) *d.nbt += 1;
+    }
+}
+__device__ __forceinline__ void wf_bn_bwd_fin_channel(const BnBwdFin& d, int c)
+{
+    const double cnt = d.count;
+    const double rstd = d.rstd[c], gam = d.gamma[c];
+    const double s0 = __ldcg(d.s0 + c);
+    const double sx = rstd * __ldcg(d.s1 + c);        // sum dy * xhat   (s1 = sum dy * (raw - mean))
+    if (d.dgamma) { d.dgamma[c] = (float)sx; d.dbeta[c] = (float)s0; }
+    const double alpha = gam * rstd;
+    const double c1 = s0 / cnt, c2 = sx / cnt;
+    d.alpha[c] = (float)alpha;
+    if (d.frozen) {          // statistics are constants: no mean / variance terms; the conv bias in front has a real gradient
+        d.beta_c[c] = 0.f;
+        d.delta[c] = 0.f;
+        if (d.conv_dbias) d.conv_dbias[c] = (float)(alpha * s0);
+        return;
+    }
+    d.beta_c[c] = (float)(-alpha * c2 * rstd);
+    d.delta[c] = (float)(-alpha * c1);
+}
+// called by ALL threads of EVERY CTA of the kernel, after the CTA's last statistics atomic (block-wide barriers inside)
+__device__ __forceinline__ void wf_bn_tail(const BnTail& t)
+{
+    if (t.counter == nullptr) return;
+    __syncthreads();                                   // the CTA's statistics atomics are issued ...
+    int last = 0;
+    if (threadIdx.x == 0) {
+        __threadfence();                               // ... and ordered before the ticket (cumulative over the barrier, as in a grid sync)
+        const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+        last = atomicAdd(t.counter, 1u) == total - 1 ? 1 : 0;
+    }
+    last = __syncthreads_or(last);
+    if (!last) return;
+    __threadfence();
+    if (t.nf) for (int c = threadIdx.x; c < t.f.C; c += blockDim.x) wf_bn_fwd_fin_channel(t.f, c);
+    for (int i = 0; i < t.nb; ++i)
+        for (int c = threadIdx.x; c < t.b[i].C; c += blockDim.x) wf_bn_bwd_fin_channel(t.b[i], c);
+    if (threadIdx.x == 0) *t.counter = 0u;
 }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }

@@ -256,6 +256,7 @@ conv_gemm_kernel(const ConvP p)
             }
         }
     }
+    wf_bn_tail(p.tail);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -20,23 +20,7 @@ __global__ void bn_finalize_fwd_kernel(BnFwdFin a, BnFwdFin b, int n)
     if ((int)blockIdx.y >= n) return;
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= d.C) return;
-    double cnt = d.count;
-    double mean = d.s0[c] / cnt;
-    double var = d.s1[c] / cnt - mean * mean;
-    if (var < 0) var = 0;
-    double rstd = 1.0 / sqrt(var + 1e-5);
-    float gam = d.gamma[c], bet = d.beta[c];
-    float sc = (float)(gam * rstd);
-    d.scale[c] = sc;
-    d.shift[c] = bet;
-    d.mean[c] = (float)mean;
-    d.rstd[c] = (float)rstd;
-    if (d.run_mean) {
-        double unb = cnt > 1 ? var * cnt / (cnt - 1) : var;
-        d.run_mean[c] = (float)(0.9 * d.run_mean[c] + 0.1 * mean);
-        d.run_var[c] = (float)(0.9 * d.run_var[c] + 0.1 * unb);
-        if (c == 0 && d.nbt) *d.nbt += 1;
-    }
+    wf_bn_fwd_fin_channel(d, c);
 }
 
 __global__ void bn_finalize_bwd_kernel(BnBwdFin a, BnBwdFin b, int n)
@@ -46,23 +30,7 @@ __global__ void bn_finalize_bwd_kernel(BnBwdFin a, BnBwdFin b, int n)
     if ((int)blockIdx.y >= n) return;
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= d.C) return;
-    double cnt = d.count;
-    double mean = d.mean[c], rstd = d.rstd[c], gam = d.gamma[c];
-    double s0 = d.s0[c];
-    double sx = rstd * d.s1[c];                       // sum dy * xhat   (s1 = sum dy * (raw - mean))
-    if (d.dgamma) { d.dgamma[c] = (float)sx; d.dbeta[c] = (float)s0; }
-    double alpha = gam * rstd;
-    double c1 = s0 / cnt, c2 = sx / cnt;
-    double be = -alpha * c2 * rstd;
-    d.alpha[c] = (float)alpha;
-    if (d.frozen) {          // statistics are constants: no mean / variance terms; the conv bias in front has a real gradient
-        d.beta_c[c] = 0.f;
-        d.delta[c] = 0.f;
-        if (d.conv_dbias) d.conv_dbias[c] = (float)(alpha * s0);
-        return;
-    }
-    d.beta_c[c] = (float)be;
-    d.delta[c] = (float)(-alpha * c1);
+    wf_bn_bwd_fin_channel(d, c);
 }
 
 // eval mode: (scale, shift) of all BatchNorms from the running statistics, one launch
@@ -201,6 +169,7 @@ __global__ void __launch_bounds__(NT) join_bwd_kernel(JoinP p)
     }
     block_accum2<NT>(sa0, sa1, p.a_stat0 + c, p.a_stat1 + c);
     if (p.r_stat0) block_accum2<NT>(sr0, sr1, p.r_stat0 + c, p.r_stat1 + c);
+    wf_bn_tail(p.tail);
 }
 
 // generic per-channel sums (sum dy, sum dy*raw) over [C][plane]

@@ -8,23 +8,6 @@
 #define WF_MAX_CONV 48
 enum { WF_LOSS_SMOOTH_L1 = 0, WF_LOSS_MSE = 1, WF_LOSS_L1 = 2 };
 
-struct BnFwdFin {
-    int C; double count;
-    const double *s0, *s1;
-    const float *gamma, *beta;
-    float *scale, *shift, *mean, *rstd;
-    float *run_mean, *run_var;          // nullptr: do not touch running statistics
-    long long* nbt;
-};
-struct BnBwdFin {
-    int C; double count;
-    const double *s0, *s1;              // sum dy, sum dy*(raw - mean)
-    const float *gamma, *mean, *rstd;
-    float *dgamma, *dbeta;              // may be nullptr
-    float *alpha, *beta_c, *delta;
-    int frozen;                         // eval-mode BatchNorm (running statistics): a fixed per-channel affine, dx = gamma*rstd*dy
-    float* conv_dbias;                  // frozen only: gradient of the bias of the conv feeding this BatchNorm (or nullptr)
-};
 struct BnEvalEntry { int C, Cpad, gamma_off, run_off, coef_off; };
 struct BnEvalTable { int n; BnEvalEntry e[WF_MAX_BN]; };
 
@@ -38,6 +21,7 @@ struct JoinP {
     int r_mode; const float *r_scale, *r_shift, *r_mean;
     long long r_sc, r_sp, r_sb;
     double *a_stat0, *a_stat1, *r_stat0, *r_stat1;
+    BnTail tail;                        // join_bwd: finalize of the (one or two) BatchNorms whose backward sums it completes
 };
 
 struct MetricThr { int n; float v[WF_MAX_THR]; };
@@ -94,6 +78,7 @@ long long wf_slabtc_pack_floats(int cout, int cin, int ntaps, bool bwd);
 cudaError_t wf_launch_slabtc_pack(const SlabPackTable& tab, const float* params, float* packed, cudaStream_t st);
 bool wf_slabtc_conv_ok(const ConvP& p);
 cudaError_t wf_slabtc_debug_ts(unsigned long long* out);
+cudaError_t wf_slabtc_debug_cta(unsigned long long* out);      // [6][160] per-CTA stamps of two launches (WF_SLABTC_DBG bit 512)
 bool wf_slabtc_wgrad_ok(const WgradP& p);
 cudaError_t wf_launch_slabtc_wgrad(const WgradP& p, cudaStream_t st);
 cudaError_t wf_launch_slabtc_conv(const ConvP& p, cudaStream_t st);

@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(G_NT, 2) group_conv_kernel(const ConvP p)
             atomicAdd(p.stat1 + g * p.Cout + tid, red[1][tid]);
         }
     }
+    wf_bn_tail(p.tail);
 }
 
 template <int BM>

@@ -45,6 +45,7 @@ struct BnUnit {
     double count_per_b;       // elements per channel = count_per_b * B
     // workspace
     double *f0, *f1, *b0, *b1;
+    unsigned *fctr, *bctr;    // ticket counters of the folded finalizes (BnTail); live in the zeroed statistics regions
     float* coef;              // 8 * Cpad: scale, shift, mean, rstd, alpha, beta, delta, (spare)
     float* scale() const { return coef; }
     float* shift() const { return coef + Cpad; }
@@ -317,10 +318,10 @@ size_t layout(Net& n, int B, int flags, char* base)
     n.slpacked = bp.take<float>(sf);
     // BN statistics (fp64) and coefficients
     size_t s0 = (bp.off + 255) & ~(size_t)255;
-    for (auto& b : n.bn) { b.f0 = bp.take<double>(b.C); b.f1 = bp.take<double>(b.C); }
+    for (auto& b : n.bn) { b.f0 = bp.take<double>(b.C); b.f1 = bp.take<double>(b.C); b.fctr = reinterpret_cast<unsigned*>(bp.take<double>(1)); }
     n.fstats = base ? base + s0 : nullptr; n.fstats_bytes = bp.off - s0;
     size_t s1 = (bp.off + 255) & ~(size_t)255;
-    for (auto& b : n.bn) { b.b0 = bp.take<double>(b.C); b.b1 = bp.take<double>(b.C); }
+    for (auto& b : n.bn) { b.b0 = bp.take<double>(b.C); b.b1 = bp.take<double>(b.C); b.bctr = reinterpret_cast<unsigned*>(bp.take<double>(1)); }
     n.bstats = base ? base + s1 : nullptr; n.bstats_bytes = bp.off - s1;
     for (auto& b : n.bn) b.coef = bp.take<float>(8 * b.Cpad);
     // activations
@@ -390,6 +391,7 @@ struct Ctx {
     cudaError_t err = cudaSuccess;
     cudaStream_t side = nullptr;      // backward only: the weight-gradient kernels run here, concurrently with backward-data on `st`
     cudaEvent_t fork = nullptr;
+    std::vector<unsigned char> ftail, btail;      // per BatchNorm: its finalize rides on the kernel that completes the sums (BnTail)
     void ck(cudaError_t e) { if (err == cudaSuccess && e != cudaSuccess) err = e; }
     const float* mask_ptr(int i) const { return (masks && train) ? masks[i] : nullptr; }
 };
@@ -447,6 +449,9 @@ Pro pro_none() { return Pro{PRO_NONE, -1, no_mask()}; }
 Pro pro_act(int bn, Mask m = no_mask()) { return Pro{PRO_BNSILU, bn, m}; }
 Pro pro_aff(int bn) { return Pro{PRO_AFFINE, bn, no_mask()}; }
 
+void tail_fwd(Ctx& c, BnTail& t, int bi);
+void tail_bwd(Ctx& c, BnTail& t, int bn_a, int bn_b);
+
 void fwd_conv(Ctx& c, int ui, Act in, Pro pro)
 {
     const ConvUnit& u = c.n.conv[ui];
@@ -464,10 +469,69 @@ void fwd_conv(Ctx& c, int ui, Act in, Pro pro)
     p.bias = u.b_off >= 0 ? c.params + u.b_off : nullptr;
     p.epi_mode = c.train ? EPI_STATS : EPI_STORE;
     p.stat0 = bo.f0; p.stat1 = bo.f1;
+    tail_fwd(c, p.tail, u.bn);
     if (u.sl) p.wtc = c.n.slpacked + u.sl_fpack;
     Scope sc(c, std::string(u.tc ? "tc_fwd " : wf_slabtc_conv_ok(p) ? "slab_fwd " : wf_slide_conv_ok(p) ? (wf_slide_conv_is_thin(p) ? "slidethin_fwd " : "slide_fwd ") : wf_thin_conv_ok(p) ? "thin_fwd " : wf_group_conv_ok(p) ? "group_fwd " : "conv_fwd ") + u.name, conv_flops(u, c.N), conv_bytes(u, c.N, 0));
     if (u.tc) { p.wtc = c.n.tcpacked + u.tc_fpack; p.tc_kt = (u.cin_g + TC_KC - 1) / TC_KC; c.ck(wf_launch_tc_conv(p, c.sms, c.st)); }
     else c.ck(wf_launch_conv(p, c.st));
+}
+
+// WF_BN_TAIL=1 folds each BatchNorm finalize into the kernel that completes its sums (BnTail, wf_common.cuh).  Off by default:
+// measured on a B200 it is SLOWER than the separate one-block launches -- B = 1024: 16.70 vs 16.45 ms / step (175 vs 242 launches),
+// B = 64: 2.68 vs 2.58 ms.  With programmatic dependent launch the finalize kernel is already resident when its producer
+// drains, so a launch costs ~2 us, while the tail adds a ticket round trip to EVERY CTA of the producer and runs the fp64
+// finalize on the critical path of its last CTA.
+bool bn_tail_enabled() { static const bool v = [] { const char* e = std::getenv("WF_BN_TAIL"); return e && e[0] == '1'; }(); return v; }
+
+BnFwdFin make_fwd_fin(Ctx& c, int bi)
+{
+    const BnUnit& b = c.n.bn[bi];
+    BnFwdFin f{};
+    f.C = b.C; f.count = b.count_per_b * c.B;
+    f.s0 = b.f0; f.s1 = b.f1;
+    f.gamma = c.params + b.gamma_off; f.beta = c.params + b.gamma_off + b.C;
+    f.scale = b.scale(); f.shift = b.shift(); f.mean = b.mean(); f.rstd = b.rstd();
+    f.run_mean = c.running ? c.running + b.run_off : nullptr;
+    f.run_var = c.running ? c.running + b.run_off + b.C : nullptr;
+    f.nbt = c.nbt ? c.nbt + bi : nullptr;
+    return f;
+}
+
+BnBwdFin make_bwd_fin(Ctx& c, int bi)
+{
+    const BnUnit& b = c.n.bn[bi];
+    BnBwdFin f{};
+    f.C = b.C; f.count = b.count_per_b * c.B;
+    f.s0 = b.b0; f.s1 = b.b1;
+    f.gamma = c.params + b.gamma_off; f.mean = b.mean(); f.rstd = b.rstd();
+    f.dgamma = c.grads + b.gamma_off; f.dbeta = c.grads + b.gamma_off + b.C;
+    f.alpha = b.alpha(); f.beta_c = b.betac(); f.delta = b.delta();
+    f.frozen = c.train ? 0 : 1;
+    if (f.frozen)
+        for (const ConvUnit& u : c.n.conv)
+            if (u.bn == bi && u.b_off >= 0) f.conv_dbias = c.grads + u.b_off;
+    return f;
+}
+
+// the kernel about to be launched completes the forward sums of BatchNorm bi: let its last CTA finalize (fwd_fin then skips bi)
+void tail_fwd(Ctx& c, BnTail& t, int bi)
+{
+    if (!c.train || !bn_tail_enabled()) return;
+    t.counter = c.n.bn[bi].fctr; t.nf = 1; t.f = make_fwd_fin(c, bi);
+    if (c.ftail.size() < c.n.bn.size()) c.ftail.resize(c.n.bn.size(), 0);
+    c.ftail[bi] = 1;
+}
+// same for the backward sums of one or two BatchNorms (bwd_fin then skips them)
+void tail_bwd(Ctx& c, BnTail& t, int bn_a, int bn_b)
+{
+    if (!bn_tail_enabled()) return;
+    if (c.btail.size() < c.n.bn.size()) c.btail.resize(c.n.bn.size(), 0);
+    t.counter = c.n.bn[bn_a].bctr;
+    for (int bi : {bn_a, bn_b}) {
+        if (bi < 0) continue;
+        t.b[t.nb++] = make_bwd_fin(c, bi);
+        c.btail[bi] = 1;
+    }
 }
 
 void fwd_fin(Ctx& c, int bn_a, int bn_b = -1)
@@ -477,17 +541,10 @@ void fwd_fin(Ctx& c, int bn_a, int bn_b = -1)
     int k = 0;
     for (int bi : {bn_a, bn_b}) {
         if (bi < 0) continue;
-        const BnUnit& b = c.n.bn[bi];
-        BnFwdFin f{};
-        f.C = b.C; f.count = b.count_per_b * c.B;
-        f.s0 = b.f0; f.s1 = b.f1;
-        f.gamma = c.params + b.gamma_off; f.beta = c.params + b.gamma_off + b.C;
-        f.scale = b.scale(); f.shift = b.shift(); f.mean = b.mean(); f.rstd = b.rstd();
-        f.run_mean = c.running ? c.running + b.run_off : nullptr;
-        f.run_var = c.running ? c.running + b.run_off + b.C : nullptr;
-        f.nbt = c.nbt ? c.nbt + bi : nullptr;
-        d[k++] = f;
+        if ((size_t)bi < c.ftail.size() && c.ftail[bi]) { c.ftail[bi] = 0; continue; }
+        d[k++] = make_fwd_fin(c, bi);
     }
+    if (k == 0) return;
     Scope sc(c, "bn_fin_fwd");
     c.ck(wf_launch_bn_fwd_fin(d, k, c.st));
 }
@@ -498,19 +555,10 @@ void bwd_fin(Ctx& c, int bn_a, int bn_b = -1)
     int k = 0;
     for (int bi : {bn_a, bn_b}) {
         if (bi < 0) continue;
-        const BnUnit& b = c.n.bn[bi];
-        BnBwdFin f{};
-        f.C = b.C; f.count = b.count_per_b * c.B;
-        f.s0 = b.b0; f.s1 = b.b1;
-        f.gamma = c.params + b.gamma_off; f.mean = b.mean(); f.rstd = b.rstd();
-        f.dgamma = c.grads + b.gamma_off; f.dbeta = c.grads + b.gamma_off + b.C;
-        f.alpha = b.alpha(); f.beta_c = b.betac(); f.delta = b.delta();
-        f.frozen = c.train ? 0 : 1;
-        if (f.frozen)
-            for (const ConvUnit& u : c.n.conv)
-                if (u.bn == bi && u.b_off >= 0) f.conv_dbias = c.grads + u.b_off;
-        d[k++] = f;
+        if ((size_t)bi < c.btail.size() && c.btail[bi]) { c.btail[bi] = 0; continue; }
+        d[k++] = make_bwd_fin(c, bi);
     }
+    if (k == 0) return;
     Scope sc(c, "bn_fin_bwd");
     c.ck(wf_launch_bn_bwd_fin(d, k, c.st));
 }
@@ -518,7 +566,7 @@ void bwd_fin(Ctx& c, int bn_a, int bn_b = -1)
 // backward-data of conv unit ui: consumes (dy, raw) of the unit through its BatchNorm backward, produces the gradient
 // w.r.t. the unit's input.  epi: EPI_STORE (input is a materialised tensor), EPI_DSILU / EPI_DAFF (input is the
 // BatchNorm(+SiLU) of conv unit `src`'s raw output; also accumulates that BatchNorm's backward sums).
-void dgrad_conv(Ctx& c, int ui, float* out, int epi, int src_bn, const float* src_raw, Mask emask, bool accumulate)
+void dgrad_conv(Ctx& c, int ui, float* out, int epi, int src_bn, const float* src_raw, Mask emask, bool accumulate, bool fin_tail = false)
 {
     const ConvUnit& u = c.n.conv[ui];
     const BnUnit& bo = c.n.bn[u.bn];
@@ -537,6 +585,7 @@ void dgrad_conv(Ctx& c, int ui, float* out, int epi, int src_bn, const float* sr
         p.eraw = src_raw; p.e_scale = bs.scale(); p.e_shift = bs.shift(); p.e_mean = bs.mean();
         p.emask = emask.p; p.em_sb = emask.sb; p.em_sc = emask.sc; p.em_st = emask.st;
         p.stat0 = bs.b0; p.stat1 = bs.b1;
+        if (fin_tail) tail_bwd(c, p.tail, src_bn, -1);        // this launch alone completes src_bn's backward sums
     }
     if (u.sl) p.wtc = c.n.slpacked + u.sl_bpack;
     Scope sc(c, std::string(u.tc ? "tc_dgrad " : wf_slabtc_conv_ok(p) ? "slab_dgrad " : wf_slide_conv_ok(p) ? (wf_slide_conv_is_thin(p) ? "slidethin_dgrad " : "slide_dgrad ") : wf_thin_conv_ok(p) ? "thin_dgrad " : wf_group_conv_ok(p) ? "group_dgrad " : "conv_dgrad ") + u.name, conv_flops(u, c.N), conv_bytes(u, c.N, 1));
@@ -674,7 +723,7 @@ void decoder_bwd(Ctx& c, Act xin, Pro pro, const float* dpred, float* dxin_dy, i
     { Scope sc(c, "pool_bwd"); c.ck(wf_launch_pool_bwd(d2.raw, b2.scale(), b2.shift(), b2.mean(), dpred, d2.dy, c.B, b2.b0, b2.b1, c.st)); }
     bwd_fin(c, d2.bn);
     wgrad_conv(c, n.dec.d2, internal(d1.raw, 15, c.N), pro_act(d1.bn));
-    dgrad_conv(c, n.dec.d2, d1.dy, EPI_DSILU, d1.bn, d1.raw, no_mask(), false);
+    dgrad_conv(c, n.dec.d2, d1.dy, EPI_DSILU, d1.bn, d1.raw, no_mask(), false, true);
     bwd_fin(c, d1.bn);
     wgrad_conv(c, n.dec.d1, xin, pro);
     dgrad_conv(c, n.dec.d1, dxin_dy, EPI_DAFF, src_bn, src_raw, no_mask(), false);
@@ -711,14 +760,15 @@ void conv_block_bwd(Ctx& c, CvBlk& b, Act xin, float* dxin)
     j.a_mean = ba.mean(); j.r_mean = br.mean();
     j.dout = b.dY; j.dz = c3.dy; j.da = nullptr;           // c3.dy doubles as dy of the shortcut BatchNorm
     j.a_stat0 = ba.b0; j.a_stat1 = ba.b1; j.r_stat0 = br.b0; j.r_stat1 = br.b1;
+    tail_bwd(c, j.tail, c3.bn, ds.bn);
     { Scope sc(c, "join_bwd " + b.name); c.ck(wf_launch_join_bwd(j, c.sms, c.st)); }
     bwd_fin(c, c3.bn, ds.bn);
     Mask m0 = plane_mask(c.mask_ptr(b.mask0), b.cout), m1 = plane_mask(c.mask_ptr(b.mask0 + 1), b.cout);
     wgrad_conv(c, b.c3, internal(c2.raw, b.wout, c.N), pro_act(c2.bn, m1));
-    dgrad_conv(c, b.c3, c2.dy, EPI_DSILU, c2.bn, c2.raw, m1, false);
+    dgrad_conv(c, b.c3, c2.dy, EPI_DSILU, c2.bn, c2.raw, m1, false, true);
     bwd_fin(c, c2.bn);
     wgrad_conv(c, b.c2, internal(c1.raw, b.wout, c.N), pro_act(c1.bn, m0));
-    dgrad_conv(c, b.c2, c1.dy, EPI_DSILU, c1.bn, c1.raw, m0, false);
+    dgrad_conv(c, b.c2, c1.dy, EPI_DSILU, c1.bn, c1.raw, m0, false, true);
     bwd_fin(c, c1.bn);
     wgrad_conv(c, b.c1, xin, pro_none());
     // the shortcut conv shares dz with c3: temporarily view ds through c3's dy
@@ -753,16 +803,17 @@ void tcn_block_bwd(Ctx& c, TcnBlk& b, Act xin, float* dxin)
         j.r = xin.p; j.r_mode = PRO_NONE; j.r_sc = xin.sc; j.r_sp = 0; j.r_sb = xin.sb;
         j.dz = dxin ? dxin : b.dz;          // identity shortcut: dz IS the gradient reaching the block input
     }
+    tail_bwd(c, j.tail, pw2.bn, b.ds >= 0 ? n.conv[b.ds].bn : -1);
     { Scope sc(c, "join_bwd " + b.name); c.ck(wf_launch_join_bwd(j, c.sms, c.st)); }
     bwd_fin(c, pw2.bn, b.ds >= 0 ? n.conv[b.ds].bn : -1);
     wgrad_conv(c, b.pw2, internal(g2.raw, 1, c.N), pro_act(g2.bn));
-    dgrad_conv(c, b.pw2, g2.dy, EPI_DSILU, g2.bn, g2.raw, no_mask(), false);
+    dgrad_conv(c, b.pw2, g2.dy, EPI_DSILU, g2.bn, g2.raw, no_mask(), false, true);
     bwd_fin(c, g2.bn);
     wgrad_conv(c, b.g2, internal(pw1.raw, 1, c.N), pro_act(pw1.bn, m0));
-    dgrad_conv(c, b.g2, pw1.dy, EPI_DSILU, pw1.bn, pw1.raw, m0, false);
+    dgrad_conv(c, b.g2, pw1.dy, EPI_DSILU, pw1.bn, pw1.raw, m0, false, true);
     bwd_fin(c, pw1.bn);
     wgrad_conv(c, b.pw1, internal(g1.raw, 1, c.N), pro_act(g1.bn));
-    dgrad_conv(c, b.pw1, g1.dy, EPI_DSILU, g1.bn, g1.raw, no_mask(), false);
+    dgrad_conv(c, b.pw1, g1.dy, EPI_DSILU, g1.bn, g1.raw, no_mask(), false, true);
     bwd_fin(c, g1.bn);
     wgrad_conv(c, b.g1, xin, pro_none());
     if (b.ds >= 0) {

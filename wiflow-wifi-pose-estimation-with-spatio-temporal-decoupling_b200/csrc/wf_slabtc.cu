@@ -65,12 +65,16 @@ struct SlabGeom {
 struct SlabGeom;
 // timeline probe of CTA 0 (WF_SLABTC_DBG bit 512): globaltimer stamps of the pipeline's milestones, read by the self-test
 __device__ unsigned long long g_ts[32];
+// per-CTA stamps of two consecutive launches: [0/3] before the programmatic-dependency wait, [1/4] kernel body entry, [2/5] final sync
+__device__ unsigned long long g_cta[6][160];
 __device__ __forceinline__ void stamp(const SlabGeom& g, int slot)
 {
-    if ((g.dbg & 512) && blockIdx.x == 0) {
+    if (g.dbg & 512) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        if (g_ts[slot] == 0) g_ts[slot] = t;
+        if (blockIdx.x == 0 && slot < 14 && g_ts[slot] == 0) g_ts[slot] = t;
+        const int k = slot == 14 ? 0 : slot == 0 ? 1 : slot == 13 ? 2 : -1;
+        if (k >= 0 && blockIdx.x < 160) { if (g_cta[k][blockIdx.x] == 0) g_cta[k][blockIdx.x] = t; else g_cta[k + 3][blockIdx.x] = t; }
     }
 }
 
@@ -323,6 +327,7 @@ template <int PRO, bool MASK, int CH>
 __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                           const ConvP p, const SlabGeom g)
 {
+    if (threadIdx.x == 0) stamp(g, 14);
     wf_pdl_enter();
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -679,6 +684,7 @@ __global__ void __launch_bounds__(NTHR, 1) slab_tc_kernel(const __grid_constant_
     __syncthreads();
     if (tid == 0) stamp(g, 13);
     if (warp == NWW) tmem_dealloc(tmem_base, g.tmem_cols);
+    wf_bn_tail(p.tail);
 }
 
 // =========================================================================================================
@@ -1121,6 +1127,15 @@ const bool g_swap_lbo = [] { const char* e = std::getenv("WF_SLABTC_SWAP_LBO"); 
 }  // namespace
 
 // timeline probe (WF_SLABTC_DBG bit 512): copies and clears the 32 globaltimer stamps of CTA 0
+cudaError_t wf_slabtc_debug_cta(unsigned long long* out)
+{
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_cta, sizeof(g_cta));
+    if (e != cudaSuccess) return e;
+    void* q = nullptr;
+    if ((e = cudaGetSymbolAddress(&q, g_cta)) != cudaSuccess) return e;
+    return cudaMemset(q, 0, sizeof(g_cta));
+}
+
 cudaError_t wf_slabtc_debug_ts(unsigned long long* out)
 {
     cudaError_t e = cudaMemcpyFromSymbol(out, g_ts, sizeof(g_ts));

@@ -359,6 +359,7 @@ __global__ void __launch_bounds__(32 * MW * NW, MINB) slide_conv_kernel(const Co
             atomicAdd(p.stat1 + tid, red[1][tid]);
         }
     }
+    wf_bn_tail(p.tail);
 }
 
 // =========================================================================================================
@@ -615,6 +616,7 @@ __global__ void __launch_bounds__(256, MINB) slide_thin_kernel(const ConvP p, co
             atomicAdd(p.stat1 + tid, red[1][tid]);
         }
     }
+    wf_bn_tail(p.tail);
 }
 
 // =========================================================================================================

@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
     tc_fence_before();
     __syncthreads();
     if (warp == NPW + 1) tmem_dealloc(tmem_base, g.tmem_cols);
+    wf_bn_tail(p.tail);
 }
 
 // =========================================================================================================

@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(256, COUTP == 8 ? 4 : 3) thin_conv_kernel(cons
             if (co < p.Cout) atomicAdd((which ? p.stat1 : p.stat0) + co, red[which][co]);
         }
     }
+    wf_bn_tail(p.tail);
 }
 
 // ---------------------------------------------------------------------------------------------------------

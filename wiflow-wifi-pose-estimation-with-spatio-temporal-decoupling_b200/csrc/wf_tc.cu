@@ -71,7 +71,7 @@ __device__ __forceinline__ float4 sel4(bool c, float4 a, float4 b)
 // to columns [bnp, bnp + bn).  The tensor core truncates when it adds into the fp32 accumulator, an error that grows with the
 // number of accumulations; keeping the 2^-11-sized corrections out of the main accumulator cuts that count by three and
 // makes their own truncation irrelevant.  The epilogue adds the two in fp32.
-struct TcGeom { int bn, bnp, nst, tmem_cols, mp, mtiles; };      // mp: 128-row M tiles per CTA (they share the staged activation tile)
+struct TcGeom { int bn, bnp, nst, nsa, tmem_cols, mp, mtiles, dbg; };      // nst / nsa: stages of the activation / weight ring      // mp: 128-row M tiles per CTA (they share the staged activation tile)
 
 template <int PRO, bool MASK>
 __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const TcGeom g)
@@ -81,16 +81,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
     const int B_HALF = KC * BN * 4;                       // one of hi/lo of the BN x KC activation tile
     const int MP = g.mp;
     const int A_BYTES = MP * 2 * A_HALF;                  // weight images (hi, lo) of this CTA's M tiles
-    const int STAGE_BYTES = A_BYTES + 2 * B_HALF;
+    const int B_STAGE = 2 * B_HALF;
+    const int NSA = g.nsa;
     const int NQ = BN / 4;                                // column quads per tile
+    // Two rings: the activation tiles (64 KB a stage at bn = 256, so two stages) and the weight images (32 KB a stage, three or
+    // four).  With ONE ring of two stages the bulk copy of a stage's weights could only be requested when the MMAs two K steps back
+    // had retired and its ~1 us latency sat in every K step (measured: 1.3 us per step with the producers switched off, against
+    // 0.8 us of MMA time); the deeper weight ring asks for the image two or three steps ahead.
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+    uint8_t* smem_a = smem + STAGES * B_STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + NSA * A_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NSA + 1);
     const uint32_t bar0 = smem_u32(bars);
-    auto full_a = [&](int s) { return bar0 + 8u * s; };
-    auto full_b = [&](int s) { return bar0 + 8u * (STAGES + s); };
-    auto empty = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
-    const uint32_t accum_bar = bar0 + 8u * (3 * STAGES);
+    auto full_b = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    auto full_a = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+    auto empty_a = [&](int s) { return bar0 + 8u * (2 * STAGES + NSA + s); };
+    const uint32_t accum_bar = bar0 + 8u * (2 * STAGES + 2 * NSA);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int KT = p.tc_kt;
@@ -101,7 +108,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
     const long long col0 = (long long)blockIdx.x * BN;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_a(s), 1); mbar_init(full_b(s), NPW); mbar_init(empty(s), 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_b(s), NPW); mbar_init(empty(s), 1); }
+        for (int s = 0; s < NSA; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
         mbar_init(accum_bar, 1);
         fence_mbar_init();
     }
@@ -148,7 +156,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
             float4 v[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] = f4zero();
-            if (cval && c0 < Cin) {
+            if (cval && c0 < Cin && !(g.dbg & 1)) {
                 float4 v2[4];
                 float4 A4 = f4zero(), B4 = f4zero(), C4 = f4zero(), D4 = f4zero();
 #pragma unroll
@@ -178,8 +186,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
             if (PRO == PRO_BNBWD) pin2 += KC * in_sc;
             if (MASK) pm += KC * m_sc;
             mbar_wait(empty(s), ph ^ 1u);
-            if (active) {
-                uint8_t* bh = smem + s * STAGE_BYTES + A_BYTES;
+            if (active && !(g.dbg & 8)) {
+                uint8_t* bh = smem + s * B_STAGE;
                 uint8_t* bl = bh + B_HALF;
                 split_store(bh, bl, soff[0], v[0]);
                 split_store(bh, bl, soff[1], v[1]);
@@ -208,25 +216,105 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
         }
         float s0 = 0.f, s1 = 0.f;
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tj * 2 * g.bnp);
+        // Thread = output channel is the TMEM access pattern, but as a GLOBAL access pattern it is 32 scattered 16-byte pieces per
+        // instruction (measured: 7 of the 37 us of a 128 x 256 tile).  So every 32 x 32 block goes through a per-warp staging tile
+        // in the (by now idle) activation ring: raw tensor of the BatchNorm-backward epilogues in, results out, both as whole
+        // 128-byte rows (8 lanes x float4 per row, 4 rows per instruction).
+        const bool coal = p.out_sb == WF_T && (p.N & 3) == 0 && !(p.accumulate && p.epi_mode != EPI_STORE);
+        const bool need_raw = p.epi_mode == EPI_DSILU || p.epi_mode == EPI_DAFF;
+        float* stg = reinterpret_cast<float*>(smem) + warp * (32 * 36);          // [32 channels][32 columns + 4 pad]
+        const int lr = lane >> 3, lq = lane & 7;
         for (int cb0 = 0; cb0 < BN; cb0 += 32) {
             if (((cb0 >> 5) % (NPW / 4)) != cgrp) continue;
+            if (g.dbg & 64) continue;
+            // the lane's column quad in the row-wise passes
+            const long long colq = col0 + cb0 + lq * 4;
+            const bool qv = cb0 + lq * 4 < BN && colq < NC;
+            long long coff = 0;
+            if (coal && qv) {
+                long long pos = 0, n = colq;
+                if (p.Pout > 1) { pos = colq / p.N; n = colq - pos * p.N; }
+                const long long bb = n / WF_T;
+                coff = pos * p.out_sp + bb * p.out_sb + (n - bb * WF_T);
+            }
+            const int mrow0 = m0 + tj * BM + quarter * 32;
+            if (coal && need_raw) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = 4 * i + lr;
+                    float4 e = f4zero();
+                    if (qv && mrow0 + row < p.Cout) e = ld4(p.eraw + (long long)(mrow0 + row) * p.out_sc + coff);
+                    *reinterpret_cast<float4*>(stg + row * 36 + lq * 4) = e;
+                }
+                __syncwarp();
+            }
             float acc[32], cor[32];
             tmem_ld32(trow + (uint32_t)cb0, acc);
             tmem_ld32(trow + (uint32_t)(g.bnp + cb0), cor);
             tmem_ld_wait();
-            if (mv) {
+            if (g.dbg & 32) continue;
+            if (!coal) {
+                if (mv) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const long long colj = col0 + cb0 + j * 4;
-                    if (cb0 + j * 4 < BN && colj < NC) {
-                        int pos = 0; long long n = colj;
-                        if (p.Pout > 1) { pos = (int)(colj / p.N); n = colj - (long long)pos * p.N; }
-                        float q4[4] = {acc[j * 4 + 0] + cor[j * 4 + 0] + bias, acc[j * 4 + 1] + cor[j * 4 + 1] + bias,
-                                       acc[j * 4 + 2] + cor[j * 4 + 2] + bias, acc[j * 4 + 3] + cor[j * 4 + 3] + bias};
-                        wf_epilogue_quad(p, co, pos, (int)n, es, et, em, q4, s0, s1);
+                    for (int j = 0; j < 8; ++j) {
+                        const long long colj = col0 + cb0 + j * 4;
+                        if (cb0 + j * 4 < BN && colj < NC) {
+                            int pos = 0; long long n = colj;
+                            if (p.Pout > 1) { pos = (int)(colj / p.N); n = colj - (long long)pos * p.N; }
+                            float q4[4] = {acc[j * 4 + 0] + cor[j * 4 + 0] + bias, acc[j * 4 + 1] + cor[j * 4 + 1] + bias,
+                                           acc[j * 4 + 2] + cor[j * 4 + 2] + bias, acc[j * 4 + 3] + cor[j * 4 + 3] + bias};
+                            wf_epilogue_quad(p, co, pos, (int)n, es, et, em, q4, s0, s1);
+                        }
                     }
                 }
+                continue;
             }
+            // channel-wise pass: epilogue math and statistics, result into the staging tile
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const long long colj = col0 + cb0 + j * 4;
+                float v[4] = {acc[j * 4 + 0] + cor[j * 4 + 0] + bias, acc[j * 4 + 1] + cor[j * 4 + 1] + bias,
+                              acc[j * 4 + 2] + cor[j * 4 + 2] + bias, acc[j * 4 + 3] + cor[j * 4 + 3] + bias};
+                float* sp = stg + lane * 36 + j * 4;
+                if (mv && cb0 + j * 4 < BN && colj < NC) {
+                    if (p.epi_mode == EPI_STATS) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { s0 += v[e]; s1 = fmaf(v[e], v[e], s1); }
+                    } else if (need_raw) {
+                        const float4 r4 = *reinterpret_cast<const float4*>(sp);
+                        const float r[4] = {r4.x, r4.y, r4.z, r4.w};
+                        if (p.epi_mode == EPI_DSILU) {
+                            float mk[4] = {1.f, 1.f, 1.f, 1.f};
+                            if (p.emask) {
+                                long long n = colj;
+                                if (p.Pout > 1) n = colj % p.N;
+                                const long long bb = n / WF_T; const int t = (int)(n - bb * WF_T);
+                                const float* mp = p.emask + bb * p.em_sb + (long long)co * p.em_sc + (long long)t * p.em_st;
+                                if (p.em_st == 1) { const float4 m4 = ld4(mp); mk[0] = m4.x; mk[1] = m4.y; mk[2] = m4.z; mk[3] = m4.w; }
+                                else { const float mm = *mp; mk[0] = mk[1] = mk[2] = mk[3] = mm; }
+                            }
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) v[e] = v[e] * mk[e] * wf_dsilu(fmaf(es, r[e] - em, et));
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { s0 += v[e]; s1 = fmaf(v[e], r[e] - em, s1); }
+                    }
+                }
+                *reinterpret_cast<float4*>(sp) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+            __syncwarp();
+            // row-wise pass: whole 128-byte rows to global memory
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = 4 * i + lr;
+                if (qv && mrow0 + row < p.Cout) {
+                    float4 o = *reinterpret_cast<const float4*>(stg + row * 36 + lq * 4);
+                    float* dst = p.out + (long long)(mrow0 + row) * p.out_sc + coff;
+                    if (p.accumulate) { const float4 old = ld4(dst); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                    st4(dst, o);
+                }
+            }
+            __syncwarp();
         }
         if (mv && p.epi_mode != EPI_STORE && p.stat0 != nullptr) {
             atomicAdd(p.stat0 + co, (double)s0);
@@ -237,29 +325,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
         // ------------------------------ MMA issue (one thread) ------------------------------
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(BM, BN, 0, 1);             // A (weights) K-major, B (activations) MN-major
-            int s = 0; uint32_t ph = 0;
+            int s = 0, sa = 0; uint32_t ph = 0, pha = 0;
             for (int kc = 0; kc < KT; ++kc) {
-                mbar_wait(full_a(s), ph);
+                mbar_wait(full_a(sa), pha);
                 mbar_wait(full_b(s), ph);
                 tc_fence_after();
-                const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES);
-                const uint32_t b_hi = a0 + A_BYTES, b_lo = b_hi + B_HALF;
+                const uint32_t a0 = smem_u32(smem_a + sa * A_BYTES);
+                const uint32_t b_hi = smem_u32(smem + s * B_STAGE), b_lo = b_hi + B_HALF;
 #pragma unroll
                 for (int kk = 0; kk < KC / 8; ++kk) {
                     // 8 channels = 8 rows of 128 bytes per K step; 32-column blocks KC*128 bytes apart; groups of 4 rows 512 bytes apart
                     const uint64_t dbh = umma_desc_l(b_hi + kk * 1024, KC * 128, 512, 1), dbl = umma_desc_l(b_lo + kk * 1024, KC * 128, 512, 1);
                     const uint32_t accf = (kc | kk) != 0 ? 1u : 0u;
+                    if (g.dbg & 2) continue;
                     for (int tj = 0; tj < ntile; ++tj) {          // the M tiles of this CTA share the activation descriptors
                         const uint32_t a_hi = a0 + tj * 2 * A_HALF, a_lo = a_hi + A_HALF;
                         const uint64_t dah = umma_desc(a_hi + kk * 2 * A_LBO, A_LBO, A_SBO), dal = umma_desc(a_lo + kk * 2 * A_LBO, A_LBO, A_SBO);
                         const uint32_t t_main = tmem_base + (uint32_t)(tj * 2 * g.bnp), t_cor = t_main + (uint32_t)g.bnp;
-                        umma_tf32(t_cor, dal, dbh, idesc, accf);
-                        umma_tf32(t_cor, dah, dbl, idesc, 1u);
+                        if (!(g.dbg & 16)) {
+                            umma_tf32(t_cor, dal, dbh, idesc, accf);
+                            umma_tf32(t_cor, dah, dbl, idesc, 1u);
+                        }
                         umma_tf32(t_main, dah, dbh, idesc, accf);
                     }
                 }
                 umma_commit(empty(s));
+                umma_commit(empty_a(sa));
                 if (++s == STAGES) { s = 0; ph ^= 1u; }
+                if (++sa == NSA) { sa = 0; pha ^= 1u; }
             }
             umma_commit(accum_bar);
         }
@@ -268,13 +361,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
             for (int kc = 0; kc < KT; ++kc) {
-                mbar_wait(empty(s), ph ^ 1u);
+                mbar_wait(empty_a(s), ph ^ 1u);
+                if (g.dbg & 4) { mbar_arrive(full_a(s)); if (++s == NSA) { s = 0; ph ^= 1u; } continue; }       // no weight copies
                 mbar_arrive_expect_tx(full_a(s), ntile * 2 * A_HALF);
                 for (int tj = 0; tj < ntile; ++tj) {
                     const float* wsrc = p.wtc + ((size_t)(mt0 + tj) * KT + kc) * (2 * A_HALF / 4);
-                    bulk_g2s(smem_u32(smem + s * STAGE_BYTES + tj * 2 * A_HALF), wsrc, 2 * A_HALF, full_a(s));
+                    bulk_g2s(smem_u32(smem_a + s * A_BYTES + tj * 2 * A_HALF), wsrc, 2 * A_HALF, full_a(s));
                 }
-                if (++s == STAGES) { s = 0; ph ^= 1u; }
+                if (++s == NSA) { s = 0; ph ^= 1u; }
             }
         }
     }
@@ -519,7 +613,7 @@ __global__ void tc_pack_kernel(TcPackTable tab, const float* params, float* pack
     }
 }
 
-constexpr int SMEM_MAX = 200 * 1024;
+constexpr int SMEM_MAX = 227 * 1024;
 
 template <int PRO, bool MASK>
 cudaError_t launch_conv_t(const ConvP& p, const TcGeom& g, dim3 grid, int smem, cudaStream_t st)
@@ -573,17 +667,22 @@ cudaError_t wf_launch_tc_conv(const ConvP& p, int num_sms, cudaStream_t st)
     static const int bn_env = [] { const char* e = std::getenv("WF_TC_BN"); return e ? std::atoi(e) : 0; }();       // experiments only
     if (bn_env >= 64 && bn_env <= bn_max && bn_env % 32 == 0) best_bn = bn_env;
     TcGeom g{};
+    static const int dbg_env = [] { const char* e = std::getenv("WF_TC_DBG"); return e ? std::atoi(e) : 0; }();       // measurements: 1 no activation loads, 2 no MMAs
+    g.dbg = dbg_env;
     g.mp = mp; g.mtiles = (int)mt;
     g.bn = best_bn;
     g.bnp = (best_bn + 31) / 32 * 32;
     g.tmem_cols = 32;
     while (g.tmem_cols < mp * 2 * g.bnp) g.tmem_cols *= 2;
-    const int stage = mp * 2 * A_HALF + 2 * KC * g.bn * 4;
-    const int budget = (g.tmem_cols <= 256 && mp == 1) ? 100 * 1024 : SMEM_MAX - 256;       // narrow tiles: leave room for a second CTA per SM
-    g.nst = budget / stage;
+    const int a_bytes = mp * 2 * A_HALF, b_stage = 2 * KC * g.bn * 4;
+    const int budget = (g.tmem_cols <= 256 && mp == 1) ? 100 * 1024 : SMEM_MAX - 512;       // narrow tiles: leave room for a second CTA per SM
+    g.nst = budget / (a_bytes + b_stage);
     if (g.nst > 4) g.nst = 4;
     if (g.nst < 2) g.nst = 2;
-    const int smem = g.nst * stage + (3 * g.nst + 1) * 8 + 16;
+    g.nsa = g.nst + (budget - g.nst * (a_bytes + b_stage)) / a_bytes;      // what is left deepens the weight ring
+    if (g.nsa > 4) g.nsa = 4;
+    if (g.nsa < g.nst) g.nsa = g.nst;
+    const int smem = g.nst * b_stage + g.nsa * a_bytes + (2 * g.nst + 2 * g.nsa + 1) * 8 + 16;
     dim3 grid((unsigned)((NC + g.bn - 1) / g.bn), (unsigned)((mt + mp - 1) / mp));
     const bool mask = p.pro_mode == PRO_BNSILU && p.mask != nullptr;
     switch (p.pro_mode) {

@@ -6,7 +6,9 @@
  *
  * Conventions
  *  - every pointer is a DEVICE pointer to fp32 data unless stated otherwise; all buffers are owned by the caller;
- *    the library allocates nothing and keeps no mutable global state (it is re-entrant across streams/threads);
+ *    the library allocates no device memory and keeps no state that outlives a call except per-THREAD bookkeeping
+ *    (last error string, profiler records, the programmatic-launch switch, one side stream + events per host thread)
+ *    and a process-wide launch counter, so it is re-entrant across streams and threads;
  *  - work is only enqueued on `stream`; no call synchronises, so every call is CUDA-graph capturable;
  *  - return value: 0 ok, <0 argument error (WF_E_*), >0 a cudaError_t; wf_last_error_string() describes the last
  *    failure on the calling thread.  There is no CPU fallback: without an sm_100a device the calls fail.

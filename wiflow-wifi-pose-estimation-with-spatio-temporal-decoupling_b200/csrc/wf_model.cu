@@ -29,6 +29,7 @@ constexpr int T = WF_T;
 struct ProfRec { std::string name; cudaEvent_t a, b; double flops, bytes; };
 thread_local std::vector<ProfRec> g_prof;
 std::atomic<long long> g_launches{0};
+inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 // windows per pass of an eval-mode forward (bounds the workspace); WF_EVAL_CHUNK overrides it for measurements
 const int EVAL_CHUNK = [] { const char* e = std::getenv("WF_EVAL_CHUNK"); const int v = e ? std::atoi(e) : 0; return v >= 64 ? v : 4096; }();
 // WF_DISABLE_TC=1 routes the pointwise convs through the CUDA-core GEMM instead of tcgen05 (A/B measurements only)
@@ -936,7 +937,7 @@ int run_forward(const wf_block_desc* d, const float* x, const float* params, flo
             cur = Act{xc, T, 0, (long long)n.tcn[0].cin * T};
         } else {
             RefStrides rs = ref_strides(d, false, n);
-            c.ck((g_launches.fetch_add(1), 0) ? cudaSuccess : wf_launch_permute(xc, n.in_buf, n.in_C, n.in_P, bc, rs.sb, rs.sc, rs.sp, rs.st, 1, c.sms, st));
+            { count_launch(); c.ck(wf_launch_permute(xc, n.in_buf, n.in_C, n.in_P, bc, rs.sb, rs.sc, rs.sp, rs.st, 1, c.sms, st)); }
             cur = internal(n.in_buf, n.in_P, c.N);
         }
         for (auto& t : n.tcn) { tcn_block_fwd(c, t, cur); cur = internal(t.X, 1, c.N); }
@@ -956,9 +957,9 @@ int run_forward(const wf_block_desc* d, const float* x, const float* params, flo
             if (!n.ax.empty()) {
                 // output = bn_output(sv): apply the affine while permuting (JoinP-free path: use a conv-free affine permute)
                 const BnUnit& bo = n.bn[n.ax.back().bn_out];
-                c.ck((g_launches.fetch_add(1), 0) ? cudaSuccess : wf_launch_permute_affine(src, yc, n.out_C, n.out_P, bc, rs.sb, rs.sc, rs.sp, rs.st, bo.scale(), bo.shift(), bo.mean(), c.sms, st));
+                { count_launch(); c.ck(wf_launch_permute_affine(src, yc, n.out_C, n.out_P, bc, rs.sb, rs.sc, rs.sp, rs.st, bo.scale(), bo.shift(), bo.mean(), c.sms, st)); }
             } else {
-                c.ck((g_launches.fetch_add(1), 0) ? cudaSuccess : wf_launch_permute(src, yc, n.out_C, n.out_P, bc, rs.sb, rs.sc, rs.sp, rs.st, 0, c.sms, st));
+                { count_launch(); c.ck(wf_launch_permute(src, yc, n.out_C, n.out_P, bc, rs.sb, rs.sc, rs.sp, rs.st, 0, c.sms, st)); }
             }
         }
     }
@@ -1006,11 +1007,11 @@ int run_backward(const wf_block_desc* d, const float* x, const float* params, co
         if (!n.ax.empty()) {
             // dy is the gradient of bn_output's output: permute into dsv and accumulate its BatchNorm-backward sums
             AxBlk& ah = n.ax.back();
-            c.ck((g_launches.fetch_add(1), 0) ? cudaSuccess : wf_launch_permute(dy, ah.dsv, n.out_C, n.out_P, B, rs.sb, rs.sc, rs.sp, rs.st, 1, c.sms, st));
+            { count_launch(); c.ck(wf_launch_permute(dy, ah.dsv, n.out_C, n.out_P, B, rs.sb, rs.sc, rs.sp, rs.st, 1, c.sms, st)); }
             const BnUnit& bo = n.bn[ah.bn_out];
             c.ck(wf_launch_bn_bwd_stats(ah.dsv, ah.sv_raw, bo.mean(), 64, 15LL * c.N, bo.b0, bo.b1, c.sms, st));
         } else {
-            c.ck((g_launches.fetch_add(1), 0) ? cudaSuccess : wf_launch_permute(dy, n.dout_buf, n.out_C, n.out_P, B, rs.sb, rs.sc, rs.sp, rs.st, 1, c.sms, st));
+            { count_launch(); c.ck(wf_launch_permute(dy, n.dout_buf, n.out_C, n.out_P, B, rs.sb, rs.sc, rs.sp, rs.st, 1, c.sms, st)); }
             g_in = n.dout_buf;
         }
     }
@@ -1043,10 +1044,10 @@ int run_backward(const wf_block_desc* d, const float* x, const float* params, co
     if (want_dx) {
         if (n.in_is_ref_bct) {
             const int C = n.tcn[0].cin;
-            c.ck((g_launches.fetch_add(1), 0) ? cudaSuccess : wf_launch_permute(n.din_buf, dx, C, 1, B, (long long)C * T, T, 0, 1, 0, c.sms, st));
+            { count_launch(); c.ck(wf_launch_permute(n.din_buf, dx, C, 1, B, (long long)C * T, T, 0, 1, 0, c.sms, st)); }
         } else {
             RefStrides rs = ref_strides(d, false, n);
-            c.ck((g_launches.fetch_add(1), 0) ? cudaSuccess : wf_launch_permute(n.din_buf, dx, n.in_C, n.in_P, B, rs.sb, rs.sc, rs.sp, rs.st, 0, c.sms, st));
+            { count_launch(); c.ck(wf_launch_permute(n.din_buf, dx, n.in_C, n.in_P, B, rs.sb, rs.sc, rs.sp, rs.st, 0, c.sms, st)); }
         }
     }
     if (c.side) {                     // join: the caller's stream owns the complete gradient again

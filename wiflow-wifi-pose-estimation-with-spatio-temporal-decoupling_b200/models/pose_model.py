@@ -34,13 +34,10 @@ class WiFlowPoseModel(WFBlock):
                 nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
                 if m.bias is not None:
                     nn.init.constant_(m.bias, 0)
-            elif isinstance(m, (nn.BatchNorm1d, nn.LayerNorm)):
+            elif isinstance(m, nn.BatchNorm1d):
                 nn.init.constant_(m.weight, 1)
                 nn.init.constant_(m.bias, 0)
-            elif isinstance(m, nn.Linear):
-                nn.init.xavier_normal_(m.weight)
-                if m.bias is not None:
-                    nn.init.constant_(m.bias, 0)
+            # (the reference also lists nn.Linear / nn.LayerNorm; the model has neither, and constant_ draws no random numbers)
 
     def _wf_desc_key(self):
         return (_lib.BLOCK_MODEL, 0, 0, 0, 0)

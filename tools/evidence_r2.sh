@@ -18,6 +18,17 @@ for spec in "slab_tc_kernel 7 slab_fwd" "slab_tc_kernel 8 slab_dgrad" "slab_wgra
   python tools/sass_hist.py /tmp/r2_$3.ncu-rep > gpurun_out/ev/r2_$3_sass.txt 2>&1
   REPS="$REPS /tmp/r2_$3.ncu-rep"
 done
+# the pointwise tcgen05 kernels on the 540 -> 540 TCN layer at B = 1024 (tests/native/tc_selftest p: 3rd launch of each = warm)
+for spec in "pw_tc_kernel pw_tc" "pw_wgrad_tc_kernel pw_wgrad_tc"; do set -- $spec
+  ncu --set full --import-source on --clock-control none -k regex:$1 --launch-skip 2 --launch-count 1 -f -o /tmp/r2_$2 tests/native/tc_selftest p > /tmp/ncu_r2_$2.log 2>&1; tail -1 /tmp/ncu_r2_$2.log
+  python tools/summarize_ncu.py full /tmp/r2_$2.ncu-rep gpurun_out/ev/r2_$2_ncu.txt
+  python tools/sass_hist.py /tmp/r2_$2.ncu-rep > gpurun_out/ev/r2_$2_sass.txt 2>&1
+  REPS="$REPS /tmp/r2_$2.ncu-rep"
+done
 python tools/summarize_ncu.py traffic gpurun_out/ev/r2_ncu_traffic.json $REPS
+# ablations of pw_tc_kernel on the same layer (WF_TC_DBG bits: 1 no activation loads, 2 no MMAs, 4 no weight copies, 8 no operand
+# stores, 16 main product only, 32 no epilogue memory traffic, 64 no epilogue)
+( for d in 0 1 2 4 8 9 15 32 47 79; do echo "WF_TC_DBG=$d"; WF_TC_DBG=$d tests/native/tc_selftest p 2>&1 | grep "perf conv" | head -2; done ) > gpurun_out/ev/r2_pw_tc_ablation.txt 2>&1
+tests/native/slab_selftest bench > gpurun_out/ev/r2_slab_microbench.txt 2>&1
 cuobjdump -sass wiflow-*/libwiflow_b200.so | grep -oE "UTCHMMA|UTMALDG|UTMASTG|UBLKCP|LDTM|STTM|UTCBAR|HMMA\.[0-9A-Z.]+" | sort | uniq -c > gpurun_out/ev/r2_sass_mnemonics.txt; cat gpurun_out/ev/r2_sass_mnemonics.txt
 du -sh gpurun_out

@@ -18,7 +18,7 @@
 // flight (2-3 stages), not the tap window, which is what lets 64-channel layers keep 128-column tiles plus all tap weights
 // (hi and lo, 96 KB) in the 227 KB of shared memory.
 //
-// Warp roles (672 threads): warp 16 lane 0 issues the TMA loads, lane 0 of warps 17-20 issue tcgen05.mma, warps 0-15 are workers:
+// Warp roles (640 threads): warp 16 lane 0 issues the TMA loads, warps 17-19 issue tcgen05.mma (warp-uniform, one elected lane), warps 0-15 are workers:
 //   * transform: the raw slab (TMA) is rewritten IN PLACE as the activated operand -- BatchNorm+SiLU+Dropout2d, BatchNorm only,
 //     or BatchNorm-backward of (dy, raw) -- split into tf32 hi / lo images (3xTF32, fp32 parity: a*b ~ a_lo*b_hi + a_hi*b_lo +
 //     a_hi*b_hi).  Addresses are linear (the swizzle permutes 32-byte chunks inside a row, a row is one channel), so the

@@ -383,7 +383,7 @@ def run_ours(args, rank, world, local_rank):
     B = args.batch
     torch.manual_seed(0)
     model = wf.WiFlowPoseModel(dropout=0.5).to(dev)
-    ts = wf.TrainStep(model, B, process_group=pg)
+    ts = wf.TrainStep(model, B, process_group=pg, dropout_rng=args.dropout_rng)
     nbatch = 4
     xs, ys = [], []
     for i in range(nbatch):
@@ -449,7 +449,9 @@ def run_ours(args, rank, world, local_rank):
             'config': {'workload': workload_name(args), 'per_gpu_batch': B, 'global_batch': B * world, 'parallelism': f'dp{world}',
                        'l2': f'inputs rotate over {nbatch} batches ({nbatch * B * 43200 / 1e6:.0f} MB) and every step streams '
                              f'{ts.ws.numel() / 1e9:.1f} GB of saved activations, far above the 126 MB L2',
-                       'collective': 'NCCL all-reduce of the flat 8.9 MB fp32 gradient per step' if world > 1 else 'none'},
+                       'collective': 'NCCL all-reduce of the flat 8.9 MB fp32 gradient per step' if world > 1 else 'none',
+                       'dropout_rng': "philox: all 18 masks of a step drawn inside the timed step by one wf_dropout_masks launch" if args.dropout_rng == 'philox'
+                                      else "torch: one F.dropout(ones) draw per site inside the timed step (the parity mode)"},
             'e2e': {'value': e2e_value, 'unit': 'samples/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'how': 'TrainStep.step(pinned host x, y) + device->host read of its [loss, position, bone, grad_norm] every step; one step '
                            'in flight (the read of step i completes while step i+1 runs), wall clock over the timed steps'},
@@ -644,6 +646,8 @@ def main():
     ap.add_argument('--batch', type=int, default=1024, help='windows per GPU per step')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-extras', action='store_true')
+    ap.add_argument('--dropout-rng', default='philox', choices=['philox', 'torch'],
+                    help="how TrainStep draws the dropout masks: the library's one-launch Philox generator (default) or torch's generator")
     ap.add_argument('--ref-batch', type=int, default=0, help='windows per step of the reference arm (0: choose)')
     ap.add_argument('--c5-worker', default='', help='internal: run the C5 microbench in this process and print JSON')
     args = ap.parse_args()

@@ -118,6 +118,14 @@ WF_API int wf_noise_scale(const float* x, const float* noise, float* y, long lon
                    long long n_stat, wf_stream_t stream);
 WF_API int wf_keypoint_batch(const float* frames, long long n_frames, const long long* idx, float* y, int B, int K, int clean,
                       wf_stream_t stream);
+/* wf_dropout_masks: the dropout masks of one training step in ONE launch (perf mode of the nn.Dropout / nn.Dropout2d draws of
+ *   models/tcn.py:30,43 and models/convnet.py:15,20; the parity mode passes masks drawn by torch's generator instead).
+ *   out / numel / p: HOST arrays of n_sites (<= 32) device buffers, their element counts and drop probabilities;
+ *   out[i][k] = u >= p[i] ? 1/(1-p[i]) : 0 with u = Philox4x32-10(counter = (k/4, draw), key = seed ^ f(i))[k%4] * 2^-32.
+ *   state: 2 x uint64 on the DEVICE, zeroed once by the caller: [0] = draw counter, advanced by one per call ON THE DEVICE (so a
+ *   captured CUDA graph draws fresh masks on every replay), [1] = scratch.  Same (seed, draw) -> same masks. */
+WF_API int wf_dropout_masks(float* const* out, const long long* numel, const float* p, int n_sites, unsigned long long seed,
+                     unsigned long long* state, wf_stream_t stream);
 WF_API int wf_keypoint_sequences(float* frames, const long long* seq_off, int n_seq, int K, wf_stream_t stream);
 
 /* ---- measurement hooks (bench.py) ----

@@ -281,3 +281,64 @@ def test_cpu_tensors_are_rejected(wf):
         model(torch.randn(2, 540, 20))
     with pytest.raises(RuntimeError):
         model(torch.randn(2, 540, 21).cuda())
+
+
+def test_philox_dropout_masks_statistics_and_replay():
+    """perf-mode dropout (wf_dropout_masks; reference draws: models/tcn.py:30,43 nn.Dropout, models/convnet.py:15,20 nn.Dropout2d):
+    values are 0 or 1/(1-p), keep rate within 5 sigma, sites independent, same (seed, draw) -> same masks, and the draw counter
+    advances on the device so that two calls (or two replays of a captured graph) differ"""
+    import wiflow_b200 as wf
+    from wiflow_b200 import ops
+    dev = torch.device('cuda')
+    shapes = [(64, 540, 20), (64, 540, 20), (64, 8), (3, 5), (64, 64)]
+    ps = [0.5, 0.5, 0.3, 0.3, 0.0]
+    st = torch.zeros(2, device=dev, dtype=torch.int64)
+    a = ops.dropout_masks(shapes, ps, 1234, st, dev)
+    torch.cuda.synchronize()
+    assert st.tolist() == [1, 0]
+    for m, sh, p in zip(a, shapes, ps):
+        assert tuple(m.shape) == tuple(sh)
+        keep = 1.0 / (1.0 - p)
+        vals = torch.unique(m).tolist()
+        assert all(abs(v) < 1e-12 or abs(v - keep) < 1e-6 for v in vals), vals
+        n = m.numel()
+        rate = (m != 0).double().mean().item()
+        sigma = (p * (1 - p) / n) ** 0.5
+        assert abs(rate - (1 - p)) <= 5 * sigma + 1e-12, (sh, p, rate)
+    # the two equally shaped, equally parametrised sites are different streams, uncorrelated
+    x, y = (a[0] != 0).double().flatten(), (a[1] != 0).double().flatten()
+    assert not torch.equal(a[0], a[1])
+    corr = ((x - x.mean()) * (y - y.mean())).mean().item() / (x.std().item() * y.std().item())
+    assert abs(corr) < 5.0 / x.numel() ** 0.5, corr
+    # neighbouring elements of one site as well
+    corr1 = ((x[1:] - x.mean()) * (x[:-1] - x.mean())).mean().item() / x.var().item()
+    assert abs(corr1) < 5.0 / x.numel() ** 0.5, corr1
+    # next draw differs; resetting the counter reproduces the first draw
+    b = ops.dropout_masks(shapes, ps, 1234, st, dev)
+    assert not torch.equal(a[0], b[0]) and st.tolist() == [2, 0]
+    st.zero_()
+    c = ops.dropout_masks(shapes, ps, 1234, st, dev)
+    assert all(torch.equal(u, v) for u, v in zip(a, c))
+    st.zero_()
+    d = ops.dropout_masks(shapes, ps, 99, st, dev)
+    assert not torch.equal(a[0], d[0])
+
+
+def test_train_step_with_philox_dropout_runs_and_redraws():
+    """TrainStep(dropout_rng='philox'): the captured graph draws fresh masks on every replay (losses of identical inputs differ
+    from step to step beyond what the weight update explains is not checkable; the device draw counter is), and the loss falls"""
+    import wiflow_b200 as wf
+    torch.manual_seed(0)
+    model = wf.WiFlowPoseModel(dropout=0.5).cuda()
+    ts = wf.TrainStep(model, 8, dropout_rng='philox', lr=1e-3)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(8, 540, 20, generator=g).cuda()
+    y = torch.rand(8, 15, 2, generator=g).cuda()
+    losses = []
+    for _ in range(12):
+        out = ts.step(x, y)
+        losses.append(float(out[0]))
+    torch.cuda.synchronize()
+    assert int(ts.rng_state[0]) >= 12 and int(ts.rng_state[1]) == 0       # one draw per executed step (an eager warm-up before the capture counts too)
+    assert all(l == l and l < 1e3 for l in losses)
+    assert min(losses[-4:]) < losses[0]

@@ -62,6 +62,8 @@ def lib():
     L.wf_window_load.argtypes = [vp, ll, vp, vp, ip, ip, ip, ip, vp, vp, vp]
     L.wf_noise_scale.restype = ip
     L.wf_noise_scale.argtypes = [vp, vp, vp, ll, f, f, vp, ll, vp]
+    L.wf_dropout_masks.restype = ip
+    L.wf_dropout_masks.argtypes = [vp, vp, vp, ip, ctypes.c_ulonglong, vp, vp]
     L.wf_keypoint_batch.restype = ip
     L.wf_keypoint_batch.argtypes = [vp, ll, vp, vp, ip, ip, ip, vp]
     L.wf_keypoint_sequences.restype = ip

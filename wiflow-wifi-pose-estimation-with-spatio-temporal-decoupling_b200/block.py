@@ -104,10 +104,16 @@ class WFBlock(nn.Module):
             _flatten(nbts, torch.int64)
         return _flat_view(params), _flat_view(run), _flat_view(nbts)
 
-    def _wf_masks(self, B, device):
+    def _wf_masks(self, B, device, rng_state=None, seed=0):
+        """the step's dropout masks in the reference's forward order.  Default: torch's generator (the draws nn.Dropout /
+        nn.Dropout2d would make, so a seeded run matches the oracle); with rng_state (2 int64 on the device): the library's
+        one-launch Philox generator (ops.dropout_masks) -- different stream of random numbers, same distribution"""
         sites = self._wf_dropout_sites()
         if all(p == 0 for p, _, _ in sites):
             return []
+        if rng_state is not None:
+            shapes = [(B, C, 20) if kind == 'elem' else (B, C) for _, kind, C in sites]
+            return ops.dropout_masks(shapes, [p for p, _, _ in sites], seed, rng_state, device)
         masks = []
         cache = _ONES       # the all-ones inputs of the draws, filled once per shape (not per step); module-level: never pickled / deep-copied
         for p, kind, C in sites:

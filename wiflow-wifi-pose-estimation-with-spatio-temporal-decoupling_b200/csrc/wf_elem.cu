@@ -51,6 +51,55 @@ __global__ void bn_eval_coefs_kernel(BnEvalTable tab, const float* params, const
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Dropout masks of a whole training step in one launch (perf mode of models/tcn.py:30,43 nn.Dropout and models/convnet.py:15,20
+// nn.Dropout2d; the parity mode draws them with torch's generator, block.py).  Site i: out[k] = u >= p ? 1/(1-p) : 0 for k < numel,
+// u = Philox4x32-10(counter = (k/4, draw), key = seed ^ site)[k%4] * 2^-32.  `draw` lives on the device (state[0]) and is advanced
+// by the last CTA to finish, so every replay of a captured graph draws fresh masks; state[1] is that CTA ticket.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+__global__ void __launch_bounds__(256) dropout_masks_kernel(MaskTable tab, unsigned long long seed, unsigned long long* state)
+{
+    wf_pdl_enter();
+    const unsigned long long draw = __ldcg(state);
+    const MaskSite st = tab.s[blockIdx.y];
+    const unsigned long long ks = seed ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(blockIdx.y + 1));
+    const uint2 key = make_uint2((unsigned)ks, (unsigned)(ks >> 32));
+    const float keep = 1.f / (1.f - st.p);
+    const long long n4 = (st.numel + 3) / 4;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
+        const uint4 r = philox4x32_10(make_uint4((unsigned)q, (unsigned)(q >> 32), (unsigned)draw, (unsigned)(draw >> 32)), key);
+        float4 m;
+        m.x = (float)r.x * 2.3283064365386963e-10f >= st.p ? keep : 0.f;
+        m.y = (float)r.y * 2.3283064365386963e-10f >= st.p ? keep : 0.f;
+        m.z = (float)r.z * 2.3283064365386963e-10f >= st.p ? keep : 0.f;
+        m.w = (float)r.w * 2.3283064365386963e-10f >= st.p ? keep : 0.f;
+        if (q * 4 + 3 < st.numel) st4(st.out + q * 4, m);
+        else {
+            const float v[4] = {m.x, m.y, m.z, m.w};
+            for (int j = 0; j < 4 && q * 4 + j < st.numel; ++j) st.out[q * 4 + j] = v[j];
+        }
+    }
+    // every CTA has read `draw` before it takes a ticket, so the last one may advance it
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long total = (unsigned long long)gridDim.x * gridDim.y;
+        if (atomicAdd(state + 1, 1ull) == total - 1) { state[1] = 0ull; state[0] = draw + 1ull; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Residual joins.  TCN: silu(mask*silu(bn(pw2)) + res) (models/tcn.py:74), conv blocks: silu(bn(c3) + bn(ds))
 // (models/convnet.py:36-37,72-73).  One channel per blockIdx.y, float4 over the [P][N] plane.
 // ---------------------------------------------------------------------------------------------------------
@@ -489,6 +538,17 @@ static int ew_blocks(long long total4, int C, int num_sms)
     if (want > cap) want = cap;
     if (want < 1) want = 1;
     return (int)want;
+}
+cudaError_t wf_launch_dropout_masks(const MaskTable& tab, unsigned long long seed, unsigned long long* state, int num_sms, cudaStream_t st)
+{
+    long long nmax = 0;
+    for (int i = 0; i < tab.n; ++i) nmax = tab.s[i].numel > nmax ? tab.s[i].numel : nmax;
+    long long bx = cdiv((nmax + 3) / 4, 256 * 4);                       // ~4 quads per thread of the largest site
+    const long long cap = (long long)num_sms * 8 / tab.n + 1;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    wf_launch_pdl(dropout_masks_kernel, dim3((unsigned)bx, (unsigned)tab.n), dim3(256), 0, st, tab, seed, state);
+    return cudaGetLastError();
 }
 cudaError_t wf_launch_join_fwd(const JoinP& p, int num_sms, cudaStream_t st)
 {

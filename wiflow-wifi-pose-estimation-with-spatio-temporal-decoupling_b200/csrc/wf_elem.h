@@ -11,6 +11,10 @@ enum { WF_LOSS_SMOOTH_L1 = 0, WF_LOSS_MSE = 1, WF_LOSS_L1 = 2 };
 struct BnEvalEntry { int C, Cpad, gamma_off, run_off, coef_off; };
 struct BnEvalTable { int n; BnEvalEntry e[WF_MAX_BN]; };
 
+#define WF_MAX_MASK_SITES 32
+struct MaskSite { float* out; long long numel; float p; };
+struct MaskTable { int n; MaskSite s[WF_MAX_MASK_SITES]; };
+
 struct JoinP {
     const float *a, *r;
     float* out;
@@ -90,6 +94,7 @@ cudaError_t wf_launch_tc_wgrad(const WgradP& p, int num_sms, cudaStream_t st);
 int wf_conv_bm_for(int M);
 int wf_conv_bk_for(int M);
 
+cudaError_t wf_launch_dropout_masks(const MaskTable& tab, unsigned long long seed, unsigned long long* state, int num_sms, cudaStream_t st);
 cudaError_t wf_launch_bn_fwd_fin(const BnFwdFin* d, int n, cudaStream_t st);
 cudaError_t wf_launch_bn_bwd_fin(const BnBwdFin* d, int n, cudaStream_t st);
 cudaError_t wf_launch_bn_eval_coefs(const BnEvalTable& tab, const float* params, const float* running, float* coefs, cudaStream_t st);

@@ -1207,6 +1207,25 @@ int wf_noise_scale(const float* x, const float* noise, float* y, long long n, fl
     return e == cudaSuccess ? 0 : fail((int)e, cudaGetErrorString(e));
 }
 
+int wf_dropout_masks(float* const* out, const long long* numel, const float* p, int n_sites, unsigned long long seed,
+                     unsigned long long* state, wf_stream_t stream)
+{
+    if (int e = check_device()) return e;
+    if (n_sites == 0) return 0;
+    if (!out || !numel || !p || !state || n_sites < 0 || n_sites > WF_MAX_MASK_SITES) return fail(WF_E_ARG, "null pointer or more than 32 sites");
+    MaskTable tab{};
+    for (int i = 0; i < n_sites; ++i) {
+        if (!out[i] || numel[i] < 0 || !(p[i] >= 0.f && p[i] < 1.f)) return fail(WF_E_ARG, "mask site: null buffer, negative size or p outside [0,1)");
+        if ((uintptr_t)out[i] & 15) return fail(WF_E_ARG, "mask buffers must be 16-byte aligned");
+        if (numel[i] == 0) continue;
+        tab.s[tab.n++] = MaskSite{out[i], numel[i], p[i]};
+    }
+    if (tab.n == 0) return 0;
+    g_launches.fetch_add(1);
+    cudaError_t e = wf_launch_dropout_masks(tab, seed, state, num_sms(), (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail((int)e, cudaGetErrorString(e));
+}
+
 int wf_keypoint_batch(const float* frames, long long n_frames, const long long* idx, float* y, int B, int K, int clean, wf_stream_t stream)
 {
     if (int e = check_device()) return e;

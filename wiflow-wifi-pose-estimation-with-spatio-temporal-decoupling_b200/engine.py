@@ -41,7 +41,7 @@ class TrainStep:
 
     def __init__(self, model: WiFlowPoseModel, batch_size: int, lr=1e-4, weight_decay=5e-5, betas=(0.9, 0.999), eps=1e-8,
                  max_norm=1.0, position_weight=1.0, bone_weight=0.2, loss_type='smooth_l1', process_group=None,
-                 use_cuda_graph=True, dropout=True, accumulation_steps=1, metric_thresholds=None):
+                 use_cuda_graph=True, dropout=True, accumulation_steps=1, metric_thresholds=None, dropout_rng='torch', seed=None):
         self.model = model
         self.B = int(batch_size)
         self.k = max(1, int(accumulation_steps))            # micro-batches per optimizer step (train.py:80, :243-249)
@@ -51,6 +51,10 @@ class TrainStep:
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (process_group is not None or (dist.is_available() and dist.is_initialized())) else 1
         self.dropout = dropout
+        if dropout_rng not in ('torch', 'philox'):
+            raise ValueError("dropout_rng must be 'torch' (masks drawn by torch's generator, as nn.Dropout would: the parity mode) or "
+                             "'philox' (the library's one-launch generator: the perf mode)")
+        self.dropout_rng = dropout_rng
         model.train()
         self.params, self.running, self.nbt = model._wf_state()
         dev = self.params.device
@@ -62,6 +66,13 @@ class TrainStep:
         self.exp_avg = torch.zeros(n, device=dev)
         self.exp_avg_sq = torch.zeros(n, device=dev)
         self.adam_state = ops.adam_state(dev)
+        self.rng_state = None
+        if dropout_rng == 'philox':
+            # device-side draw counter (every graph replay draws fresh masks); the key mixes in the rank: each replica sees other data
+            self.rng_state = torch.zeros(2, device=dev, dtype=torch.int64)
+            base = torch.initial_seed() if seed is None else int(seed)
+            rank = dist.get_rank(process_group) if self.world > 1 else 0
+            self.rng_seed = (base * 0x9E3779B97F4A7C15 + (rank + 1) * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
         self.flags = _lib.FLAG_TRAIN | _lib.FLAG_SAVE
         self.ws = torch.empty(ops.workspace_bytes(MODEL_DESC, self.B, self.flags), device=dev, dtype=torch.uint8)
         self.x = torch.zeros(self.B, 540, 20, device=dev)
@@ -99,7 +110,12 @@ class TrainStep:
         """forward + PoseLoss + backward of one micro-batch (any B <= self.B: the workspace was sized for self.B)"""
         m = self.model
         B = x.shape[0]
-        masks = m._wf_masks(B, self.dev) if self.dropout else []
+        if not self.dropout:
+            masks = []
+        elif self.rng_state is not None:
+            masks = m._wf_masks(B, self.dev, self.rng_state, self.rng_seed)
+        else:
+            masks = m._wf_masks(B, self.dev)
         self.pred = ops.block_forward(x, self.params, self.running, self.nbt, masks, MODEL_DESC, self.flags, self.ws)
         out3, dpred = ops.pose_loss(self.pred, y, self.loss[0], self.loss[1], self.loss[2], self.loss_scratch, True)
         self.out[:3].copy_(out3)

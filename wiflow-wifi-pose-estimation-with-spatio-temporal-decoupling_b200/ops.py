@@ -208,6 +208,25 @@ def noise_scale(x: torch.Tensor, noise, level: float, scale: float, stats, out: 
     return out
 
 
+def dropout_masks(shapes, ps, seed: int, state: torch.Tensor, device) -> List[torch.Tensor]:
+    """Dropout masks of one step in one launch (wf_dropout_masks): one float32 tensor per (shape, p), entries 0 or 1/(1-p).
+    state: 2 int64 on the device, zeroed once (the draw counter advances on the device, so graph replays draw fresh masks)."""
+    _need_cuda(state)
+    if state.dtype != torch.int64 or state.numel() < 2:
+        raise RuntimeError('dropout_masks needs an int64 state tensor of 2 elements')
+    outs = [torch.empty(*sh, device=device, dtype=torch.float32) for sh in shapes]
+    n = len(outs)
+    if n == 0:
+        return outs
+    ptrs = (ctypes.c_void_p * n)(*[o.data_ptr() for o in outs])
+    numel = (ctypes.c_longlong * n)(*[o.numel() for o in outs])
+    pp = (ctypes.c_float * n)(*[float(p) for p in ps])
+    with torch.cuda.device(device):
+        rc = _lib.lib().wf_dropout_masks(ptrs, numel, pp, n, int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(state), _stream())
+    _lib.check(rc, 'wf_dropout_masks')
+    return outs
+
+
 def keypoint_batch(frames: torch.Tensor, idx, clean: bool = True, out: torch.Tensor = None) -> torch.Tensor:
     """y[b] = frames[idx[b]] ([K,2]; zeros for indices outside the array) with all-zero joints replaced by the mean of the others."""
     _need_cuda(frames, idx, out)

@@ -112,8 +112,13 @@ def test_train_step_b64_vs_oracle(wf):
             continue                      # Adam normalises noise-level gradients to +-lr: direction is not defined
         step_ref = params[n] - before[n].double()
         step_got = p.detach().cpu().double() - before[n].double()
-        # Adam's update is lr * m / (sqrt(v) + eps): elements whose gradient is far above the rounding noise must move alike
-        big = g64[n].abs() > 1e-3 * g64[n].abs().max()
+        # Adam's update is lr * m / (sqrt(v) + eps): elements whose gradient is far above the rounding noise must move alike.
+        # "Far above the noise" is measured against the fp32 oracle's own error on that tensor, not only against the tensor's
+        # largest entry: up.downsample.0.weight (Conv2d(1, 8, 1) + BatchNorm: one weight per channel, and BatchNorm cancels its
+        # scale) has a gradient of the order of the BatchNorm eps, i.e. ALL of it is rounding noise, and the first Adam step
+        # turns noise into +-lr.  (Seen as a 2-in-14 flake of this test before the second condition was added.)
+        noise = (g32[n].double() - g64[n]).abs().max()
+        big = (g64[n].abs() > 1e-3 * g64[n].abs().max()) & (g64[n].abs() > 50 * noise)
         if big.any():
             assert (step_got[big] - step_ref[big]).abs().max().item() <= 2e-2 * 1e-4 + 1e-9, n
 

@@ -71,9 +71,12 @@ __device__ __forceinline__ float4 sel4(bool c, float4 a, float4 b)
 // to columns [bnp, bnp + bn).  The tensor core truncates when it adds into the fp32 accumulator, an error that grows with the
 // number of accumulations; keeping the 2^-11-sized corrections out of the main accumulator cuts that count by three and
 // makes their own truncation irrelevant.  The epilogue adds the two in fp32.
-struct TcGeom { int bn, bnp, nst, nsa, tmem_cols, mp, mtiles, dbg; };      // nst / nsa: stages of the activation / weight ring      // mp: 128-row M tiles per CTA (they share the staged activation tile)
+struct TcGeom { int bn, bnp, nst, nsa, tmem_cols, mp, mtiles, dbg, mgroups, total; };      // nst / nsa: stages of the activation / weight ring      // mp: 128-row M tiles per CTA (they share the staged activation tile)
 
-template <int PRO, bool MASK>
+// PERSIST: a CTA walks tiles blockIdx.x, + gridDim.x, ...; otherwise exactly one tile (straight-line code: the loop-carried state of
+// the persistent form costs the BatchNorm+SiLU producers 13 % at the 96-register budget of an 18-warp CTA -- 5 warps per scheduler
+// x 32 x R <= 16 K registers -- so it is used only where a CTA gets many tiles)
+template <int PRO, bool MASK, bool PERSIST>
 __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const TcGeom g)
 {
     wf_pdl_enter();
@@ -101,11 +104,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int KT = p.tc_kt;
-    const int mt0 = blockIdx.y * MP;                      // first M tile of this CTA
-    const int ntile = min(MP, g.mtiles - mt0);
-    const int m0 = mt0 * BM;
     const long long NC = (long long)p.Pout * p.N;
-    const long long col0 = (long long)blockIdx.x * BN;
+    // Persistent CTAs: tile = blockIdx.x, + gridDim.x, ... over (column tile, M-tile group), M fastest so that the CTAs working at the
+    // same time share the activation columns in L2.  Launch, TMEM allocation and barrier set-up are paid once per CTA instead of once
+    // per tile (~5 of the ~32 us of a 128 x 256 tile); the rings and their phases simply run on across tiles.
+#define WF_TC_TILE_VARS(tile)                                          \
+    const int mt0 = ((tile) % g.mgroups) * MP;                         \
+    const int ntile = min(MP, g.mtiles - mt0);                         \
+    const int m0 = mt0 * BM;                                           \
+    const long long col0 = (long long)((tile) / g.mgroups) * BN;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_b(s), NPW); mbar_init(empty(s), 1); }
@@ -126,6 +133,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
         // transposed 4x4 micro blocks in registers into a K-major image: 32 selects per chunk and thread).
         const bool active = tid < (KC / 4) * NQ;
         const int q = tid % NQ, kq = tid / NQ;
+        int s = 0; uint32_t ph = 0;
+        int tile = blockIdx.x, it = 0;
+        do {
+        WF_TC_TILE_VARS(tile)
         const long long col = col0 + q * 4;
         const bool cval = active && col < NC;
         const float *pin = p.in, *pin2 = p.in2, *pm = p.mask;
@@ -140,7 +151,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
         }
         const long long in_sc = p.in_sc, m_sc = p.m_sc;
         const int m_st = p.m_st, Cin = p.Cin;
-        const float *ca_p = p.pro_a + kq * 4, *cb_p = p.pro_b + kq * 4, *cc_p = p.pro_c + kq * 4, *cd_p = p.pro_d + kq * 4;
         // MN-major operand image (SWIZZLE_128B_BASE32B): row = channel (K) of the stage, 128 bytes = 32 columns, 32-byte chunks XORed
         // with the row index mod 4; 32-column blocks KC*128 bytes apart.  A thread's float4 (4 columns of one channel) is one 16-byte
         // chunk of that image: no transpose, and a quarter warp (8 lanes = 8 consecutive column quads) fills one 128-byte row.
@@ -150,7 +160,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
             const int row = kq * 4 + j;
             soff[j] = (uint32_t)((q >> 3) * (KC * 128) + row * 128 + (((q & 7) ^ ((row & 3) << 1)) << 4));
         }
-        int s = 0; uint32_t ph = 0;
         for (int kc = 0; kc < KT; ++kc) {
             const int c0 = kc * KC + kq * 4;
             float4 v[4];
@@ -172,8 +181,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
                     }
                 }
                 if (PRO != PRO_NONE) {       // per-channel coefficients of the 4 channels: one 128-bit load per array
-                    A4 = ld4(ca_p + kc * KC); B4 = ld4(cb_p + kc * KC); D4 = ld4(cd_p + kc * KC);
-                    if (PRO == PRO_BNBWD) C4 = ld4(cc_p + kc * KC);
+                    A4 = ld4(p.pro_a + c0); B4 = ld4(p.pro_b + c0); D4 = ld4(p.pro_d + c0);      // (bases from the constant bank: no live pointers)
+                    if (PRO == PRO_BNBWD) C4 = ld4(p.pro_c + c0);
                     v[0] = pro4<PRO, MASK>(v[0], v2[0], A4.x, B4.x, C4.x, D4.x);
                     v[1] = pro4<PRO, MASK>(v[1], v2[1], A4.y, B4.y, C4.y, D4.y);
                     v[2] = pro4<PRO, MASK>(v[2], v2[2], A4.z, B4.z, C4.z, D4.z);
@@ -201,7 +210,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
         }
 
         // ------------------------------ epilogue: one thread per output channel ------------------------------
-        mbar_wait(accum_bar, 0);
+        mbar_wait(accum_bar, (uint32_t)it & 1u);
         tc_fence_after();
         const int quarter = warp & 3, cgrp = warp >> 2;
         for (int tj = 0; tj < ntile; ++tj) {
@@ -321,11 +330,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
             atomicAdd(p.stat1 + co, (double)s1);
         }
         }
+        // next tile: its operand stores reuse the staging tiles, its first MMA overwrites the accumulators just read
+        if (!PERSIST) break;
+        tc_fence_before();
+        asm volatile("bar.sync 1, %0;" ::"r"(NPROD) : "memory");
+        tile += gridDim.x; ++it;
+        } while (tile < g.total);
     } else if (warp == NPW) {
         // ------------------------------ MMA issue (one thread) ------------------------------
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(BM, BN, 0, 1);             // A (weights) K-major, B (activations) MN-major
             int s = 0, sa = 0; uint32_t ph = 0, pha = 0;
+            int tile = blockIdx.x;
+            do {
+            WF_TC_TILE_VARS(tile)
+            (void)m0; (void)col0;
             for (int kc = 0; kc < KT; ++kc) {
                 mbar_wait(full_a(sa), pha);
                 mbar_wait(full_b(s), ph);
@@ -355,11 +374,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
                 if (++sa == NSA) { sa = 0; pha ^= 1u; }
             }
             umma_commit(accum_bar);
+            tile += gridDim.x;
+            } while (PERSIST && tile < g.total);
         }
     } else {
         // ------------------------------ weight tiles: one 32 KB bulk copy per stage ------------------------------
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
+            int tile = blockIdx.x;
+            do {
+            WF_TC_TILE_VARS(tile)
+            (void)m0; (void)col0;
             for (int kc = 0; kc < KT; ++kc) {
                 mbar_wait(empty_a(s), ph ^ 1u);
                 if (g.dbg & 4) { mbar_arrive(full_a(s)); if (++s == NSA) { s = 0; ph ^= 1u; } continue; }       // no weight copies
@@ -370,8 +395,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
                 }
                 if (++s == NSA) { s = 0; ph ^= 1u; }
             }
+            tile += gridDim.x;
+            } while (PERSIST && tile < g.total);
         }
     }
+#undef WF_TC_TILE_VARS
     tc_fence_before();
     __syncthreads();
     if (warp == NPW + 1) tmem_dealloc(tmem_base, g.tmem_cols);
@@ -615,13 +643,18 @@ __global__ void tc_pack_kernel(TcPackTable tab, const float* params, float* pack
 
 constexpr int SMEM_MAX = 227 * 1024;
 
+template <int PRO, bool MASK, bool PERSIST>
+cudaError_t launch_conv_p(const ConvP& p, const TcGeom& g, dim3 grid, int smem, cudaStream_t st)
+{
+    static WfSmemOptIn optin;
+    if (cudaError_t e = wf_smem_optin(optin, pw_tc_kernel<PRO, MASK, PERSIST>, SMEM_MAX)) return e;
+    wf_launch_pdl(pw_tc_kernel<PRO, MASK, PERSIST>, dim3(grid), dim3(NTHREADS), smem, st, p, g);
+    return cudaGetLastError();
+}
 template <int PRO, bool MASK>
 cudaError_t launch_conv_t(const ConvP& p, const TcGeom& g, dim3 grid, int smem, cudaStream_t st)
 {
-    static WfSmemOptIn optin;
-    if (cudaError_t e = wf_smem_optin(optin, pw_tc_kernel<PRO, MASK>, SMEM_MAX)) return e;
-    wf_launch_pdl(pw_tc_kernel<PRO, MASK>, dim3(grid), dim3(NTHREADS), smem, st, p, g);
-    return cudaGetLastError();
+    return (int)grid.x < g.total ? launch_conv_p<PRO, MASK, true>(p, g, grid, smem, st) : launch_conv_p<PRO, MASK, false>(p, g, grid, smem, st);
 }
 
 template <int GPRO, int XPRO, bool MASK>
@@ -683,7 +716,16 @@ cudaError_t wf_launch_tc_conv(const ConvP& p, int num_sms, cudaStream_t st)
     if (g.nsa > 4) g.nsa = 4;
     if (g.nsa < g.nst) g.nsa = g.nst;
     const int smem = g.nst * b_stage + g.nsa * a_bytes + (2 * g.nst + 2 * g.nsa + 1) * 8 + 16;
-    dim3 grid((unsigned)((NC + g.bn - 1) / g.bn), (unsigned)((mt + mp - 1) / mp));
+    g.mgroups = (int)((mt + mp - 1) / mp);
+    const long long total = ((NC + g.bn - 1) / g.bn) * g.mgroups;
+    if (total >= (1LL << 31)) return cudaErrorInvalidValue;
+    g.total = (int)total;
+    // persistent only when the epilogue's staging tiles (16 warps x 4.5 KB) stay inside the activation ring: the weight copies of the
+    // next tile start while the epilogue of this one still runs.  WF_TC_PERSIST=0: one tile per CTA (measurements)
+    static const bool persist_env = [] { const char* e = std::getenv("WF_TC_PERSIST"); return !(e && e[0] == '0'); }();
+    // ... and only where a CTA would get at least four tiles (the attention projections: 15 positions x 20 480 columns)
+    const bool persist = persist_env && (long long)g.nst * b_stage >= (long long)NPW * 32 * 36 * 4 && total >= 4LL * num_sms;
+    dim3 grid((unsigned)(persist ? num_sms : total));
     const bool mask = p.pro_mode == PRO_BNSILU && p.mask != nullptr;
     switch (p.pro_mode) {
         case PRO_NONE: return launch_conv_t<PRO_NONE, false>(p, g, grid, smem, st);

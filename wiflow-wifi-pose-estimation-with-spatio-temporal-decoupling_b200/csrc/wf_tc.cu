@@ -450,31 +450,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const WgradP p
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < NPW) {
-        // producers: a warp stages 8 rows x 16 columns (512 contiguous bytes of the K-major image) per unit; a stage has
-        // (16 + bn/8) row groups x 2 column halves = up to 96 units, unit u = warp + 16 j  ->  row group u/2, half = warp & 1
-        static_assert(KC == 32 && NPW % 2 == 0, "unit mapping assumes two 16-column halves per stage");
-        constexpr int MAXG = ((BM / 8 + WG_BN_MAX / 8) * 2 + NPW - 1) / NPW;
-        const int r8 = lane & 7;
-        const int q = (warp & 1) * 4 + (lane >> 3);           // column quad of this thread inside the 32-column stage
-        const int ngroups = BM / 8 + bn / 8;
+        // producers: a unit is 4 rows x 32 columns -- one warp-level request covers 4 rows x 128 contiguous bytes (the first version
+        // staged 8 rows x 64 bytes because a no-swizzle K-major core matrix wants 8 rows per quarter warp: twice the tag look-ups
+        // per byte, and the loads are what this kernel waits for, profiles/r2_pw_wgrad_tc_ablation.txt).  The images are
+        // SWIZZLE_128B K-major: row r of a tile at r * 128 bytes, its 16-byte chunk c (4 columns) at ((c ^ (r & 7)) * 16), so the 8
+        // lanes of a quarter warp (one row, chunks 0..7) hit 8 different bank groups.  Unit u = warp + 16 j: u < 32 are G' rows.
+        static_assert(KC == 32 && BM / 4 == 2 * NPW, "a stage row is one 128-byte swizzle row; units 0, 1 of every warp are G' rows");
+        constexpr int MAXG = (BM / 4 + WG_BN_MAX / 4 + NPW - 1) / NPW;
+        const int r8 = lane >> 3;                              // row of this thread inside the unit (0..3)
+        const int q = lane & 7;                                // column quad of this thread inside the 32-column stage
+        const int ngroups = BM / 4 + (bn + 3) / 4;
         // per-unit row: element offset of the row inside its tensor, coefficients, validity
         unsigned rowoff[MAXG], moff[MAXG];
         float ca[MAXG], cb[MAXG], cc[MAXG], cd[MAXG];
         unsigned valid = 0;
 #pragma unroll
         for (int j = 0; j < MAXG; ++j) {
-            const int grp = (warp >> 1) + j * (NPW / 2);
+            const int grp = warp + j * NPW;
             rowoff[j] = 0; moff[j] = 0; ca[j] = cb[j] = cc[j] = cd[j] = 0.f;
-            if (grp < BM / 8) {
-                const int co = m0 + grp * 8 + r8;
+            if (grp < BM / 4) {
+                const int co = m0 + grp * 4 + r8;
                 if (co < p.Cout) {
                     valid |= 1u << j;
                     rowoff[j] = (unsigned)((long long)co * NC);
                     if (GPRO == PRO_BNBWD) { ca[j] = p.g_a[co]; cb[j] = p.g_b[co]; cc[j] = p.g_c[co]; cd[j] = p.g_d[co]; }
                 }
             } else if (grp < ngroups) {
-                const int ci = c0 + (grp - BM / 8) * 8 + r8;
-                if (ci < p.Cin) {
+                const int ci = c0 + (grp - BM / 4) * 4 + r8;
+                if (ci < p.Cin && (grp - BM / 4) * 4 + r8 < bn) {
                     valid |= 1u << j;
                     rowoff[j] = (unsigned)((long long)ci * p.in_sc);
                     if (MASK) moff[j] = (unsigned)((long long)ci * p.m_sc);
@@ -487,7 +490,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const WgradP p
         long long pos = 0, n = col;
         if (p.Pout > 1) { pos = col / p.N; n = col - pos * p.N; }
         long long b = n / WF_T; int t = (int)(n - b * WF_T);
-        const uint32_t soff = (uint32_t)(q * A_LBO + r8 * 16);
+        // byte offset inside a unit's 4 rows: (row & 7) = (warp & 1) * 4 + r8 for every unit of this warp (u = warp + 16 j)
+        const uint32_t soff = (uint32_t)(r8 * 128 + ((q ^ ((warp & 1) * 4 + r8)) << 4));
         const int m_st = p.m_st;
         for (int kc = 0; kc < KT; ++kc) {
             const int s = kc % WG_STAGES;
@@ -501,8 +505,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const WgradP p
             // of the chunk are issued first, as bare predicated loads with no arithmetic inside the guards, so that ptxas keeps up to
             // 2*MAXG 128-bit requests per thread in flight; the prologues run afterwards.  (With the math inside the guards every unit
             // waited for its own loads in turn: long-scoreboard stalls were 11.6 per issued instruction and the tensor pipe 9 % busy.)
-            constexpr int GUNITS = (BM / 8) / (NPW / 2);
-            static_assert((BM / 8) % (NPW / 2) == 0, "G' row groups must fill whole units");
+            constexpr int GUNITS = (BM / 4) / NPW;
             float4 v[MAXG], w[MAXG];
 #pragma unroll
             for (int j = 0; j < MAXG; ++j) {
@@ -532,9 +535,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const WgradP p
             uint8_t* bh = ah + 2 * A_HALF;
 #pragma unroll
             for (int j = 0; j < MAXG; ++j) {
-                const int grp = (warp >> 1) + j * (NPW / 2);
-                if (grp < BM / 8) split_store(ah, ah + A_HALF, (uint32_t)(grp * A_SBO) + soff, v[j]);
-                else if (grp < ngroups) split_store(bh, bh + B_HALF, (uint32_t)((grp - BM / 8) * A_SBO) + soff, v[j]);
+                const int grp = warp + j * NPW;
+                if (grp < BM / 4) split_store(ah, ah + A_HALF, (uint32_t)(grp * 512) + soff, v[j]);
+                else if (grp < ngroups) split_store(bh, bh + B_HALF, (uint32_t)((grp - BM / 4) * 512) + soff, v[j]);
             }
             fence_proxy_async_smem();
             __syncwarp();
@@ -593,8 +596,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_wgrad_tc_kernel(const WgradP p
                 const uint32_t b_hi = a_hi + 2 * A_HALF, b_lo = b_hi + B_HALF;
 #pragma unroll
                 for (int kk = 0; kk < KC / 8; ++kk) {
-                    const uint64_t dah = umma_desc(a_hi + kk * 2 * A_LBO, A_LBO, A_SBO), dal = umma_desc(a_lo + kk * 2 * A_LBO, A_LBO, A_SBO);
-                    const uint64_t dbh = umma_desc(b_hi + kk * 2 * A_LBO, A_LBO, A_SBO), dbl = umma_desc(b_lo + kk * 2 * A_LBO, A_LBO, A_SBO);
+                    // SWIZZLE_128B K-major: 8-row groups 1024 bytes apart, a K step of 8 columns = 32 bytes inside the 128-byte row
+                    const uint64_t dah = umma_desc_l(a_hi + kk * 32, 16, 1024, 2), dal = umma_desc_l(a_lo + kk * 32, 16, 1024, 2);
+                    const uint64_t dbh = umma_desc_l(b_hi + kk * 32, 16, 1024, 2), dbl = umma_desc_l(b_lo + kk * 32, 16, 1024, 2);
                     const uint32_t accf = (kc | kk) != 0 ? 1u : 0u;
                     umma_tf32(tmem_cor, dal, dbh, idesc, accf);
                     umma_tf32(tmem_cor, dah, dbl, idesc, 1u);

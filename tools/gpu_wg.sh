@@ -1,4 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 tests/native/slab_selftest 4 > gpurun_out/r2_selftest.txt 2>&1; tail -2 gpurun_out/r2_selftest.txt
-timeout 600 tests/native/slab_selftest bench 2>&1 | grep -v timeline | tail -12
+timeout 300 tests/native/slab_selftest wgrad 2>&1 | tail -12
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+bash tools/gpu_quick.sh

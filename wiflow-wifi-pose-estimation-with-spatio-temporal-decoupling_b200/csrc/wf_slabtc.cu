@@ -932,11 +932,27 @@ __global__ void __launch_bounds__(NTHR, 1) slab_wgrad_kernel(const __grid_consta
         int blk = (int)(u0 / g.ncol32), c32 = (int)(u0 - (long long)blk * g.ncol32);
         for (long long u = u0; u < u1; ++u) {
             const int n0 = c32 * 32, p0 = blk * g.PBk, q0 = p0 * g.s + g.dpmin;
+            // Dropout2d values of this thread's X' chunks (one per (window, channel); the A rows are at most 256, i.e. at most four
+            // chunks per thread): requested BEFORE the wait for the TMA tile, all at once -- inside the loop each was a dependent
+            // global load in front of the chunk's transform (3.4 M two-sector requests per step in the ncu request survey).
+            float mkv[4] = {1.f, 1.f, 1.f, 1.f};
+            if (MASK) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int id = tid + j * NWORK;
+                    if (id < a_chunks) {
+                        const int row = id >> 3, quad = (id & 7) ^ (row & 7);
+                        const int n = n0 + quad * 4, c = row & (p.Cin - 1);
+                        if (n < p.N) mkv[j] = __ldg(p.mask + (long long)(n / WF_T) * p.m_sb + (long long)c * p.m_sc);
+                    }
+                }
+            }
             warp_wait(raw_full(st), ph, lane);
             const uint32_t a_hi = smem0 + (uint32_t)(st * stage_bytes), a_lo = a_hi + (uint32_t)g.a_half;
             const uint32_t b_hi = a_lo + (uint32_t)g.a_half, b_lo = b_hi + (uint32_t)g.b_half;
             // (two chunks per trip with their loads batched was tried: 5-10 % slower at the 96-register budget)
-            for (int id = tid; id < tot_chunks; id += NWORK) {
+            int jj = 0;
+            for (int id = tid; id < tot_chunks; id += NWORK, ++jj) {
                 const bool isA = id < a_chunks;
                 const int cid = isA ? id : id - a_chunks;
                 const int row = cid >> 3, quad = (cid & 7) ^ (row & 7);
@@ -947,8 +963,7 @@ __global__ void __launch_bounds__(NTHR, 1) slab_wgrad_kernel(const __grid_consta
                     const int pos = row >> cin_sh, c = row & (p.Cin - 1);
                     const float4 x = lds4(a_hi + off);
                     const bool ok = n < p.N && q0 + pos >= 0 && q0 + pos < g.Pin_eff;
-                    float mk = 1.f;
-                    if (MASK && ok) mk = __ldg(p.mask + (long long)(n / WF_T) * p.m_sb + (long long)c * p.m_sc);
+                    const float mk = jj == 0 ? mkv[0] : jj == 1 ? mkv[1] : jj == 2 ? mkv[2] : mkv[3];
                     const float4 co = make_float4(tab[c], tab[64 + c], 0.f, tab[128 + c]);
                     y.x = ok ? pro1<XPRO>(x.x, 0.f, mk, co) : 0.f; y.y = ok ? pro1<XPRO>(x.y, 0.f, mk, co) : 0.f;
                     y.z = ok ? pro1<XPRO>(x.z, 0.f, mk, co) : 0.f; y.w = ok ? pro1<XPRO>(x.w, 0.f, mk, co) : 0.f;

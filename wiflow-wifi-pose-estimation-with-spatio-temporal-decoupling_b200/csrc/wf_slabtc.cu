@@ -952,7 +952,7 @@ __global__ void __launch_bounds__(NTHR, 1) slab_wgrad_kernel(const __grid_consta
             const uint32_t b_hi = a_lo + (uint32_t)g.a_half, b_lo = b_hi + (uint32_t)g.b_half;
             // (two chunks per trip with their loads batched was tried: 5-10 % slower at the 96-register budget)
             int jj = 0;
-            for (int id = tid; id < tot_chunks; id += NWORK, ++jj) {
+            for (int id = tid; id < ((g.dbg & 1) ? 0 : tot_chunks); id += NWORK, ++jj) {      // (dbg 1: measurement without the transform)
                 const bool isA = id < a_chunks;
                 const int cid = isA ? id : id - a_chunks;
                 const int row = cid >> 3, quad = (cid & 7) ^ (row & 7);
@@ -993,7 +993,7 @@ __global__ void __launch_bounds__(NTHR, 1) slab_wgrad_kernel(const __grid_consta
         const int nw = p.Cout * p.Cin * p.ntaps;
         for (int i = tid; i < nw; i += NWORK) red[i] = 0.f;
         asm volatile("bar.sync 1, %0;" ::"r"(NWORK) : "memory");
-        if (u1 > u0) {
+        if (u1 > u0 && !(g.dbg & 4)) {
             const int lq = warp & 3, part = warp >> 2;
             for (int mt = 0; mt < g.MT; ++mt) {
                 const int row = mt * 128 + lq * 32 + lane;
@@ -1018,8 +1018,16 @@ __global__ void __launch_bounds__(NTHR, 1) slab_wgrad_kernel(const __grid_consta
             }
         }
         asm volatile("bar.sync 1, %0;" ::"r"(NWORK) : "memory");
-        if (u1 > u0)
-            for (int i = tid; i < nw; i += NWORK) atomicAdd(p.dw + i, red[i]);
+        if (u1 > u0 && !(g.dbg & 8)) {
+            // one reduction per weight and CTA into the gradient; 128-bit reductions (sm_90+) where the tensor's offset in the flat
+            // gradient allows it: 148 CTAs x 12 288 weights of a 64 -> 64 layer are 1.8 M scalar reductions per launch otherwise
+            if (((reinterpret_cast<uintptr_t>(p.dw) & 15) == 0) && (nw & 3) == 0) {
+                for (int i = tid * 4; i < nw; i += NWORK * 4)
+                    atomicAdd(reinterpret_cast<float4*>(p.dw + i), *reinterpret_cast<const float4*>(red + i));
+            } else {
+                for (int i = tid; i < nw; i += NWORK) atomicAdd(p.dw + i, red[i]);
+            }
+        }
     } else if (warp == NWW) {
         // =============================== TMA producer ===============================
         if (lane == 0) {
@@ -1030,12 +1038,15 @@ __global__ void __launch_bounds__(NTHR, 1) slab_wgrad_kernel(const __grid_consta
             for (long long u = u0; u < u1; ++u) {
                 const int n0 = c32 * 32, p0 = blk * g.PBk, q0 = p0 * g.s + g.dpmin;
                 mbar_wait(slab_empty(st), ph ^ 1u);
-                mbar_arrive_expect_tx(raw_full(st), tx);
                 const uint32_t a_hi = smem0 + (uint32_t)(st * stage_bytes);
                 const uint32_t b_hi = a_hi + 2u * (uint32_t)g.a_half, b_lo = b_hi + (uint32_t)g.b_half;
-                tma_load_3d(a_hi, &tmX, n0, 0, q0, raw_full(st));
-                tma_load_3d(b_hi, &tmG, n0, 0, p0, raw_full(st));
-                tma_load_3d(b_lo, &tmR, n0, 0, p0, raw_full(st));
+                if (g.dbg & 16) mbar_arrive(raw_full(st));                 // (measurement without the TMA loads)
+                else {
+                    mbar_arrive_expect_tx(raw_full(st), tx);
+                    tma_load_3d(a_hi, &tmX, n0, 0, q0, raw_full(st));
+                    tma_load_3d(b_hi, &tmG, n0, 0, p0, raw_full(st));
+                    tma_load_3d(b_lo, &tmR, n0, 0, p0, raw_full(st));
+                }
                 if (++st == NS) { st = 0; ph ^= 1u; }
                 if (++c32 == g.ncol32) { c32 = 0; ++blk; }
             }
@@ -1057,7 +1068,7 @@ __global__ void __launch_bounds__(NTHR, 1) slab_wgrad_kernel(const __grid_consta
             const uint32_t b_hi16 = a_lo16 + ((uint32_t)g.a_half >> 4);
             for (int ks = 0; ks < 4; ++ks)
                 for (int mt = 0; mt < g.MT; ++mt, ++item) {
-                    if (item % NI != me) continue;
+                    if (item % NI != me || (g.dbg & 2)) continue;            // (dbg 2: measurement without the MMAs)
                     const uint32_t ao = (uint32_t)(mt * 128 * 128 + ks * 32) >> 4, bo = (uint32_t)(ks * 32) >> 4;    // 32 B per K step inside the 128 B row
                     const uint32_t d = tmem_base + (uint32_t)(mt * 2 * g.NBr);
                     umma_tf32_pred(d, mk_desc(hi32, (a_hi16 + ao) | lbo), mk_desc(hi32, (b_hi16 + bo) | lbo), idesc1, lead);

@@ -184,3 +184,32 @@ def test_empty_batch_follows_the_reference():
         m(x)
     blk = wf.AsymmetricConvBlock(8, 16).cuda().eval()
     assert tuple(blk(torch.zeros(0, 8, 20, 240, device='cuda')).shape) == (0, 16, 20, 120)
+
+
+def test_same_process_second_device():
+    """the shared-memory opt-in (cudaFuncSetAttribute) and the SM-count cache are per device -- a model moved to cuda:1 after
+    cuda:0 was used must run (train-mode forward + backward + eval forward) and agree with device 0"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    import wiflow_b200 as wf
+    torch.manual_seed(0)
+    m0 = wf.WiFlowPoseModel(dropout=0.0).cuda(0)
+    for m in m0.modules():
+        if isinstance(m, torch.nn.Dropout2d):
+            m.p = 0.0
+    m1 = copy.deepcopy(m0).cuda(1)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(16, 540, 20, generator=g)
+    outs, grads = [], []
+    for dev, m in ((0, m0), (1, m1)):
+        with torch.cuda.device(dev):
+            m.train()
+            y = m(x.cuda(dev))
+            y.square().mean().backward()
+            torch.cuda.synchronize(dev)
+            grads.append(torch.cat([p.grad.flatten().cpu() for p in m.parameters()]))
+            m.eval()
+            with torch.no_grad():
+                outs.append(m(x.cuda(dev)).cpu())
+    assert rel_err(outs[1], outs[0]) < 1e-6
+    assert rel_err(grads[1], grads[0]) < 1e-4

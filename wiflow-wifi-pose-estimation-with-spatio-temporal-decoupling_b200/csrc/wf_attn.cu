@@ -56,15 +56,20 @@ __global__ void __launch_bounds__(RT * GH * L, attn_min_blocks(RT * GH * L, MODE
     // Every global load of the tile is issued before the first transform (the loops are fully unrolled and the guards hold nothing but
     // the load), so a thread has up to NIT + 2*GIT 128-bit requests in flight instead of one load -> use -> store chain per item.
     constexpr int Q = L / 4;                                        // width axis: column quads per row
-    constexpr int ITEMS = WIDTH ? 3 * GC * RT * Q : 3 * GC * LP;
-    constexpr int GITEMS = WIDTH ? GC * RT * Q : GC * LP;
+    constexpr int H = WIDTH ? 1 : RT / 4;                           // height axis: column quads (4 consecutive n) per tile
+    constexpr int ITEMS = WIDTH ? 3 * GC * RT * Q : 3 * GC * LP * H;
+    constexpr int GITEMS = WIDTH ? GC * RT * Q : GC * LP * H;
     constexpr int NIT = (ITEMS + NT - 1) / NT, GIT = MODE >= ATT_BWD_STATS ? (GITEMS + NT - 1) / NT : 0;
-    static_assert(WIDTH || RT == 4, "height-axis tiles are 4 consecutive n wide");
+    // height axis: a tile row set is RT = 4 H consecutive n; with H = 2 the two quads of a (channel, slot) are one whole 32-byte sector
+    // (with H = 1 every global access of these kernels is a 16-byte piece of its own cache line: 7.5 tag look-ups per request and half
+    // of every sector unused, profiles/r2_l1_request_survey.txt)
+    static_assert(WIDTH || RT % 4 == 0, "height-axis tiles are whole quads of n wide");
     float4 tv[NIT], gd[GIT > 0 ? GIT : 1], gw[GIT > 0 ? GIT : 1];
     // item -> (tile channel, row / slot, quad) and its global offset without the channel term; valid = inside the tensor
     auto t_item = [&](int idx, int& c, int& r, int& s, long long& off) -> bool {
         if (WIDTH) { const int q = idx % Q; r = (idx / Q) % RT; c = idx / (Q * RT); s = q * 4; off = row_base(r) + s; return row0 + r < nrows; }
-        s = idx % LP; c = idx / LP; r = 0; off = (long long)s * N + row0; return s < L && row0 < nrows;
+        const int h = idx % H; s = (idx / H) % LP; c = idx / (H * LP); r = 4 * h; off = (long long)s * N + row0 + 4 * h;
+        return s < L && row0 + 4 * h < nrows;
     };
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
@@ -95,7 +100,7 @@ __global__ void __launch_bounds__(RT * GH * L, attn_min_blocks(RT * GH * L, MODE
                 v.x = fmaf(a, v.x - mu, b); v.y = fmaf(a, v.y - mu, b); v.z = fmaf(a, v.z - mu, b); v.w = fmaf(a, v.w - mu, b);
             }
             if (WIDTH) st4(&T[tix(c, r, s)], v);
-            else { T[tix(c, 0, s)] = v.x; T[tix(c, 1, s)] = v.y; T[tix(c, 2, s)] = v.z; T[tix(c, 3, s)] = v.w; }
+            else { T[tix(c, r, s)] = v.x; T[tix(c, r + 1, s)] = v.y; T[tix(c, r + 2, s)] = v.z; T[tix(c, r + 3, s)] = v.w; }
         }
     }
 #pragma unroll
@@ -112,7 +117,7 @@ __global__ void __launch_bounds__(RT * GH * L, attn_min_blocks(RT * GH * L, MODE
                 v.z = fmaf(a, d.z, fmaf(b, w.z - mu, e)); v.w = fmaf(a, d.w, fmaf(b, w.w - mu, e));
             }
             if (WIDTH) st4(&G[tix(c, r, s)], v);
-            else { G[tix(c, 0, s)] = v.x; G[tix(c, 1, s)] = v.y; G[tix(c, 2, s)] = v.z; G[tix(c, 3, s)] = v.w; }
+            else { G[tix(c, r, s)] = v.x; G[tix(c, r + 1, s)] = v.y; G[tix(c, r + 2, s)] = v.z; G[tix(c, r + 3, s)] = v.w; }
         }
     }
     __syncthreads();
@@ -184,11 +189,11 @@ __global__ void __launch_bounds__(RT * GH * L, attn_min_blocks(RT * GH * L, MODE
                 if (row0 + rr < nrows) st4(p.sv_raw + (g0 * 8 + c) * cstride + row_base(rr) + qq * 4, ld4(&T[tix(c, rr, qq * 4)]));
             }
         } else {
-            for (int idx = tid; idx < GC * L; idx += NT) {
-                const int s = idx % L, c = idx / L;
-                if (row0 < nrows)
-                    st4(p.sv_raw + (g0 * 8 + c) * cstride + (long long)s * N + row0,
-                        make_float4(T[tix(c, 0, s)], T[tix(c, 1, s)], T[tix(c, 2, s)], T[tix(c, 3, s)]));
+            for (int idx = tid; idx < GC * L * H; idx += NT) {
+                const int h = idx % H, s = (idx / H) % L, c = idx / (H * L), r4 = 4 * h;
+                if (row0 + r4 < nrows)
+                    st4(p.sv_raw + (g0 * 8 + c) * cstride + (long long)s * N + row0 + r4,
+                        make_float4(T[tix(c, r4, s)], T[tix(c, r4 + 1, s)], T[tix(c, r4 + 2, s)], T[tix(c, r4 + 3, s)]));
             }
         }
         if (p.sv_s0 && tid < GC) {
@@ -300,11 +305,11 @@ __global__ void __launch_bounds__(RT * GH * L, attn_min_blocks(RT * GH * L, MODE
                 if (row0 + rr < nrows) st4(p.dqkv + qkv_chan(c) * cstride + row_base(rr) + qq * 4, ld4(&T[tix(c, rr, qq * 4)]));
             }
         } else {
-            for (int idx = tid; idx < 3 * GC * L; idx += NT) {
-                const int s = idx % L, c = idx / L;
-                if (row0 < nrows)
-                    st4(p.dqkv + qkv_chan(c) * cstride + (long long)s * N + row0,
-                        make_float4(T[tix(c, 0, s)], T[tix(c, 1, s)], T[tix(c, 2, s)], T[tix(c, 3, s)]));
+            for (int idx = tid; idx < 3 * GC * L * H; idx += NT) {
+                const int h = idx % H, s = (idx / H) % L, c = idx / (H * L), r4 = 4 * h;
+                if (row0 + r4 < nrows)
+                    st4(p.dqkv + qkv_chan(c) * cstride + (long long)s * N + row0 + r4,
+                        make_float4(T[tix(c, r4, s)], T[tix(c, r4 + 1, s)], T[tix(c, r4 + 2, s)], T[tix(c, r4 + 3, s)]));
             }
         }
         return;
@@ -381,6 +386,18 @@ cudaError_t launch_attn_mode(const AttnP& p, cudaStream_t st)
         if (w == 2) return launch_attn<20, 20, 1, 4, true, MODE>(p, st);
         if (w == 1) return launch_attn<20, 20, 1, 8, true, MODE>(p, st);
         return launch_attn<20, 20, 2, 8, true, MODE>(p, st);
+    }
+    // default: eight-column tiles with half as many groups per CTA (same thread counts and shared memory as the four-column ones:
+    // attention 1.80 -> 1.61 ms per step); WF_ATTN_H8=0 the four-column tiles, 2 sixteen-column tiles
+    static const int h8 = [] { const char* e = std::getenv("WF_ATTN_H8"); return e ? std::atoi(e) : 1; }();
+    if (h8 == 2) {                 // sixteen-column tiles (64 contiguous bytes per channel and slot)
+        if (h >= 1) return launch_attn<15, 16, 16, 1, false, MODE>(p, st);
+        return launch_attn<15, 16, 16, 2, false, MODE>(p, st);
+    }
+    if (h8 == 1) {
+        if (h == 2) return launch_attn<15, 16, 8, 1, false, MODE>(p, st);
+        if (h == 1) return launch_attn<15, 16, 8, 2, false, MODE>(p, st);
+        return launch_attn<15, 16, 8, 4, false, MODE>(p, st);
     }
     if (h == 2) return launch_attn<15, 16, 4, 2, false, MODE>(p, st);
     if (h == 1) return launch_attn<15, 16, 4, 4, false, MODE>(p, st);

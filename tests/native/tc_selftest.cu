@@ -114,7 +114,7 @@ static int run_perf(int M, int K, int N, int pro)
     TcPackTable tab{}; tab.n = 1; tab.e[0] = TcPackEntry{0, M, K, 0, pf};
     CK(wf_launch_tc_pack(tab, dW, dP, 0));
     ConvP p{};
-    p.in = dX; p.in_sc = N; p.in_sp = 0; p.in_sb = WF_T; p.pro_mode = pro; p.pro_a = dA; p.pro_b = dA + K; p.pro_c = dA + 2 * K; p.pro_d = dA + 3 * K;
+    p.in = dX; p.in2 = dX; p.in_sc = N; p.in_sp = 0; p.in_sb = WF_T; p.pro_mode = pro; p.pro_a = dA; p.pro_b = dA + K; p.pro_c = dA + 2 * K; p.pro_d = dA + 3 * K;
     p.Cin = K; p.Cout = M; p.groups = 1; p.Pin = 1; p.Pout = 1; p.N = N; p.ntaps = 1; p.pmul = 1; p.pdiv = 1;
     p.out = dD; p.out_sc = N; p.out_sp = 0; p.out_sb = WF_T; p.epi_mode = EPI_STATS; p.stat0 = dS; p.stat1 = dS + M;
     p.wtc = dP; p.tc_kt = (K + TC_KC - 1) / TC_KC;
@@ -146,6 +146,7 @@ int main(int argc, char** argv)
         run_perf(540, 540, 20480, PRO_BNSILU);
         run_perf(240, 340, 20480, PRO_BNSILU);
         run_perf(192, 64, 15 * 20480, PRO_AFFINE);
+        run_perf(64, 192, 15 * 20480, PRO_BNBWD);      // backward-data of the attention qkv projection
         return 0;
     }
     const int verbose = argc > 1 ? atoi(argv[1]) : 12;

@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pw_tc_kernel(const ConvP p, const
             }
             __syncwarp();
         }
-        if (mv && p.epi_mode != EPI_STORE && p.stat0 != nullptr) {
+        if (mv && p.epi_mode != EPI_STORE && p.stat0 != nullptr && !(g.dbg & 128)) {
             atomicAdd(p.stat0 + co, (double)s0);
             atomicAdd(p.stat1 + co, (double)s1);
         }
@@ -704,7 +704,7 @@ cudaError_t wf_launch_tc_conv(const ConvP& p, int num_sms, cudaStream_t st)
     static const int bn_env = [] { const char* e = std::getenv("WF_TC_BN"); return e ? std::atoi(e) : 0; }();       // experiments only
     if (bn_env >= 64 && bn_env <= bn_max && bn_env % 32 == 0) best_bn = bn_env;
     TcGeom g{};
-    static const int dbg_env = [] { const char* e = std::getenv("WF_TC_DBG"); return e ? std::atoi(e) : 0; }();       // measurements: 1 no activation loads, 2 no MMAs
+    static const int dbg_env = [] { const char* e = std::getenv("WF_TC_DBG"); return e ? std::atoi(e) : 0; }();       // measurements: 1 no activation loads, 2 no MMAs, 4 no weight copies, 8 no operand stores, 16 main product only, 32 no epilogue memory traffic, 64 no epilogue, 128 no statistics reductions
     g.dbg = dbg_env;
     g.mp = mp; g.mtiles = (int)mt;
     g.bn = best_bn;
